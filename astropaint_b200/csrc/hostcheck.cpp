@@ -1,0 +1,131 @@
+// TEST-ONLY host build of the device arithmetic headers (g++ -ffp-contract=off).
+//
+// libap_hostcheck.so lets the CPU test-suite (-m "not gpu") validate healpix.cuh, geom.cuh,
+// qagi.cuh, profiles.cuh and spline.cuh against the oracle and scipy in a container with no
+// GPU.  It is never loaded by the product path (astropaint_b200/_capi.py loads only
+// libastropaint_b200.so and raises if it is missing).
+#include <cstdint>
+#include <cmath>
+
+#include "common.cuh"
+#include "healpix.cuh"
+#include "geom.cuh"
+#include "profiles.cuh"
+#include "spline.cuh"
+
+using namespace ap;
+
+template <int P>
+static void eval_R(const double* p, int64_t n, const double* R, double* out) {
+  double ctx[kCtx];
+  profile_setup<P>(p, ctx);
+  for (int64_t i = 0; i < n; ++i) out[i] = profile_eval_R<P>(ctx, R[i]);
+}
+
+extern "C" {
+
+int64_t hc_query_disc(int64_t nside, double x, double y, double z, double radius, int64_t* out, int64_t cap) {
+  Hpx h = make_hpx(nside);
+  DiscHeader d = disc_header(h, x, y, z, radius);
+  int64_t n = 0;
+  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+    RingSpan s = ring_span(h, d, iz);
+    for (int32_t j = 0; j < s.len; ++j) {
+      if (out && n < cap) out[n] = span_pixel_sorted(s, j);
+      ++n;
+    }
+  }
+  return n;
+}
+
+// R (and R_vec) of every disc pixel, in ascending pixel order; also the span-based R range
+int64_t hc_disc_R(int64_t nside, double x, double y, double z, double radius, double theta, double phi, double D_a,
+                  double* R, double* Rvec, int64_t cap, double* rmin, double* rmax) {
+  Hpx h = make_hpx(nside);
+  DiscHeader d = disc_header(h, x, y, z, radius);
+  HaloCenter c = make_center(theta, phi, D_a, true);
+  int64_t n = 0;
+  double smin = INFINITY, smax = -INFINITY;
+  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+    RingSpan s = ring_span(h, d, iz);
+    if (s.len <= 0) continue;
+    RingGeom g = ring_geom(h, iz, s, c);
+    double a, b;
+    span_sep_range(g, s, c.phi, a, b);
+    smin = fmin(smin, a);
+    smax = fmax(smax, b);
+    for (int32_t j = 0; j < s.len; ++j) {
+      int64_t p = span_pixel_sorted(s, j);
+      int32_t ip = (int32_t)(p - s.startpix);
+      if (n < cap) {
+        if (R) R[n] = c.D_a * pixel_sep(g, ip, c.phi);
+        if (Rvec) pixel_chord(g, ip, c, Rvec[3 * n], Rvec[3 * n + 1], Rvec[3 * n + 2]);
+      }
+      ++n;
+    }
+  }
+  if (rmin) *rmin = D_a * smin;
+  if (rmax) *rmax = D_a * smax;
+  return n;
+}
+
+void hc_vec2pix(int64_t nside, int64_t n, const double* x, const double* y, const double* z, int64_t* out) {
+  Hpx h = make_hpx(nside);
+  for (int64_t i = 0; i < n; ++i) out[i] = vec2pix_ring(h, x[i], y[i], z[i]);
+}
+
+void hc_qagi_b16(double R, double R_200c, double M_200c, double redshift, double* result, double* abserr, int* neval,
+                 int* ier) {
+  double ctx[kCtx];
+  b16_setup(R_200c, M_200c, redshift, ctx);
+  QagiResult q;
+  b16_tau_2D(ctx, R, &q);
+  *result = q.result;
+  *abserr = q.abserr;
+  *neval = q.neval;
+  *ier = q.ier;
+}
+
+double hc_b16_tau_3D(double r, double R_200c, double M_200c, double redshift) {
+  double ctx[kCtx];
+  b16_setup(R_200c, M_200c, redshift, ctx);
+  B16Integrand f;
+  f.inv_R200xc = ctx[0]; f.alpha = ctx[1]; f.expo = ctx[2]; f.K = ctx[3]; f.R = 0.0;
+  return f(r) / 2.0;  // with R = 0 the LOS weight 2r/sqrt(r^2) is 2
+}
+
+double hc_critical_density(double z) { return critical_density(z); }
+
+int hc_profile_R(int profile, const double* p, int64_t n, const double* R, double* out) {
+  switch (profile) {
+    case P_CONSTANT: eval_R<P_CONSTANT>(p, n, R, out); return 0;
+    case P_LINEAR: eval_R<P_LINEAR>(p, n, R, out); return 0;
+    case P_SOLID_SPHERE: eval_R<P_SOLID_SPHERE>(p, n, R, out); return 0;
+    case P_GAUSSIAN: eval_R<P_GAUSSIAN>(p, n, R, out); return 0;
+    case P_NFW_RHO2D: eval_R<P_NFW_RHO2D>(p, n, R, out); return 0;
+    case P_NFW_TAU2D: eval_R<P_NFW_TAU2D>(p, n, R, out); return 0;
+    case P_NFW_KSZ: eval_R<P_NFW_KSZ>(p, n, R, out); return 0;
+    case P_NFW_DEFLECTION: eval_R<P_NFW_DEFLECTION>(p, n, R, out); return 0;
+    case P_B16_TAU2D: eval_R<P_B16_TAU2D>(p, n, R, out); return 0;
+  }
+  return 1;
+}
+
+int hc_profile_vec(int profile, const double* p, int64_t n, const double* Rvec, double* out) {
+  if (profile != P_NFW_BG) return 1;
+  double ctx[kCtx];
+  profile_setup<P_NFW_BG>(p, ctx);
+  for (int64_t i = 0; i < n; ++i)
+    out[i] = profile_eval_vec<P_NFW_BG>(ctx, Rvec[3 * i], Rvec[3 * i + 1], Rvec[3 * i + 2]);
+  return 0;
+}
+
+int hc_spline(int n, const double* x, const double* y, int64_t m, const double* X, double* out) {
+  if (n < 4 || n > kMaxNodes) return 1;
+  double c[(kMaxNodes - 1) * 4];
+  spline_build_nak(n, x, y, c);
+  for (int64_t i = 0; i < m; ++i) out[i] = spline_eval(n, x, c, X[i]);
+  return 0;
+}
+
+}  // extern "C"

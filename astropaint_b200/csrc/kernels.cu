@@ -1,0 +1,764 @@
+// astropaint_b200 — sm_100a kernels and the C ABI (include/astropaint_b200.h).
+//
+// Kernel map (DESIGN.md has the roofline of each):
+//   disc_count_kernel    K1  per-halo ring walk: pixel count, ring count, R range
+//   disc_pixels_kernel   K1b flat (halo, pixel) list (+R, +R_vec) for parity and Python templates
+//   paint_kernel<P>      K3  fused disc query -> pixel geometry -> template -> fp64 RED scatter
+//   table_nodes / b16_tau_nodes / spline_build   K4  @interpolate tables on device
+//   paint_b16_small      the len(R) < n_samples bypass of @interpolate
+//   cutout_kernel / stack_kernel   K5  CartesianProj cutouts and their stack
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/astropaint_b200.h"
+#include "common.cuh"
+#include "healpix.cuh"
+#include "geom.cuh"
+#include "profiles.cuh"
+#include "spline.cuh"
+
+using namespace ap;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+#define AP_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+  } while (0)
+#define AP_LAUNCH_CHECK()                                                               \
+  do {                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess) return fail(std::string("launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* ap_last_error(void) { return g_err.c_str(); }
+extern "C" int ap_version(void) { return 100; }
+
+struct HalosDev {
+  int64_t n;
+  const double *x, *y, *z, *radius, *theta, *phi, *D_a;
+};
+static HalosDev to_dev(const ap_halos* h) {
+  HalosDev d;
+  d.n = h->n;
+  d.x = h->d_x; d.y = h->d_y; d.z = h->d_z; d.radius = h->d_radius;
+  d.theta = h->d_theta; d.phi = h->d_phi; d.D_a = h->d_D_a;
+  return d;
+}
+
+static int check_halos(const ap_halos* h, bool need_center) {
+  if (!h) return fail("halos == NULL");
+  if (h->n < 0) return fail("halos.n < 0");
+  if (h->n > 0 && (!h->d_x || !h->d_y || !h->d_z || !h->d_radius)) return fail("halos: x/y/z/radius NULL");
+  if (need_center && h->n > 0 && (!h->d_theta || !h->d_phi || !h->d_D_a)) return fail("halos: theta/phi/D_a NULL");
+  return 0;
+}
+static int check_nside(int64_t nside) {
+  if (nside < 1 || nside > (int64_t(1) << 29)) return fail("nside out of range");
+  // ring pixel counts and ring numbers are held in int32 inside the kernels
+  if (nside > 8192 * 32) return fail("nside > 262144 not supported by the int32 ring arithmetic");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: disc count (+ R range)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) disc_count_kernel(Hpx hpx, HalosDev H, int64_t* n_pix, int32_t* n_rings,
+                                                         double* rmin, double* rmax) {
+  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H.n) return;
+  DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+  bool want_r = (rmin != nullptr);
+  HaloCenter c;
+  if (want_r) c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
+  int64_t total = 0;
+  double smin = INFINITY, smax = -INFINITY;
+  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+    RingSpan s = ring_span(hpx, d, iz);
+    if (s.len <= 0) continue;
+    total += s.len;
+    if (want_r) {
+      RingGeom g = ring_geom(hpx, iz, s, c);
+      double a, b;
+      span_sep_range(g, s, c.phi, a, b);
+      smin = fmin(smin, a);
+      smax = fmax(smax, b);
+    }
+  }
+  n_pix[h] = total;
+  if (n_rings) n_rings[h] = (int32_t)disc_n_rings(d);
+  if (want_r) {
+    rmin[h] = (total > 0) ? c.D_a * smin : INFINITY;
+    rmax[h] = (total > 0) ? c.D_a * smax : -INFINITY;
+  }
+}
+
+extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
+                             int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream) {
+  if (check_nside(nside)) return 1;
+  bool want_r = d_rmin || d_rmax;
+  if (check_halos(halos, want_r)) return 1;
+  if (inclusive) return fail("inclusive=True disc query is not implemented");
+  if (want_r && (!d_rmin || !d_rmax)) return fail("d_rmin and d_rmax must both be given");
+  if (!d_n_pix) return fail("d_n_pix == NULL");
+  if (halos->n == 0) return 0;
+  int threads = 128;
+  int64_t blocks = (halos->n + threads - 1) / threads;
+  disc_count_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), d_n_pix,
+                                                                            d_n_rings, d_rmin, d_rmax);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b: flat pixel list (+R, +R_vec); one warp per halo
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) disc_pixels_kernel(Hpx hpx, HalosDev H, const int64_t* pix_off, int64_t* pix,
+                                                          double* R, double* Rvec) {
+  int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (h >= H.n) return;
+  DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+  bool want = (R != nullptr) || (Rvec != nullptr);
+  HaloCenter c;
+  if (want) c = make_center(H.theta[h], H.phi[h], H.D_a[h], Rvec != nullptr);
+  int64_t run = pix_off[h];
+  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+    RingSpan s = ring_span(hpx, d, iz);
+    if (s.len <= 0) continue;
+    RingGeom g;
+    if (want) g = ring_geom(hpx, iz, s, c);
+    for (int32_t j = lane; j < s.len; j += 32) {
+      int64_t p = span_pixel_sorted(s, j);
+      int64_t o = run + j;
+      pix[o] = p;
+      if (want) {
+        int32_t ip = (int32_t)(p - s.startpix);
+        if (R) R[o] = c.D_a * pixel_sep(g, ip, c.phi);
+        if (Rvec) {
+          double rx, ry, rz;
+          pixel_chord(g, ip, c, rx, ry, rz);
+          Rvec[3 * o + 0] = rx;
+          Rvec[3 * o + 1] = ry;
+          Rvec[3 * o + 2] = rz;
+        }
+      }
+    }
+    run += s.len;
+  }
+}
+
+extern "C" int ap_disc_pixels(int64_t nside, const ap_halos* halos, const int64_t* d_pix_off, int64_t* d_pix,
+                              double* d_R, double* d_R_vec, void* stream) {
+  if (check_nside(nside)) return 1;
+  if (check_halos(halos, d_R || d_R_vec)) return 1;
+  if (halos->n == 0) return 0;
+  if (!d_pix_off || !d_pix) return fail("d_pix_off / d_pix NULL");
+  int threads = 256;
+  int64_t blocks = (halos->n * 32 + threads - 1) / threads;
+  disc_pixels_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), d_pix_off,
+                                                                             d_pix, d_R, d_R_vec);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// scatter-add of a flat work list
+// ------------------------------------------------------------------------------------------
+__global__ void scatter_add_kernel(int64_t n, const int64_t* pix, const double* val, double* map) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) atomicAdd(&map[pix[i]], val[i]);
+}
+
+extern "C" int ap_scatter_add(int64_t n, const int64_t* d_pix, const double* d_val, double* d_map, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n == 0) return 0;
+  if (!d_pix || !d_val || !d_map) return fail("scatter_add: NULL pointer");
+  int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  scatter_add_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(n, d_pix, d_val, d_map);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: fused painter
+// ------------------------------------------------------------------------------------------
+constexpr int kPaintThreads = 256;
+constexpr int kMaxHalosPerBlock = 32;
+constexpr int P_TABLE = 100;
+
+struct ParamPtrs {
+  const double* p[kMaxParams];
+  int32_t stride[kMaxParams];
+  int32_t n;
+};
+
+struct TableArgs {
+  const double* nodes;
+  const double* coef;
+  const int32_t* n_nodes;
+  const double* scale;
+  int32_t n_samples;
+};
+
+struct RingItem {
+  int64_t startpix;
+  int32_t nr, ip_lo, len, hl;
+  double A, B, phi_step, phi_off, z, sth;
+};
+
+struct PaintShared {
+  DiscHeader hdr[kMaxHalosPerBlock];
+  HaloCenter cen[kMaxHalosPerBlock];
+  double ctx[kMaxHalosPerBlock][kCtx];
+  int32_t ring_off[kMaxHalosPerBlock + 1];
+  RingItem item[kPaintThreads];
+  int32_t pix_off[kPaintThreads + 1];
+  int32_t warp_sum[kPaintThreads / 32];
+};
+
+template <int P>
+__global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
+                                                               int halos_per_block, double* __restrict__ map,
+                                                               unsigned long long* n_painted) {
+  constexpr bool VEC = (P == P_NFW_BG);
+  __shared__ PaintShared sm;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int64_t h0 = (int64_t)blockIdx.x * halos_per_block;
+  const int G = (int)min((int64_t)halos_per_block, H.n - h0);
+
+  // phase 0: per-halo headers, centres and template constants
+  if (tid < G) {
+    int64_t h = h0 + tid;
+    DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+    if (P == P_TABLE && tab.n_nodes[h] == 0) {  // bypass halo: painted elsewhere
+      d.ir_first = 1;
+      d.ir_last = 0;
+    }
+    sm.hdr[tid] = d;
+    sm.cen[tid] = make_center(H.theta[h], H.phi[h], H.D_a[h], VEC);
+    if (P != P_TABLE) {
+      double p[kMaxParams];
+#pragma unroll
+      for (int i = 0; i < kMaxParams; ++i)
+        if (i < pp.n) p[i] = pp.p[i][h * pp.stride[i]];
+      profile_setup<P>(p, sm.ctx[tid]);
+    } else {
+      sm.ctx[tid][0] = tab.scale ? tab.scale[h] : 1.0;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int32_t run = 0;
+    for (int i = 0; i < G; ++i) {
+      sm.ring_off[i] = run;
+      run += (int32_t)disc_n_rings(sm.hdr[i]);
+    }
+    sm.ring_off[G] = run;
+  }
+  __syncthreads();
+  const int32_t T = sm.ring_off[G];
+  unsigned long long painted = 0;
+
+  for (int32_t base = 0; base < T; base += kPaintThreads) {
+    // phase 1: one ring item per thread
+    int32_t it = base + tid;
+    int32_t len = 0;
+    if (it < T) {
+      int lo = 0, hi = G;  // largest hl with ring_off[hl] <= it
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (sm.ring_off[mid] <= it) lo = mid; else hi = mid;
+      }
+      const DiscHeader& d = sm.hdr[lo];
+      int64_t iz = d.ir_first + (it - sm.ring_off[lo]);
+      RingSpan s = ring_span(hpx, d, iz);
+      len = s.len;
+      RingItem& r = sm.item[tid];
+      r.startpix = s.startpix;
+      r.nr = s.nr;
+      r.ip_lo = s.ip_lo;
+      r.len = s.len;
+      r.hl = lo;
+      if (len > 0) {
+        RingGeom g = ring_geom(hpx, iz, s, sm.cen[lo]);
+        r.A = g.A; r.B = g.B; r.phi_step = g.phi_step; r.phi_off = g.phi_off; r.z = g.z; r.sth = g.sth;
+      }
+    }
+    // block exclusive scan of len
+    int32_t v = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) sm.warp_sum[warp] = v;
+    __syncthreads();
+    int32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < kPaintThreads / 32; ++w)
+      if (w < warp) woff += sm.warp_sum[w];
+    sm.pix_off[tid] = woff + v - len;
+    if (tid == kPaintThreads - 1) sm.pix_off[kPaintThreads] = woff + v;
+    __syncthreads();
+    const int32_t total = sm.pix_off[kPaintThreads];
+    painted += (tid == 0) ? (unsigned long long)total : 0ull;
+
+    // phase 2: one pixel per thread per iteration
+    for (int32_t k = tid; k < total; k += kPaintThreads) {
+      int lo = 0, hi = kPaintThreads;  // largest i with pix_off[i] <= k
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (sm.pix_off[mid] <= k) lo = mid; else hi = mid;
+      }
+      const RingItem& r = sm.item[lo];
+      int32_t ip = r.ip_lo + (k - sm.pix_off[lo]);
+      const HaloCenter& c = sm.cen[r.hl];
+      RingGeom g;
+      g.A = r.A; g.B = r.B; g.phi_step = r.phi_step; g.phi_off = r.phi_off; g.z = r.z; g.sth = r.sth;
+      double val;
+      if (VEC) {
+        double rx, ry, rz;
+        pixel_chord(g, ip, c, rx, ry, rz);
+        val = profile_eval_vec<P>(sm.ctx[r.hl], rx, ry, rz);
+      } else {
+        double R = c.D_a * pixel_sep(g, ip, c.phi);
+        if (P == P_TABLE) {
+          int64_t h = h0 + r.hl;
+          val = spline_eval(tab.n_samples, tab.nodes + h * tab.n_samples,
+                            tab.coef + h * (int64_t)(tab.n_samples - 1) * 4, R) * sm.ctx[r.hl][0];
+        } else {
+          val = profile_eval_R<P>(sm.ctx[r.hl], R);
+        }
+      }
+      int64_t pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
+      atomicAdd(&map[pix], val);
+    }
+    __syncthreads();
+  }
+  if (n_painted && tid == 0 && painted) atomicAdd(n_painted, painted);
+}
+
+static int pick_halos_per_block(int64_t n) {
+  // enough blocks to fill 148 SMs several times over; many halos per block amortise phase 0
+  int64_t g = n / (148 * 16);
+  if (g < 1) g = 1;
+  if (g > kMaxHalosPerBlock) g = kMaxHalosPerBlock;
+  return (int)g;
+}
+
+template <int P>
+static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& pp, const TableArgs& tab, double* d_map,
+                        unsigned long long* d_n_painted, void* stream) {
+  int g = pick_halos_per_block(halos->n);
+  int64_t blocks = (halos->n + g - 1) / g;
+  if (blocks > 0x7fffffffLL) return fail("too many blocks");
+  paint_kernel<P><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), pp, tab, g,
+                                                                                d_map, d_n_painted);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ap_paint_profile(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
+                                const int32_t* h_strides, int32_t n_params, double* d_map,
+                                unsigned long long* d_n_painted, void* stream) {
+  if (check_nside(nside)) return 1;
+  if (check_halos(halos, true)) return 1;
+  if (!d_map) return fail("d_map == NULL");
+  int want = profile_n_params(profile);
+  if (want < 0) return fail("unknown profile id");
+  if (n_params != want) return fail("wrong number of template parameters for this profile");
+  if (halos->n == 0) return 0;
+  ParamPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.n = n_params;
+  for (int i = 0; i < n_params; ++i) {
+    if (!h_params || !h_params[i]) return fail("NULL template parameter pointer");
+    pp.p[i] = h_params[i];
+    pp.stride[i] = h_strides ? h_strides[i] : 1;
+    if (pp.stride[i] != 0 && pp.stride[i] != 1) return fail("stride must be 0 or 1");
+  }
+  TableArgs tab;
+  memset(&tab, 0, sizeof(tab));
+  switch (profile) {
+    case P_CONSTANT: return launch_paint<P_CONSTANT>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_LINEAR: return launch_paint<P_LINEAR>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_SOLID_SPHERE: return launch_paint<P_SOLID_SPHERE>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_GAUSSIAN: return launch_paint<P_GAUSSIAN>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_NFW_RHO2D: return launch_paint<P_NFW_RHO2D>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_NFW_TAU2D: return launch_paint<P_NFW_TAU2D>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_NFW_KSZ: return launch_paint<P_NFW_KSZ>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_NFW_DEFLECTION: return launch_paint<P_NFW_DEFLECTION>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_NFW_BG: return launch_paint<P_NFW_BG>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_B16_TAU2D: return launch_paint<P_B16_TAU2D>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+  }
+  return fail("unknown profile id");
+}
+
+extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, const double* d_nodes,
+                              const double* d_coef, const int32_t* d_n_nodes, const double* d_scale, double* d_map,
+                              unsigned long long* d_n_painted, void* stream) {
+  if (check_nside(nside)) return 1;
+  if (check_halos(halos, true)) return 1;
+  if (n_samples < 4 || n_samples > kMaxNodes) return fail("n_samples must be in [4, 32]");
+  if (!d_map || !d_nodes || !d_coef || !d_n_nodes) return fail("paint_table: NULL pointer");
+  if (halos->n == 0) return 0;
+  ParamPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  TableArgs tab;
+  tab.nodes = d_nodes; tab.coef = d_coef; tab.n_nodes = d_n_nodes; tab.scale = d_scale; tab.n_samples = n_samples;
+  return launch_paint<P_TABLE>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: @interpolate tables
+// ------------------------------------------------------------------------------------------
+__global__ void table_nodes_kernel(int64_t n, const int64_t* n_pix, const double* rmin, const double* rmax,
+                                   int32_t ns, int32_t method, double* nodes, int32_t* n_nodes) {
+  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n) return;
+  if (n_pix[h] < ns) {  // len(R) < n_samples -> direct evaluation (utils.py:510-511)
+    n_nodes[h] = 0;
+    for (int i = 0; i < ns; ++i) nodes[h * ns + i] = 0.0;
+    return;
+  }
+  n_nodes[h] = ns;
+  double a = rmin[h], b = rmax[h];
+  if (method == 1) {  // logspace: sample_array clamps the minimum to eps = 1e-3 (utils.py:417-421)
+    if (a < 1.0e-3) a = 1.0e-3;
+    a = log10(a);
+    b = log10(b);
+  }
+  // np.linspace: step = (b - a) / (n - 1); y_i = i * step + a; y_{n-1} = b
+  double step = AP_SUB(b, a) / (double)(ns - 1);
+  for (int i = 0; i < ns; ++i) {
+    double v = (i == ns - 1) ? b : AP_ADD(AP_MUL((double)i, step), a);
+    if (method == 1) v = pow(10.0, v);
+    nodes[h * ns + i] = v;
+  }
+}
+
+extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d_rmin, const double* d_rmax,
+                              int32_t n_samples, int32_t method, double* d_nodes, int32_t* d_n_nodes, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n_samples < 2 || n_samples > kMaxNodes) return fail("n_samples must be in [2, 32]");
+  if (method != 0 && method != 1) return fail("method must be 0 (linspace) or 1 (logspace)");
+  if (n == 0) return 0;
+  if (!d_n_pix || !d_rmin || !d_rmax || !d_nodes || !d_n_nodes) return fail("table_nodes: NULL pointer");
+  int threads = 128;
+  table_nodes_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n, d_n_pix, d_rmin, d_rmax, n_samples, method, d_nodes, d_n_nodes);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(128) b16_tau_nodes_kernel(int64_t n, const double* R200, const double* M200,
+                                                            const double* zred, int32_t ns, const double* nodes,
+                                                            const int32_t* n_nodes, double* values) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ns) return;
+  int64_t h = t / ns;
+  if (n_nodes[h] == 0) {
+    values[t] = 0.0;
+    return;
+  }
+  double ctx[kCtx];
+  b16_setup(R200[h], M200[h], zred[h], ctx);
+  values[t] = b16_tau_2D(ctx, nodes[t]);
+}
+
+extern "C" int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double* d_M_200c, const double* d_redshift,
+                                int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes, double* d_values,
+                                void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n == 0) return 0;
+  if (!d_R_200c || !d_M_200c || !d_redshift || !d_nodes || !d_n_nodes || !d_values) return fail("b16_tau_nodes: NULL pointer");
+  int threads = 128;
+  int64_t total = n * n_samples;
+  b16_tau_nodes_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n, d_R_200c, d_M_200c, d_redshift, n_samples, d_nodes, d_n_nodes, d_values);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(128) spline_build_kernel(int64_t n, int32_t ns, const double* nodes,
+                                                           const double* values, const int32_t* n_nodes, double* coef) {
+  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n) return;
+  double* c = coef + h * (int64_t)(ns - 1) * 4;
+  if (n_nodes[h] == 0) {
+    for (int i = 0; i < (ns - 1) * 4; ++i) c[i] = 0.0;
+    return;
+  }
+  double x[kMaxNodes], y[kMaxNodes], cc[(kMaxNodes - 1) * 4];
+  for (int i = 0; i < ns; ++i) {
+    x[i] = nodes[h * ns + i];
+    y[i] = values[h * ns + i];
+  }
+  spline_build_nak(ns, x, y, cc);
+  for (int i = 0; i < (ns - 1) * 4; ++i) c[i] = cc[i];
+}
+
+extern "C" int ap_spline_build(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,
+                               const int32_t* d_n_nodes, double* d_coef, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n_samples < 4 || n_samples > kMaxNodes) return fail("n_samples must be in [4, 32]");
+  if (n == 0) return 0;
+  if (!d_nodes || !d_values || !d_n_nodes || !d_coef) return fail("spline_build: NULL pointer");
+  int threads = 128;
+  spline_build_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n, n_samples, d_nodes, d_values, d_n_nodes, d_coef);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// bypass: halos with 0 < n_pix < n_samples; one warp per halo, lane k owns pixel k
+__global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev H, const double* R200, const double* M200,
+                                                              const double* zred, const double* scale, const int64_t* n_pix,
+                                                              int32_t ns, double* map, unsigned long long* n_painted) {
+  int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (h >= H.n) return;
+  int64_t np = n_pix[h];
+  if (np <= 0 || np >= ns) return;
+  if (lane >= np) return;
+  DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+  HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
+  int64_t run = 0;
+  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+    RingSpan s = ring_span(hpx, d, iz);
+    if (s.len <= 0) continue;
+    if (lane < run + s.len) {
+      RingGeom g = ring_geom(hpx, iz, s, c);
+      int32_t ip = s.ip_lo + (int32_t)(lane - run);
+      double R = c.D_a * pixel_sep(g, ip, c.phi);
+      double ctx[kCtx];
+      b16_setup(R200[h], M200[h], zred[h], ctx);
+      double val = b16_tau_2D(ctx, R) * (scale ? scale[h] : 1.0);
+      int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
+      atomicAdd(&map[pix], val);
+      break;
+    }
+    run += s.len;
+  }
+  if (n_painted && lane == 0) atomicAdd(n_painted, (unsigned long long)np);
+}
+
+extern "C" int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
+                                  const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
+                                  int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream) {
+  if (check_nside(nside)) return 1;
+  if (check_halos(halos, true)) return 1;
+  if (n_samples < 2 || n_samples > 32) return fail("n_samples must be in [2, 32]");
+  if (halos->n == 0) return 0;
+  if (!d_R_200c || !d_M_200c || !d_redshift || !d_n_pix || !d_map) return fail("paint_b16_small: NULL pointer");
+  int threads = 128;
+  int64_t blocks = (halos->n * 32 + threads - 1) / threads;
+  paint_b16_small_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      make_hpx(nside), to_dev(halos), d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: cutouts and stack
+// ------------------------------------------------------------------------------------------
+struct CutGrid {
+  double lon0, dlon, lat0, dlat;  // x_j = lon0 + (j + 0.5) dlon ; y_i = lat0 + (i + 0.5) dlat  [deg]
+  int32_t xsize, ysize;
+};
+
+__device__ __forceinline__ void image_vec(const CutGrid& g, int32_t s, double& vx, double& vy, double& vz) {
+  int32_t i = s / g.xsize, j = s - i * g.xsize;
+  const double dtor = kPi / 180.0;
+  double x = g.lon0 + ((double)j + 0.5) * g.dlon;
+  double y = g.lat0 + ((double)i + 0.5) * g.dlat;
+  double theta = kHalfPi - y * dtor;  // xy2vec: theta = pi/2 - y, phi = flip * x, flip = -1 (astro)
+  double phi = -(x * dtor);
+  double st, ct, sp, cp;
+  sincos(theta, &st, &ct);
+  sincos(phi, &sp, &cp);
+  vx = st * cp;
+  vy = st * sp;
+  vz = ct;
+}
+
+// Rotator(rot=(lon, lat)).I = m1(lon) m2(-lat): rows of the 3x3 matrix
+__device__ __forceinline__ void rot_matrix(double lon_deg, double lat_deg, double* m) {
+  const double dtor = kPi / 180.0;
+  double s1, c1, s2, c2;
+  sincos(lon_deg * dtor, &s1, &c1);
+  sincos(-(lat_deg * dtor), &s2, &c2);
+  m[0] = c1 * c2; m[1] = -s1; m[2] = c1 * s2;
+  m[3] = s1 * c2; m[4] = c1;  m[5] = s1 * s2;
+  m[6] = -s2;     m[7] = 0.0; m[8] = c2;
+}
+
+constexpr int kStackThreads = 256;
+constexpr int kStackHalos = 128;
+
+template <bool STACK>
+__global__ void __launch_bounds__(kStackThreads) cutout_kernel(Hpx hpx, const double* __restrict__ map, int64_t n_sel,
+                                                               const double* lon, const double* lat, CutGrid grid,
+                                                               const double* weight, double* out) {
+  __shared__ double rot[kStackHalos][9];
+  __shared__ double wgt[kStackHalos];
+  const int32_t nsamp = grid.xsize * grid.ysize;
+  const int32_t s = blockIdx.x * kStackThreads + threadIdx.x;
+  const int64_t hbase = (int64_t)blockIdx.y * kStackHalos;
+  const int nh = (int)min((int64_t)kStackHalos, n_sel - hbase);
+  for (int i = threadIdx.x; i < nh; i += kStackThreads) {
+    rot_matrix(lon[hbase + i], lat[hbase + i], rot[i]);
+    wgt[i] = weight ? weight[hbase + i] : 1.0;
+  }
+  __syncthreads();
+  if (s >= nsamp) return;
+  double vx, vy, vz;
+  image_vec(grid, s, vx, vy, vz);
+  double acc = 0.0;
+  for (int i = 0; i < nh; ++i) {
+    const double* m = rot[i];
+    double sx = m[0] * vx + m[1] * vy + m[2] * vz;
+    double sy = m[3] * vx + m[4] * vy + m[5] * vz;
+    double sz = m[6] * vx + m[7] * vy + m[8] * vz;
+    int64_t pix = vec2pix_ring(hpx, sx, sy, sz);
+    double v = __ldg(&map[pix]);
+    if (STACK)
+      acc += wgt[i] * v;
+    else
+      out[(hbase + i) * (int64_t)nsamp + s] = v;
+  }
+  if (STACK) atomicAdd(&out[s], acc);
+}
+
+static int cut_grid(double lon0, double lon1, double lat0, double lat1, int32_t xsize, int32_t ysize, CutGrid& g) {
+  if (xsize < 1 || ysize < 1) return fail("xsize/ysize must be >= 1");
+  // CartesianProj.set_proj_plane_info: lonra[1] = lonra[0] + (mod(lonra[1]-lonra[0], 360) or 360)
+  double span = fmod(lon1 - lon0, 360.0);
+  if (span < 0) span += 360.0;
+  if (span == 0) span = 360.0;
+  if (!(lat0 >= -90.0 && lat1 <= 90.0 && lat0 < lat1)) return fail("invalid lat_range");
+  g.lon0 = lon0;
+  g.dlon = span / xsize;
+  g.lat0 = lat0;
+  g.dlat = (lat1 - lat0) / ysize;
+  g.xsize = xsize;
+  g.ysize = ysize;
+  return 0;
+}
+
+extern "C" int ap_cutouts(int64_t nside, const double* d_map, int64_t n_sel, const double* d_lon_deg,
+                          const double* d_lat_deg, double lon0, double lon1, double lat0, double lat1, int32_t xsize,
+                          int32_t ysize, double* d_out, void* stream) {
+  if (check_nside(nside)) return 1;
+  CutGrid g;
+  if (cut_grid(lon0, lon1, lat0, lat1, xsize, ysize, g)) return 1;
+  if (n_sel < 0) return fail("n_sel < 0");
+  if (n_sel == 0) return 0;
+  if (!d_map || !d_lon_deg || !d_lat_deg || !d_out) return fail("cutouts: NULL pointer");
+  dim3 grid((xsize * ysize + kStackThreads - 1) / kStackThreads, (unsigned)((n_sel + kStackHalos - 1) / kStackHalos));
+  if (grid.y > 65535) return fail("too many halos in one ap_cutouts call (max 8388480)");
+  cutout_kernel<false><<<grid, kStackThreads, 0, (cudaStream_t)stream>>>(make_hpx(nside), d_map, n_sel, d_lon_deg, d_lat_deg,
+                                                                        g, nullptr, d_out);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ap_stack_cutouts(int64_t nside, const double* d_map, int64_t n_sel, const double* d_lon_deg,
+                                const double* d_lat_deg, double lon0, double lon1, double lat0, double lat1,
+                                int32_t xsize, int32_t ysize, const double* d_weight, double* d_stack, void* stream) {
+  if (check_nside(nside)) return 1;
+  CutGrid g;
+  if (cut_grid(lon0, lon1, lat0, lat1, xsize, ysize, g)) return 1;
+  if (n_sel < 0) return fail("n_sel < 0");
+  if (n_sel == 0) return 0;
+  if (!d_map || !d_lon_deg || !d_lat_deg || !d_stack) return fail("stack_cutouts: NULL pointer");
+  dim3 grid((xsize * ysize + kStackThreads - 1) / kStackThreads, (unsigned)((n_sel + kStackHalos - 1) / kStackHalos));
+  if (grid.y > 65535) return fail("too many halos in one ap_stack_cutouts call (max 8388480)");
+  cutout_kernel<true><<<grid, kStackThreads, 0, (cudaStream_t)stream>>>(make_hpx(nside), d_map, n_sel, d_lon_deg, d_lat_deg,
+                                                                       g, d_weight, d_stack);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry
+// ------------------------------------------------------------------------------------------
+extern "C" int ap_spray_host(int profile, int64_t nside, int64_t n, const double* h_x, const double* h_y,
+                             const double* h_z, const double* h_radius, const double* h_theta, const double* h_phi,
+                             const double* h_D_a, const double* const* h_params, const int32_t* h_strides,
+                             int32_t n_params, double* h_map, uint64_t* h_n_painted) {
+  if (check_nside(nside)) return 1;
+  if (n < 0) return fail("n < 0");
+  if (n_params < 0 || n_params > kMaxParams) return fail("bad n_params");
+  if (!h_map) return fail("h_map == NULL");
+  const int64_t npix = 12 * nside * nside;
+  const double* cols[7] = {h_x, h_y, h_z, h_radius, h_theta, h_phi, h_D_a};
+  double* d_cols[7] = {0};
+  double* d_par[kMaxParams] = {0};
+  double* d_map = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  int rc = 0;
+  cudaStream_t st = nullptr;
+  auto cleanup = [&]() {
+    for (auto p : d_cols) if (p) cudaFree(p);
+    for (auto p : d_par) if (p) cudaFree(p);
+    if (d_map) cudaFree(d_map);
+    if (d_cnt) cudaFree(d_cnt);
+    if (st) cudaStreamDestroy(st);
+  };
+#define AP_TRY(call)                                                                  \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      cleanup();                                                                      \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                \
+    }                                                                                 \
+  } while (0)
+  AP_TRY(cudaStreamCreate(&st));
+  AP_TRY(cudaMalloc(&d_map, sizeof(double) * npix));
+  AP_TRY(cudaMemcpyAsync(d_map, h_map, sizeof(double) * npix, cudaMemcpyHostToDevice, st));
+  AP_TRY(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+  AP_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+  for (int i = 0; i < 7 && n > 0; ++i) {
+    if (!cols[i]) { cleanup(); return fail("NULL halo column"); }
+    AP_TRY(cudaMalloc(&d_cols[i], sizeof(double) * n));
+    AP_TRY(cudaMemcpyAsync(d_cols[i], cols[i], sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  }
+  for (int i = 0; i < n_params && n > 0; ++i) {
+    if (!h_params || !h_params[i]) { cleanup(); return fail("NULL template parameter"); }
+    int64_t len = (h_strides && h_strides[i] == 0) ? 1 : n;
+    AP_TRY(cudaMalloc(&d_par[i], sizeof(double) * len));
+    AP_TRY(cudaMemcpyAsync(d_par[i], h_params[i], sizeof(double) * len, cudaMemcpyHostToDevice, st));
+  }
+  {
+    ap_halos H;
+    H.n = n;
+    H.d_x = d_cols[0]; H.d_y = d_cols[1]; H.d_z = d_cols[2]; H.d_radius = d_cols[3];
+    H.d_theta = d_cols[4]; H.d_phi = d_cols[5]; H.d_D_a = d_cols[6];
+    rc = ap_paint_profile(profile, nside, &H, d_par, h_strides, n_params, d_map, d_cnt, st);
+  }
+  if (rc == 0) {
+    AP_TRY(cudaMemcpyAsync(h_map, d_map, sizeof(double) * npix, cudaMemcpyDeviceToHost, st));
+    unsigned long long cnt = 0;
+    AP_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    AP_TRY(cudaStreamSynchronize(st));
+    if (h_n_painted) *h_n_painted = cnt;
+  }
+  cleanup();
+  return rc;
+}

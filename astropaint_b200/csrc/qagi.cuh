@@ -1,0 +1,422 @@
+// QUADPACK dqagie / dqk15i / dqelg / dqpsrt, restated for one semi-infinite range
+// (bound, +inf), as a host/device template.
+//
+// The reference's @LOS_integrate (astropaint/lib/utils.py:428-454) calls
+//   scipy.integrate.quad(f, R_i, np.inf, epsabs=0., epsrel=1.e-2)        (utils.py:448)
+// which is QUADPACK dqagie(inf=1, limit=50).  With epsrel=1e-2 its true error on the
+// Battaglia16 integrand reaches ~2.5e-3, so reproducing the reference map to 1e-6 means
+// reproducing QUADPACK's adaptive decisions, not the integral: this file follows the
+// published netlib algorithm (Piessens et al. 1983, public domain) statement by statement.
+// csrc/hostcheck.cpp compiles it with g++ and tests/test_qagi_host.py checks it against
+// scipy.integrate.quad (value, abserr, neval) on the CPU.
+#pragma once
+#include "common.cuh"
+
+namespace ap {
+
+constexpr int kQagiLimit = 50;       // scipy.integrate.quad default `limit`
+constexpr double kEpmach = 2.220446049250313e-16;   // d1mach(4)
+constexpr double kUflow = 2.2250738585072014e-308;  // d1mach(1)
+constexpr double kOflow = 1.7976931348623157e+308;  // d1mach(2)
+
+struct QagiResult {
+  double result, abserr;
+  int neval, ier, last;
+};
+
+// 15-point transformed Gauss-Kronrod rule on (a, b) subset of (0, 1], x = boun + (1-t)/t.
+template <class F>
+AP_HD_NOINLINE void qk15i(const F& f, double boun, double a, double b, double& result,
+                          double& abserr, double& resabs, double& resasc) {
+  const double wg[8] = {0.0, 0.129484966168869693270611432679082, 0.0,
+                        0.279705391489276667901467771423780, 0.0,
+                        0.381830050505118944950369775488975, 0.0,
+                        0.417959183673469387755102040816327};
+  const double xgk[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
+                         0.864864423359769072789712788640926, 0.741531185599394439863864773280788,
+                         0.586087235467691130294144838258730, 0.405845151377397166906606412076961,
+                         0.207784955007898467600689403773245, 0.0};
+  const double wgk[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+                         0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+                         0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+                         0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
+  double fv1[7], fv2[7];
+  double centr = AP_MUL(0.5, AP_ADD(a, b));
+  double hlgth = AP_MUL(0.5, AP_SUB(b, a));
+  double tabsc1 = AP_ADD(boun, AP_SUB(1.0, centr) / centr);
+  double fval1 = f(tabsc1);
+  double fc = (fval1 / centr) / centr;
+  double resg = AP_MUL(wg[7], fc);
+  double resk = AP_MUL(wgk[7], fc);
+  resabs = fabs(resk);
+  for (int j = 0; j < 7; ++j) {
+    double absc = AP_MUL(hlgth, xgk[j]);
+    double absc1 = AP_SUB(centr, absc);
+    double absc2 = AP_ADD(centr, absc);
+    double t1 = AP_ADD(boun, AP_SUB(1.0, absc1) / absc1);
+    double t2 = AP_ADD(boun, AP_SUB(1.0, absc2) / absc2);
+    double f1 = f(t1);
+    double f2 = f(t2);
+    f1 = (f1 / absc1) / absc1;
+    f2 = (f2 / absc2) / absc2;
+    fv1[j] = f1;
+    fv2[j] = f2;
+    double fsum = AP_ADD(f1, f2);
+    resg = AP_ADD(resg, AP_MUL(wg[j], fsum));
+    resk = AP_ADD(resk, AP_MUL(wgk[j], fsum));
+    resabs = AP_ADD(resabs, AP_MUL(wgk[j], AP_ADD(fabs(f1), fabs(f2))));
+  }
+  double reskh = AP_MUL(resk, 0.5);
+  resasc = AP_MUL(wgk[7], fabs(AP_SUB(fc, reskh)));
+  for (int j = 0; j < 7; ++j)
+    resasc = AP_ADD(resasc, AP_MUL(wgk[j], AP_ADD(fabs(AP_SUB(fv1[j], reskh)),
+                                                    fabs(AP_SUB(fv2[j], reskh)))));
+  result = AP_MUL(resk, hlgth);
+  resasc = AP_MUL(resasc, hlgth);
+  resabs = AP_MUL(resabs, hlgth);
+  abserr = fabs(AP_MUL(AP_SUB(resk, resg), hlgth));
+  if (resasc != 0.0 && abserr != 0.0) {
+    double q = AP_MUL(200.0, abserr) / resasc;
+    double p = AP_MUL(q, sqrt(q));  // q**1.5
+    abserr = AP_MUL(resasc, fmin(1.0, p));
+  }
+  if (resabs > kUflow / (50.0 * kEpmach)) abserr = fmax(AP_MUL(kEpmach * 50.0, resabs), abserr);
+}
+
+// epsilon algorithm (dqelg).  epstab has 52 entries, 1-based in the original.
+AP_HD_NOINLINE void qelg(int& n, double* epstab, double& result, double& abserr, double* res3la,
+                         int& nres) {
+  nres += 1;
+  abserr = kOflow;
+  result = epstab[n - 1];
+  if (n < 3) {
+    abserr = fmax(abserr, 5.0 * kEpmach * fabs(result));
+    return;
+  }
+  const int limexp = 50;
+  epstab[n + 1] = epstab[n - 1];
+  int newelm = (n - 1) / 2;
+  epstab[n - 1] = kOflow;
+  int num = n;
+  int k1 = n;
+  bool converged = false;
+  for (int i = 1; i <= newelm; ++i) {
+    int k2 = k1 - 1, k3 = k1 - 2;
+    double res = epstab[k1 + 1];
+    double e0 = epstab[k3 - 1], e1 = epstab[k2 - 1], e2 = res;
+    double e1abs = fabs(e1);
+    double delta2 = AP_SUB(e2, e1), err2 = fabs(delta2);
+    double tol2 = AP_MUL(fmax(fabs(e2), e1abs), kEpmach);
+    double delta3 = AP_SUB(e1, e0), err3 = fabs(delta3);
+    double tol3 = AP_MUL(fmax(e1abs, fabs(e0)), kEpmach);
+    if (!(err2 > tol2 || err3 > tol3)) {
+      // e0, e1, e2 equal to within machine accuracy: convergence assumed
+      result = res;
+      abserr = AP_ADD(err2, err3);
+      abserr = fmax(abserr, 5.0 * kEpmach * fabs(result));
+      converged = true;
+      break;
+    }
+    double e3 = epstab[k1 - 1];
+    epstab[k1 - 1] = e1;
+    double delta1 = AP_SUB(e1, e3), err1 = fabs(delta1);
+    double tol1 = AP_MUL(fmax(e1abs, fabs(e3)), kEpmach);
+    if (err1 <= tol1 || err2 <= tol2 || err3 <= tol3) {
+      n = i + i - 1;
+      break;
+    }
+    double ss = AP_SUB(AP_ADD(1.0 / delta1, 1.0 / delta2), 1.0 / delta3);
+    double epsinf = fabs(AP_MUL(ss, e1));
+    if (!(epsinf > 1.0e-4)) {
+      n = i + i - 1;
+      break;
+    }
+    res = AP_ADD(e1, 1.0 / ss);
+    epstab[k1 - 1] = res;
+    k1 -= 2;
+    double error = AP_ADD(AP_ADD(err2, fabs(AP_SUB(res, e2))), err3);
+    if (error > abserr) continue;
+    abserr = error;
+    result = res;
+  }
+  if (converged) return;  // label 100 already applied
+  // shift the table
+  if (n == limexp) n = 2 * (limexp / 2) - 1;
+  int ib = ((num / 2) * 2 == num) ? 2 : 1;
+  int ie = newelm + 1;
+  for (int i = 1; i <= ie; ++i) {
+    int ib2 = ib + 2;
+    epstab[ib - 1] = epstab[ib2 - 1];
+    ib = ib2;
+  }
+  if (num != n) {
+    int indx = num - n + 1;
+    for (int i = 1; i <= n; ++i) {
+      epstab[i - 1] = epstab[indx - 1];
+      indx += 1;
+    }
+  }
+  if (nres < 4) {
+    res3la[nres - 1] = result;
+    abserr = kOflow;
+  } else {
+    abserr = AP_ADD(AP_ADD(fabs(AP_SUB(result, res3la[2])), fabs(AP_SUB(result, res3la[1]))),
+                    fabs(AP_SUB(result, res3la[0])));
+    res3la[0] = res3la[1];
+    res3la[1] = res3la[2];
+    res3la[2] = result;
+  }
+  abserr = fmax(abserr, 5.0 * kEpmach * fabs(result));
+}
+
+// dqpsrt: keep iord (1-based indices stored in a 0-based array) sorted by decreasing elist.
+AP_HD_NOINLINE void qpsrt(int limit, int last, int& maxerr, double& ermax, const double* elist,
+                          int* iord, int& nrmax) {
+  if (last <= 2) {
+    iord[0] = 1;
+    iord[1] = 2;
+  } else {
+    double errmax = elist[maxerr - 1];
+    if (nrmax != 1) {
+      int ido = nrmax - 1;
+      for (int i = 1; i <= ido; ++i) {
+        int isucc = iord[nrmax - 2];
+        if (errmax <= elist[isucc - 1]) break;
+        iord[nrmax - 1] = isucc;
+        nrmax -= 1;
+      }
+    }
+    int jupbn = last;
+    if (last > (limit / 2 + 2)) jupbn = limit + 3 - last;
+    double errmin = elist[last - 1];
+    int jbnd = jupbn - 1;
+    int ibeg = nrmax + 1;
+    bool placed = false;
+    int i = ibeg;
+    for (; i <= jbnd; ++i) {
+      int isucc = iord[i - 1];
+      if (errmax >= elist[isucc - 1]) {
+        placed = true;
+        break;
+      }
+      iord[i - 2] = isucc;
+    }
+    if (!placed) {
+      iord[jbnd - 1] = maxerr;
+      iord[jupbn - 1] = last;
+    } else {
+      iord[i - 2] = maxerr;
+      int k = jbnd;
+      bool placed2 = false;
+      for (int j = i; j <= jbnd; ++j) {
+        int isucc = iord[k - 1];
+        if (errmin < elist[isucc - 1]) {
+          placed2 = true;
+          break;
+        }
+        iord[k] = isucc;
+        k -= 1;
+      }
+      if (placed2)
+        iord[k] = last;
+      else
+        iord[i - 1] = last;
+    }
+  }
+  maxerr = iord[nrmax - 1];
+  ermax = elist[maxerr - 1];
+}
+
+// dqagie with inf = 1: integral of f over (bound, +inf).
+template <class F>
+AP_HD_NOINLINE QagiResult qagi_upper(const F& f, double bound, double epsabs, double epsrel) {
+  const int limit = kQagiLimit;
+  double alist[kQagiLimit], blist[kQagiLimit], rlist[kQagiLimit], elist[kQagiLimit];
+  int iord[kQagiLimit];
+  double rlist2[52], res3la[3];
+  QagiResult out;
+  int ier = 0, last = 0;
+  double result = 0.0, abserr = 0.0;
+  alist[0] = 0.0;
+  blist[0] = 1.0;
+  rlist[0] = 0.0;
+  elist[0] = 0.0;
+  iord[0] = 0;
+  if (epsabs <= 0.0 && epsrel < fmax(50.0 * kEpmach, 0.5e-28)) {
+    out.result = 0.0; out.abserr = 0.0; out.neval = 0; out.ier = 6; out.last = 0;
+    return out;
+  }
+  double boun = bound;
+  double defabs, resabs;
+  qk15i(f, boun, 0.0, 1.0, result, abserr, defabs, resabs);
+  last = 1;
+  rlist[0] = result;
+  elist[0] = abserr;
+  iord[0] = 1;
+  double dres = fabs(result);
+  double errbnd = fmax(epsabs, AP_MUL(epsrel, dres));
+  if (abserr <= 100.0 * kEpmach * defabs && abserr > errbnd) ier = 2;
+  if (limit == 1) ier = 1;
+  bool done = (ier != 0 || (abserr <= errbnd && abserr != resabs) || abserr == 0.0);
+  if (!done) {
+    rlist2[0] = result;
+    double errmax = abserr;
+    int maxerr = 1;
+    double area = result;
+    double errsum = abserr;
+    abserr = kOflow;
+    int nrmax = 1, nres = 0, ktmin = 0, numrl2 = 2;
+    bool extrap = false, noext = false;
+    int ierro = 0, iroff1 = 0, iroff2 = 0, iroff3 = 0;
+    int ksgn = -1;
+    if (dres >= (1.0 - 50.0 * kEpmach) * defabs) ksgn = 1;
+    double small = 0.0, erlarg = 0.0, ertest = 0.0, correc = 0.0, erlast;
+    double reseps, abseps;
+    // exit codes of the main loop: 0 = fell off the end (-> 100), 100, 115
+    int exit_label = 100;
+    for (last = 2; last <= limit; ++last) {
+      double a1 = alist[maxerr - 1];
+      double b1 = AP_MUL(0.5, AP_ADD(alist[maxerr - 1], blist[maxerr - 1]));
+      double a2 = b1;
+      double b2 = blist[maxerr - 1];
+      erlast = errmax;
+      double area1, error1, defab1, area2, error2, defab2, rabs;
+      qk15i(f, boun, a1, b1, area1, error1, rabs, defab1);
+      qk15i(f, boun, a2, b2, area2, error2, rabs, defab2);
+      double area12 = AP_ADD(area1, area2);
+      double erro12 = AP_ADD(error1, error2);
+      errsum = AP_SUB(AP_ADD(errsum, erro12), errmax);
+      area = AP_SUB(AP_ADD(area, area12), rlist[maxerr - 1]);
+      if (!(defab1 == error1 || defab2 == error2)) {
+        if (!(fabs(AP_SUB(rlist[maxerr - 1], area12)) > AP_MUL(1.0e-5, fabs(area12)) ||
+              erro12 < AP_MUL(0.99, errmax))) {
+          if (extrap) iroff2 += 1; else iroff1 += 1;
+        }
+        if (last > 10 && erro12 > errmax) iroff3 += 1;
+      }
+      rlist[maxerr - 1] = area1;
+      rlist[last - 1] = area2;
+      errbnd = fmax(epsabs, AP_MUL(epsrel, fabs(area)));
+      if (iroff1 + iroff2 >= 10 || iroff3 >= 20) ier = 2;
+      if (iroff2 >= 5) ierro = 3;
+      if (last == limit) ier = 1;
+      if (fmax(fabs(a1), fabs(b2)) <= (1.0 + 100.0 * kEpmach) * (fabs(a2) + 1000.0 * kUflow)) ier = 4;
+      if (error2 > error1) {
+        alist[maxerr - 1] = a2;
+        alist[last - 1] = a1;
+        blist[last - 1] = b1;
+        rlist[maxerr - 1] = area2;
+        rlist[last - 1] = area1;
+        elist[maxerr - 1] = error2;
+        elist[last - 1] = error1;
+      } else {
+        alist[last - 1] = a2;
+        blist[maxerr - 1] = b1;
+        blist[last - 1] = b2;
+        elist[maxerr - 1] = error1;
+        elist[last - 1] = error2;
+      }
+      qpsrt(limit, last, maxerr, errmax, elist, iord, nrmax);
+      if (errsum <= errbnd) { exit_label = 115; break; }
+      if (ier != 0) { exit_label = 100; break; }
+      if (last == 2) {
+        small = 0.375;
+        erlarg = errsum;
+        ertest = errbnd;
+        rlist2[1] = area;
+        continue;
+      }
+      if (noext) continue;
+      erlarg = AP_SUB(erlarg, erlast);
+      if (fabs(AP_SUB(b1, a1)) > small) erlarg = AP_ADD(erlarg, erro12);
+      if (!extrap) {
+        if (fabs(AP_SUB(blist[maxerr - 1], alist[maxerr - 1])) > small) continue;
+        extrap = true;
+        nrmax = 2;
+      }
+      if (!(ierro == 3 || erlarg <= ertest)) {
+        int id = nrmax;
+        int jupbnd = last;
+        if (last > (2 + limit / 2)) jupbnd = limit + 3 - last;
+        bool cont = false;
+        for (int k = id; k <= jupbnd; ++k) {
+          maxerr = iord[nrmax - 1];
+          errmax = elist[maxerr - 1];
+          if (fabs(AP_SUB(blist[maxerr - 1], alist[maxerr - 1])) > small) { cont = true; break; }
+          nrmax += 1;
+        }
+        if (cont) continue;
+      }
+      // perform extrapolation
+      numrl2 += 1;
+      rlist2[numrl2 - 1] = area;
+      qelg(numrl2, rlist2, reseps, abseps, res3la, nres);
+      ktmin += 1;
+      if (ktmin > 5 && abserr < AP_MUL(1.0e-3, errsum)) ier = 5;
+      if (!(abseps >= abserr)) {
+        ktmin = 0;
+        abserr = abseps;
+        result = reseps;
+        correc = erlarg;
+        ertest = fmax(epsabs, AP_MUL(epsrel, fabs(reseps)));
+        if (abserr <= ertest) { exit_label = 100; break; }
+      }
+      if (numrl2 == 1) noext = true;
+      if (ier == 5) { exit_label = 100; break; }
+      maxerr = iord[0];
+      errmax = elist[maxerr - 1];
+      nrmax = 1;
+      extrap = false;
+      small = AP_MUL(small, 0.5);
+      erlarg = errsum;
+    }
+    if (last > limit) last = limit;  // loop ran to completion (Fortran leaves last = limit+1; list holds limit)
+    bool sum_list = (exit_label == 115);
+    bool finished = false;
+    if (!sum_list) {
+      // label 100
+      if (abserr == kOflow) {
+        sum_list = true;
+      } else if (ier + ierro == 0) {
+        // label 110
+        if (!(ksgn == -1 && fmax(fabs(result), fabs(area)) <= AP_MUL(defabs, 0.01))) {
+          if (0.01 > result / area || result / area > 100.0 || errsum > fabs(area)) ier = 6;
+        }
+        finished = true;
+      } else {
+        if (ierro == 3) abserr = AP_ADD(abserr, correc);
+        if (ier == 0) ier = 3;
+        bool go110 = false;
+        if (result != 0.0 && area != 0.0) {
+          if (abserr / fabs(result) > errsum / fabs(area)) sum_list = true; else go110 = true;
+        } else if (abserr > errsum) {
+          sum_list = true;
+        } else if (area == 0.0) {
+          finished = true;
+        } else {
+          go110 = true;
+        }
+        if (go110) {
+          if (!(ksgn == -1 && fmax(fabs(result), fabs(area)) <= AP_MUL(defabs, 0.01))) {
+            if (0.01 > result / area || result / area > 100.0 || errsum > fabs(area)) ier = 6;
+          }
+          finished = true;
+        }
+      }
+    }
+    if (sum_list && !finished) {
+      result = 0.0;
+      for (int k = 0; k < last; ++k) result = AP_ADD(result, rlist[k]);
+      abserr = errsum;
+    }
+  }
+  out.neval = 30 * last - 15;
+  if (ier > 2) ier -= 1;
+  out.result = result;
+  out.abserr = abserr;
+  out.ier = ier;
+  out.last = last;
+  return out;
+}
+
+}  // namespace ap

@@ -1,0 +1,130 @@
+/* astropaint_b200 — C ABI of the B200-native painting hot path.
+ *
+ * The reference (syasini/AstroPaint) has no FFI: the path sits behind a plain Python object
+ * API (Painter.spray / Canvas.stack_cutouts).  These entry points are what a maintainer binds
+ * (ctypes stub in INTEGRATION.md) to replace the per-halo Python/healpy/numpy loop.  Each one
+ * cites the reference lines it replaces (paths relative to the reference repo).
+ *
+ * Conventions: every `const double*` / `int64_t*` argument named d_* is a DEVICE pointer owned
+ * by the caller; h_* is a HOST pointer.  `stream` is a cudaStream_t passed as void* (NULL =
+ * default stream); all device entry points are asynchronous on it.  Return value 0 = OK,
+ * non-zero = error (ap_last_error() gives the message).  Nothing here falls back to the CPU.
+ */
+#ifndef ASTROPAINT_B200_H
+#define ASTROPAINT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* profile ids for ap_paint_profile (the built-in templates as device functions) */
+enum ap_profile {
+  AP_CONSTANT = 0,       /* profiles/spherical.py:44-59   constant_density_2D(R, constant) */
+  AP_LINEAR = 1,         /* profiles/spherical.py:62-79   linear_density_2D(R, intercept, slope) */
+  AP_SOLID_SPHERE = 2,   /* profiles/spherical.py:25-42   solid_sphere_2D(R, M_200c, R_200c) */
+  AP_GAUSSIAN = 3,       /* README.md:99-101              gaussian(R, R_200c, x, y, z) */
+  AP_NFW_RHO2D = 4,      /* profiles/NFW.py:65-80         rho_2D_bartlemann(R, rho_s, R_s) */
+  AP_NFW_TAU2D = 5,      /* profiles/NFW.py:153-169       tau_2D(R, rho_s, R_s) */
+  AP_NFW_KSZ = 6,        /* profiles/NFW.py:172-178       kSZ_T(R, rho_s, R_s, v_r, T_cmb) */
+  AP_NFW_DEFLECTION = 7, /* profiles/NFW.py:111-150       deflection_angle(R, c_200c, R_200c, M_200c) */
+  AP_NFW_BG = 8,         /* profiles/NFW.py:181-193       BG(R_vec, c_200c, R_200c, M_200c, theta, phi, v_th, v_ph, T_cmb) */
+  AP_B16_TAU2D = 9       /* profiles/Battaglia16.py:221-239 tau_2D(R, R_200c, M_200c, redshift) */
+};
+
+/* Per-halo geometry inputs shared by all entry points (catalog columns, paint_bucket.py:308-364):
+ *   d_x, d_y, d_z   raw Cartesian position [Mpc]  -> disc centre of hp.query_disc (:1222-1225)
+ *   d_radius        R_times * arcmin2rad(R_ang_200c) [rad], computed on the host (:1226-1227)
+ *   d_theta, d_phi  catalog (theta, phi) -> centre of hp.rotator.angdist (:1202-1203, :1264)
+ *   d_D_a           angular-diameter distance [Mpc] (:1273)                                  */
+typedef struct ap_halos {
+  int64_t n;
+  const double *d_x, *d_y, *d_z, *d_radius, *d_theta, *d_phi, *d_D_a;
+} ap_halos;
+
+const char* ap_last_error(void);
+int ap_version(void);
+
+/* hp.query_disc per halo (Canvas.Disc.gen_pixel_index, paint_bucket.py:1215-1229), counts only.
+ * d_n_pix[n] (required), d_n_rings[n] (optional).  If d_rmin/d_rmax are non-NULL they receive
+ * min/max of R = D_a * angdist over each halo's pixels (gen_cent2pix_mpc, :1266-1273), i.e.
+ * R.min()/R.max() of utils.sample_array (lib/utils.py:411-412); +inf/-inf for empty discs.   */
+int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
+                  int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream);
+
+/* Flat (halo, pixel) work list: pixel ids of halo h in ascending order at
+ * d_pix[d_pix_off[h] .. d_pix_off[h+1]) — identical to np.concatenate of gen_pixel_index().
+ * Optional outputs (NULL to skip): d_R[total] = gen_cent2pix_mpc (:1266-1273),
+ * d_R_vec[total*3] = gen_cent2pix_mpc_vec (:1283-1290).                                       */
+int ap_disc_pixels(int64_t nside, const ap_halos* halos, const int64_t* d_pix_off, int64_t* d_pix,
+                   double* d_R, double* d_R_vec, void* stream);
+
+/* np.add.at(canvas.pixels, pixel_index, values) for a flat work list (paint_bucket.py:2387-2389). */
+int ap_scatter_add(int64_t n, const int64_t* d_pix, const double* d_val, double* d_map, void* stream);
+
+/* Painter.spray for a built-in template (paint_bucket.py:2378-2389 fused: disc query, pixel
+ * geometry, template, scatter-add).  h_params[i] is the DEVICE pointer of the i-th template
+ * argument (reference signature order, R/R_vec excluded); h_strides[i] is 1 for a per-halo
+ * array, 0 for a single broadcast value.  d_map is the fp64 HEALPix RING map (12*nside^2),
+ * accumulated in place.  d_n_painted (optional, device uint64) is incremented by the number of
+ * (halo, pixel) pairs painted.                                                               */
+int ap_paint_profile(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
+                     const int32_t* h_strides, int32_t n_params, double* d_map,
+                     unsigned long long* d_n_painted, void* stream);
+
+/* @interpolate support (lib/utils.py:457-521).  Nodes: for halos with n_pix >= n_samples,
+ * sample_array(R, n_samples, method) (:406-425; method 0 = linspace, 1 = logspace with
+ * eps = 1e-3) into d_nodes[n*n_samples] and d_n_nodes[h] = n_samples; else d_n_nodes[h] = 0
+ * (the `len(R) < n_samples` bypass, :510-511).                                               */
+int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d_rmin, const double* d_rmax,
+                   int32_t n_samples, int32_t method, double* d_nodes, int32_t* d_n_nodes, void* stream);
+
+/* Battaglia16.tau_2D at the nodes: one QUADPACK qagie(epsabs=0, epsrel=1e-2) per (halo, node)
+ * (lib/utils.py:445-448 through Battaglia16.py:132-155, :221-239).                           */
+int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double* d_M_200c, const double* d_redshift,
+                     int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes,
+                     double* d_values, void* stream);
+
+/* InterpolatedUnivariateSpline(nodes, values, k=3) per halo -> piecewise-cubic coefficients
+ * d_coef[n*(n_samples-1)*4] (lib/utils.py:519).                                              */
+int ap_spline_build(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,
+                    const int32_t* d_n_nodes, double* d_coef, void* stream);
+
+/* Painter.spray for a tabulated template: value = spline_h(R) * d_scale[h] (d_scale optional).
+ * Halos with d_n_nodes[h] == 0 are skipped (bypass halos are painted by ap_paint_b16_small or
+ * through the flat work list).                                                               */
+int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, const double* d_nodes,
+                   const double* d_coef, const int32_t* d_n_nodes, const double* d_scale, double* d_map,
+                   unsigned long long* d_n_painted, void* stream);
+
+/* The `len(R) < n_samples` branch of Battaglia16.tau_2D_interp / kSZ_T: halos with
+ * 0 < n_pix < n_samples get tau_2D (QUADPACK) evaluated at every pixel (lib/utils.py:510-511). */
+int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
+                       const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
+                       int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream);
+
+/* Canvas.cutouts / stack_cutouts (paint_bucket.py:1601-1743, 1745-1941): healpy
+ * CartesianProj(lonra, latra, xsize, ysize).projmap(map, rot=(lon, lat), vec2pix) per halo.
+ * d_lon_deg/d_lat_deg[n_sel] are the catalog lon/lat (degrees) of the selected halos.
+ * ap_cutouts writes d_out[n_sel*ysize*xsize]; ap_stack_cutouts accumulates
+ * d_stack[ysize*xsize] += sum_h weight_h * cutout_h (d_weight optional).                    */
+int ap_cutouts(int64_t nside, const double* d_map, int64_t n_sel, const double* d_lon_deg,
+               const double* d_lat_deg, double lon0, double lon1, double lat0, double lat1,
+               int32_t xsize, int32_t ysize, double* d_out, void* stream);
+int ap_stack_cutouts(int64_t nside, const double* d_map, int64_t n_sel, const double* d_lon_deg,
+                     const double* d_lat_deg, double lon0, double lon1, double lat0, double lat1,
+                     int32_t xsize, int32_t ysize, const double* d_weight, double* d_stack, void* stream);
+
+/* Host-buffer convenience entry (what bench.py's e2e leg and INTEGRATION.md's stub call):
+ * copies the halo columns and parameters host->device, paints into a device map initialised
+ * from h_map, and copies the map back.  All pointers are HOST pointers.                      */
+int ap_spray_host(int profile, int64_t nside, int64_t n, const double* h_x, const double* h_y,
+                  const double* h_z, const double* h_radius, const double* h_theta, const double* h_phi,
+                  const double* h_D_a, const double* const* h_params, const int32_t* h_strides,
+                  int32_t n_params, double* h_map, uint64_t* h_n_painted);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

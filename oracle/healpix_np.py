@@ -1,0 +1,369 @@
+"""TEST INFRASTRUCTURE — CPU oracle, never imported by the product path.
+
+numpy restatement of the healpy 1.13.0 / healpix_cxx (T_Healpix_Base<int64>, RING scheme)
+primitives that the reference's hot path calls.  healpy is a third-party dependency of the
+reference (requirements.txt:15, pinned ==1.13.0) and is NOT vendored under /root/reference
+and NOT installable here (no network) -> **parity unpinned**: this file restates the
+published HEALPix algorithms (Gorski et al. 2005; healpix_cxx `healpix_base.cc`) and is
+anchored on the reference's call sites:
+
+    hp.query_disc   astropaint/paint_bucket.py:1222
+    hp.pix2ang      astropaint/paint_bucket.py:1199,1238
+    hp.pix2vec      astropaint/paint_bucket.py:1254
+    hp.ang2vec      astropaint/paint_bucket.py:1212
+    hp.ang2pix      astropaint/paint_bucket.py:757,1183
+    hp.vec2pix      astropaint/paint_bucket.py:1721
+    hp.rotator.angdist            astropaint/paint_bucket.py:1264
+    hp.projector.CartesianProj    astropaint/paint_bucket.py:1712 (.projmap :1719)
+
+It is pinned only by construction-true tests (tests/test_oracle_healpix.py): brute-force
+disc membership over all pixels, pix2vec/vec2pix round trips, ring-structure identities.
+"""
+import math
+
+import numpy as np
+
+TWOTHIRD = 2.0 / 3.0
+TWOPI = 2.0 * math.pi
+INV_TWOPI = 1.0 / TWOPI
+HALFPI = 0.5 * math.pi
+
+
+def nside2npix(nside):
+    return 12 * int(nside) * int(nside)
+
+
+class HealpixRing:
+    """Constants of T_Healpix_Base<int64>::SetNside for the RING scheme."""
+
+    def __init__(self, nside):
+        nside = int(nside)
+        assert nside > 0
+        self.nside = nside
+        self.npix = 12 * nside * nside
+        self.ncap = 2 * nside * (nside - 1)
+        self.fact2 = 4.0 / self.npix
+        self.fact1 = (nside << 1) * self.fact2
+
+    # -- healpix_base.cc: ring_above ------------------------------------------------
+    def ring_above(self, z):
+        az = abs(z)
+        if az <= TWOTHIRD:
+            return int(self.nside * (2.0 - 1.5 * z))
+        iring = int(self.nside * math.sqrt(3.0 * (1.0 - az)))
+        return iring if z > 0 else 4 * self.nside - iring - 1
+
+    # -- healpix_base.h: ring2z -----------------------------------------------------
+    def ring2z(self, ring):
+        ns = self.nside
+        if ring < ns:
+            return 1.0 - ring * ring * self.fact2
+        if ring <= 3 * ns:
+            return (2 * ns - ring) * self.fact1
+        ring = 4 * ns - ring
+        return ring * ring * self.fact2 - 1.0
+
+    # -- healpix_base.cc: get_ring_info_small -> (startpix, ringpix, shifted) ------
+    def ring_info(self, ring):
+        ns = self.nside
+        if ring < ns:
+            return 2 * ring * (ring - 1), 4 * ring, True
+        if ring < 3 * ns:
+            return self.ncap + (ring - ns) * 4 * ns, 4 * ns, ((ring - ns) & 1) == 0
+        nr = 4 * ns - ring
+        return self.npix - 2 * nr * (nr + 1), 4 * nr, True
+
+    # -- healpix_base.cc: query_disc_internal, RING, fact == 0 ----------------------
+    def query_disc_ranges(self, vec, radius):
+        """Half-open pixel ranges [a, b) in append order (already sorted, merged)."""
+        x, y, zc = (float(v) for v in vec)
+        # pointing(vec3): the vector need not be normalised
+        theta = math.atan2(math.sqrt(x * x + y * y), zc)
+        phi = math.atan2(y, x)
+        if phi < 0.0:
+            phi += TWOPI
+        ranges = []
+
+        def append(a, b):
+            if b <= a:
+                return
+            if ranges and a <= ranges[-1][1]:
+                if b > ranges[-1][1]:
+                    ranges[-1][1] = b
+            else:
+                ranges.append([a, b])
+
+        if radius >= math.pi:
+            return [[0, self.npix]]
+        cosr = math.cos(radius)
+        z0 = math.cos(theta)
+        den = math.sqrt((1.0 - z0) * (1.0 + z0))
+        xa = 1.0 / den if den != 0.0 else math.inf  # IEEE division as in the C++ (halo on a pole)
+        rlat1 = theta - radius
+        zmax = math.cos(rlat1)
+        irmin = self.ring_above(zmax) + 1
+        if rlat1 <= 0 and irmin > 1:  # north pole in the disc
+            sp, rp, _ = self.ring_info(irmin - 1)
+            append(0, sp + rp)
+        rlat2 = theta + radius
+        zmin = math.cos(rlat2)
+        irmax = self.ring_above(zmin)
+        for iz in range(irmin, irmax + 1):
+            z = self.ring2z(iz)
+            xx = (cosr - z * z0) * xa
+            ysq = 1.0 - z * z - xx * xx
+            if ysq != ysq:      # NaN propagates as in C++: neither (ysq <= 0) nor (dphi > 0)
+                dphi = math.nan
+            else:
+                dphi = 0.0 if ysq <= 0 else math.atan2(math.sqrt(ysq), xx)
+            if dphi > 0:
+                ipix1, nr, shifted = self.ring_info(iz)
+                shift = 0.5 if shifted else 0.0
+                ipix2 = ipix1 + nr - 1
+                ip_lo = int(math.floor(nr * INV_TWOPI * (phi - dphi) - shift)) + 1
+                ip_hi = int(math.floor(nr * INV_TWOPI * (phi + dphi) - shift))
+                if ip_lo <= ip_hi:
+                    if ip_hi >= nr:
+                        ip_lo -= nr
+                        ip_hi -= nr
+                    if ip_lo < 0:
+                        append(ipix1, ipix1 + ip_hi + 1)
+                        append(ipix1 + ip_lo + nr, ipix2 + 1)
+                    else:
+                        append(ipix1 + ip_lo, ipix1 + ip_hi + 1)
+        if rlat2 >= math.pi and irmax + 1 < 4 * self.nside:  # south pole in the disc
+            sp, rp, _ = self.ring_info(irmax + 1)
+            append(sp, self.npix)
+        return ranges
+
+    def query_disc(self, vec, radius, inclusive=False):
+        if inclusive:
+            raise NotImplementedError("inclusive=True (fact=4 oversampling) is not restated")
+        ranges = self.query_disc_ranges(vec, radius)
+        if not ranges:
+            return np.empty(0, dtype=np.int64)
+        return np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in ranges])
+
+    # -- healpix_base.cc: pix2loc (RING) -> z, phi, sth, have_sth -------------------
+    def pix2loc(self, pix):
+        pix = np.atleast_1d(np.asarray(pix, dtype=np.int64))
+        ns, npix, ncap = self.nside, self.npix, self.ncap
+        z = np.empty(pix.shape, dtype=np.float64)
+        phi = np.empty(pix.shape, dtype=np.float64)
+        sth = np.zeros(pix.shape, dtype=np.float64)
+        have = np.zeros(pix.shape, dtype=bool)
+
+        north = pix < ncap
+        south = pix >= npix - ncap
+        eq = ~(north | south)
+
+        if north.any():
+            p = pix[north]
+            iring = (1 + _isqrt(1 + 2 * p)) >> 1
+            iphi = (p + 1) - 2 * iring * (iring - 1)
+            tmp = (iring * iring) * self.fact2
+            zz = 1.0 - tmp
+            z[north] = zz
+            big = zz > 0.99
+            s = np.zeros_like(zz)
+            s[big] = np.sqrt(tmp[big] * (2.0 - tmp[big]))
+            sth[north] = s
+            have[north] = big
+            phi[north] = (iphi - 0.5) * HALFPI / iring
+        if eq.any():
+            p = pix[eq]
+            nl4 = 4 * ns
+            ip = p - ncap
+            tmp = ip // nl4
+            iring = tmp + ns
+            iphi = ip - nl4 * tmp + 1
+            fodd = np.where(((iring + ns) & 1) != 0, 1.0, 0.5)
+            z[eq] = (2 * ns - iring) * self.fact1
+            phi[eq] = (iphi - fodd) * math.pi * 0.75 * self.fact1
+        if south.any():
+            p = pix[south]
+            ip = npix - p
+            iring = (1 + _isqrt(2 * ip - 1)) >> 1
+            iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1))
+            tmp = (iring * iring) * self.fact2
+            zz = tmp - 1.0
+            z[south] = zz
+            big = zz < -0.99
+            s = np.zeros_like(zz)
+            s[big] = np.sqrt(tmp[big] * (2.0 - tmp[big]))
+            sth[south] = s
+            have[south] = big
+            phi[south] = (iphi - 0.5) * HALFPI / iring
+        return z, phi, sth, have
+
+    def pix2ang(self, pix):
+        z, phi, sth, have = self.pix2loc(pix)
+        theta = np.where(have, np.arctan2(sth, z), np.arccos(z))
+        return theta, phi
+
+    def pix2vec(self, pix):
+        z, phi, sth, have = self.pix2loc(pix)
+        s = np.where(have, sth, np.sqrt((1.0 - z) * (1.0 + z)))
+        return s * np.cos(phi), s * np.sin(phi), z
+
+    # -- healpix_base.cc: loc2pix (RING) --------------------------------------------
+    def loc2pix(self, z, phi, sth, have_sth):
+        z = np.asarray(z, dtype=np.float64)
+        phi = np.asarray(phi, dtype=np.float64)
+        sth = np.asarray(sth, dtype=np.float64)
+        have_sth = np.broadcast_to(np.asarray(have_sth, dtype=bool), z.shape)
+        ns, npix, ncap = self.nside, self.npix, self.ncap
+        za = np.abs(z)
+        tt = _fmodulo(phi * (1.0 / HALFPI), 4.0)
+        pix = np.empty(z.shape, dtype=np.int64)
+
+        eq = za <= TWOTHIRD
+        if eq.any():
+            nl4 = 4 * ns
+            t1 = ns * (0.5 + tt[eq])
+            t2 = ns * z[eq] * 0.75
+            jp = (t1 - t2).astype(np.int64)
+            jm = (t1 + t2).astype(np.int64)
+            ir = ns + 1 + jp - jm
+            kshift = 1 - (ir & 1)
+            t = jp + jm - ns + kshift + 1 + nl4 + nl4
+            ip = (t >> 1) & (nl4 - 1) if (ns & (ns - 1)) == 0 else (t >> 1) % nl4
+            pix[eq] = ncap + (ir - 1) * nl4 + ip
+        po = ~eq
+        if po.any():
+            ttp = tt[po]
+            zp = z[po]
+            zap = za[po]
+            tp = ttp - ttp.astype(np.int64)
+            use_sth = (zap >= 0.99) & have_sth[po]
+            with np.errstate(invalid="ignore"):
+                tmp = np.where(use_sth,
+                               ns * sth[po] / np.sqrt((1.0 + zap) / 3.0),
+                               ns * np.sqrt(3.0 * (1.0 - zap)))
+            jp = (tp * tmp).astype(np.int64)
+            jm = ((1.0 - tp) * tmp).astype(np.int64)
+            ir = jp + jm + 1
+            ip = (ttp * ir).astype(np.int64)
+            ip = np.where(ip >= 4 * ir, ip - 4 * ir, ip)  # imodulo(ip, 4*ir)
+            pix[po] = np.where(zp > 0, 2 * ir * (ir - 1) + ip, npix - 2 * ir * (ir + 1) + ip)
+        return pix
+
+    def vec2pix(self, x, y, z):
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        z = np.asarray(z, dtype=np.float64)
+        xl = 1.0 / np.sqrt(x * x + y * y + z * z)
+        phi = np.arctan2(y, x)  # safe_atan2
+        nz = z * xl
+        sth = np.sqrt(x * x + y * y) * xl
+        return self.loc2pix(nz, phi, sth, ~(np.abs(nz) < 0.99))
+
+    def ang2pix(self, theta, phi):
+        theta = np.asarray(theta, dtype=np.float64)
+        phi = np.asarray(phi, dtype=np.float64)
+        z = np.cos(theta)
+        near_pole = (theta < 0.01) | (theta > 3.14159 - 0.01)
+        sth = np.where(near_pole, np.sin(theta), 0.0)
+        return self.loc2pix(z, phi, sth, near_pole)
+
+
+def _isqrt(v):
+    """Integer square root of int64 arrays (healpix isqrt: double sqrt + fix-up)."""
+    v = np.asarray(v, dtype=np.int64)
+    r = np.sqrt(v.astype(np.float64) + 0.5).astype(np.int64)
+    r = np.where(r * r > v, r - 1, r)
+    r = np.where((r + 1) * (r + 1) <= v, r + 1, r)
+    return r
+
+
+def _fmodulo(v1, v2):
+    """healpix fmodulo: result in [0, v2)."""
+    v1 = np.asarray(v1, dtype=np.float64)
+    out = np.where(v1 >= 0, np.where(v1 < v2, v1, np.fmod(v1, v2)), 0.0)
+    neg = v1 < 0
+    if neg.any():
+        tmp = np.fmod(v1[neg], v2) + v2
+        out = out.copy()
+        out[neg] = np.where(tmp == v2, 0.0, tmp)
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# healpy/rotator.py
+# ---------------------------------------------------------------------------------
+def dir2vec(theta, phi):
+    """healpy.rotator.dir2vec (lonlat=False)."""
+    theta = np.asarray(theta, dtype=np.float64)
+    phi = np.asarray(phi, dtype=np.float64)
+    st = np.sin(theta)
+    return np.array([st * np.cos(phi), st * np.sin(phi), np.cos(theta) + 0.0 * phi])
+
+
+def ang2vec(theta, phi):
+    """healpy.ang2vec: returns shape (3,) for scalars or (n, 3)."""
+    v = dir2vec(theta, phi)
+    return v.T if v.ndim == 2 else v
+
+
+def angdist(dir1, dir2):
+    """healpy.rotator.angdist for (theta, phi) inputs: atan2(|v1 x v2|, v1 . v2)."""
+    dir1 = np.asarray(dir1, dtype=np.float64)
+    dir2 = np.asarray(dir2, dtype=np.float64)
+    v1 = dir2vec(dir1[0], dir1[1]).reshape(3, -1)
+    v2 = dir2vec(dir2[0], dir2[1]).reshape(3, -1)
+    cx = v1[1] * v2[2] - v1[2] * v2[1]
+    cy = v1[2] * v2[0] - v1[0] * v2[2]
+    cz = v1[0] * v2[1] - v1[1] * v2[0]
+    vec_prod = np.sqrt(cx * cx + cy * cy + cz * cz)
+    scal_prod = (v1 * v2).sum(axis=0)
+    return np.arctan2(vec_prod, scal_prod)
+
+
+def rotator_inverse_matrix(lon_deg, lat_deg):
+    """Matrix of healpy Rotator(rot=(lon, lat)).I : maps the image frame (halo on +x) to the sky.
+
+    healpy euler_matrix_new(a1=lon, a2=-lat, a3=0, Z=True) builds M = m3 @ m2 @ m1 taking the
+    sky direction (lon, lat) to +x; the inverse is its transpose.
+    """
+    a1 = math.radians(lon_deg)
+    a2 = -math.radians(lat_deg)
+    c1, s1 = math.cos(a1), math.sin(a1)
+    c2, s2 = math.cos(a2), math.sin(a2)
+    m1 = np.array([[c1, -s1, 0.0], [s1, c1, 0.0], [0.0, 0.0, 1.0]])  # rot about Z by a1
+    m2 = np.array([[c2, 0.0, s2], [0.0, 1.0, 0.0], [-s2, 0.0, c2]])  # rot about Y by a2
+    return m1 @ m2
+
+
+def cartesian_projmap(hpx, healpix_map, lon_deg, lat_deg, lonra, latra, xsize, ysize=None):
+    """healpy.projector.CartesianProj(lonra, latra, xsize, ysize).projmap(map, rot=(lon, lat),
+    vec2pix_func=partial(hp.vec2pix, nside)) as called at paint_bucket.py:1712-1721.
+
+    Returns the (ysize, xsize) float64 image (nearest-pixel lookup, 'astro' flip).
+    """
+    lon0, lon1 = float(lonra[0]), float(lonra[1])
+    lat0, lat1 = float(latra[0]), float(latra[1])
+    # CartesianProj.set_proj_plane_info: lonra[1] = lonra[0] + (np.mod(lonra[1]-lonra[0], 360) or 360)
+    dl = math.fmod(lon1 - lon0, 360.0)
+    if dl < 0:
+        dl += 360.0
+    if dl == 0:
+        dl = 360.0
+    lon1 = lon0 + dl
+    if ysize is None:
+        ratio = (lat1 - lat0) / (lon1 - lon0)
+        ysize = int(round(xsize * ratio))
+    # ij2xy: pixel centres
+    j = np.arange(xsize, dtype=np.float64)
+    i = np.arange(ysize, dtype=np.float64)
+    x = lon0 + (j + 0.5) * ((lon1 - lon0) / xsize)
+    y = lat0 + (i + 0.5) * ((lat1 - lat0) / ysize)
+    X, Y = np.meshgrid(x, y)  # shape (ysize, xsize)
+    # xy2vec: flip = -1 ('astro'); theta = pi/2 - y, phi = flip * x
+    theta = HALFPI - np.radians(Y)
+    phi = -np.radians(X)
+    st = np.sin(theta)
+    v = np.array([st * np.cos(phi), st * np.sin(phi), np.cos(theta)])
+    m = rotator_inverse_matrix(lon_deg, lat_deg)
+    vs = np.tensordot(m, v, axes=(1, 0))
+    pix = hpx.vec2pix(vs[0], vs[1], vs[2])
+    return np.asarray(healpix_map)[pix]
