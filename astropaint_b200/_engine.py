@@ -1,0 +1,254 @@
+"""Device-side plumbing of the painting path: catalog columns in HBM and kernel launches.
+
+PyTorch is used for device memory, streams and (in `parallel.py`) torch.distributed; every
+compute step is a call into libastropaint_b200.so (csrc/kernels.cu) through `_capi`.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import ApHalos, c_ptr, c_i32, ptr, check
+from .lib import transform
+
+GEOMETRY_COLUMNS = ("x", "y", "z", "theta", "phi", "D_a")
+
+#: (halo, pixel) pairs per batch of the flat work-list path (R: 8 B, pixel id: 8 B, value: 8 B each)
+FLAT_BATCH_PIXELS = 1 << 25
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("astropaint_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _capi.lib()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def stream_ptr():
+    return c_ptr(torch.cuda.current_stream().cuda_stream)
+
+
+def to_device(arr, device):
+    """host float64 column -> device tensor (pinned staging so the copy is a single DMA)."""
+    a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64))
+    t = torch.from_numpy(a)
+    if t.numel() > (1 << 16):
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
+
+
+class DeviceHalos:
+    """Catalog columns of the halos being painted, resident in HBM (SoA, fp64).
+
+    `radius` is R_times * arcmin2rad(R_ang_200c), computed on the host with the reference's own
+    numpy expressions (paint_bucket.py:1226-1227, lib/transform.py:143-150) so that the disc
+    radius rounds identically.
+    """
+
+    def __init__(self, data, R_times, device, rows=None, pinned=None):
+        self.device = device
+        self._data = data
+        self._rows = rows
+        self._pinned = pinned or {}
+        self.cols = {}
+        n_all = len(data)
+        self.index = np.arange(n_all) if rows is None else np.asarray(rows)
+        self.n = len(self.index)
+        radius = R_times * transform.arcmin2rad(self._host_col("R_ang_200c"))
+        self.cols["__radius__"] = to_device(radius, device)
+        for k in GEOMETRY_COLUMNS:
+            self.col(k)
+
+    def _host_col(self, name):
+        if name in self._pinned:
+            v = self._pinned[name]
+            return v if self._rows is None else v[self._rows]
+        v = self._data[name].values
+        return v if self._rows is None else v[self._rows]
+
+    def col(self, name):
+        if name not in self.cols:
+            if name in self._pinned and self._rows is None:
+                self.cols[name] = self._pinned[name].to(self.device, non_blocking=True)
+            else:
+                self.cols[name] = to_device(self._host_col(name), self.device)
+        return self.cols[name]
+
+    def struct(self, lo=0, hi=None):
+        hi = self.n if hi is None else hi
+        s = ApHalos()
+        s.n = hi - lo
+
+        def p(name):
+            t = self.cols[name]
+            return t.data_ptr() + 8 * lo
+
+        s.d_x, s.d_y, s.d_z = p("x"), p("y"), p("z")
+        s.d_radius = p("__radius__")
+        s.d_theta, s.d_phi, s.d_D_a = p("theta"), p("phi"), p("D_a")
+        return s
+
+    def subset(self, idx):
+        """New DeviceHalos holding rows `idx` (positions within this object)."""
+        sub = DeviceHalos.__new__(DeviceHalos)
+        sub.device = self.device
+        sub._data = self._data
+        sub._pinned = {}
+        sub._rows = self.index[idx]
+        sub.index = sub._rows
+        sub.n = len(idx)
+        ti = torch.as_tensor(np.asarray(idx), device=self.device, dtype=torch.int64)
+        sub.cols = {k: v.index_select(0, ti) for k, v in self.cols.items()}
+        return sub
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel wrappers
+# ---------------------------------------------------------------------------------------------
+def disc_count(halos, nside, inclusive=False, want_range=False, want_rings=False):
+    L = _capi.lib()
+    dev = halos.device
+    n_pix = torch.empty(halos.n, dtype=torch.int64, device=dev)
+    n_rings = torch.empty(halos.n, dtype=torch.int32, device=dev) if want_rings else None
+    rmin = torch.empty(halos.n, dtype=torch.float64, device=dev) if want_range else None
+    rmax = torch.empty(halos.n, dtype=torch.float64, device=dev) if want_range else None
+    s = halos.struct()
+    check(L.ap_disc_count(nside, C.byref(s), int(bool(inclusive)), ptr(n_pix), ptr(n_rings), ptr(rmin),
+                          ptr(rmax), stream_ptr()))
+    return n_pix, n_rings, rmin, rmax
+
+
+def disc_pixels(halos, nside, n_pix, lo=0, hi=None, want_R=False, want_vec=False):
+    """Flat pixel list of halos [lo, hi): returns (offsets[int64, hi-lo+1], pix, R or None, R_vec or None)."""
+    L = _capi.lib()
+    dev = halos.device
+    hi = halos.n if hi is None else hi
+    off = torch.zeros(hi - lo + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(n_pix[lo:hi], 0, out=off[1:])
+    total = int(off[-1].item())
+    pix = torch.empty(total, dtype=torch.int64, device=dev)
+    R = torch.empty(total, dtype=torch.float64, device=dev) if want_R else None
+    Rv = torch.empty((total, 3), dtype=torch.float64, device=dev) if want_vec else None
+    s = halos.struct(lo, hi)
+    check(L.ap_disc_pixels(nside, C.byref(s), ptr(off), ptr(pix), ptr(R), ptr(Rv), stream_ptr()))
+    return off, pix, R, Rv
+
+
+def scatter_add(pix, val, d_map):
+    check(_capi.lib().ap_scatter_add(pix.numel(), ptr(pix), ptr(val), ptr(d_map), stream_ptr()))
+
+
+def paint_profile(halos, nside, profile_id, params, d_map, d_count=None):
+    """params: list of 1-element (broadcast) or n-element device tensors in device-argument order."""
+    L = _capi.lib()
+    n = len(params)
+    arr = (c_ptr * max(n, 1))()
+    strides = (c_i32 * max(n, 1))()
+    for i, t in enumerate(params):
+        assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+        arr[i] = t.data_ptr()
+        strides[i] = 0 if t.numel() == 1 and halos.n != 1 else 1
+        if strides[i] == 1 and t.numel() != halos.n:
+            raise ValueError(f"template argument #{i} has {t.numel()} values for {halos.n} halos")
+    s = halos.struct()
+    check(L.ap_paint_profile(int(profile_id), nside, C.byref(s), arr, strides, n, ptr(d_map), ptr(d_count),
+                             stream_ptr()))
+
+
+def table_nodes(halos, n_pix, rmin, rmax, n_samples, method):
+    L = _capi.lib()
+    dev = halos.device
+    nodes = torch.empty((halos.n, n_samples), dtype=torch.float64, device=dev)
+    n_nodes = torch.empty(halos.n, dtype=torch.int32, device=dev)
+    check(L.ap_table_nodes(halos.n, ptr(n_pix), ptr(rmin), ptr(rmax), n_samples,
+                           {"linspace": 0, "logspace": 1}[method], ptr(nodes), ptr(n_nodes), stream_ptr()))
+    return nodes, n_nodes
+
+
+def b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes):
+    values = torch.empty_like(nodes)
+    check(_capi.lib().ap_b16_tau_nodes(halos.n, ptr(R200), ptr(M200), ptr(zred), nodes.shape[1], ptr(nodes),
+                                       ptr(n_nodes), ptr(values), stream_ptr()))
+    return values
+
+
+def spline_build(nodes, values, n_nodes):
+    n, ns = nodes.shape
+    coef = torch.empty((n, ns - 1, 4), dtype=torch.float64, device=nodes.device)
+    check(_capi.lib().ap_spline_build(n, ns, ptr(nodes), ptr(values), ptr(n_nodes), ptr(coef), stream_ptr()))
+    return coef
+
+
+def paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count=None):
+    s = halos.struct()
+    check(_capi.lib().ap_paint_table(nside, C.byref(s), nodes.shape[1], ptr(nodes), ptr(coef), ptr(n_nodes),
+                                     ptr(scale), ptr(d_map), ptr(d_count), stream_ptr()))
+
+
+def paint_b16_small(halos, nside, R200, M200, zred, scale, n_pix, n_samples, d_map, d_count=None):
+    s = halos.struct()
+    check(_capi.lib().ap_paint_b16_small(nside, C.byref(s), ptr(R200), ptr(M200), ptr(zred), ptr(scale),
+                                         ptr(n_pix), n_samples, ptr(d_map), ptr(d_count), stream_ptr()))
+
+
+def cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize):
+    out = torch.empty((lon.numel(), ysize, xsize), dtype=torch.float64, device=d_map.device)
+    check(_capi.lib().ap_cutouts(nside, ptr(d_map), lon.numel(), ptr(lon), ptr(lat), float(lon_range[0]),
+                                 float(lon_range[1]), float(lat_range[0]), float(lat_range[1]), xsize, ysize,
+                                 ptr(out), stream_ptr()))
+    return out
+
+
+def stack_cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize, weight=None, stack=None):
+    if stack is None:
+        stack = torch.zeros((ysize, xsize), dtype=torch.float64, device=d_map.device)
+    check(_capi.lib().ap_stack_cutouts(nside, ptr(d_map), lon.numel(), ptr(lon), ptr(lat), float(lon_range[0]),
+                                       float(lon_range[1]), float(lat_range[0]), float(lat_range[1]), xsize,
+                                       ysize, ptr(weight), ptr(stack), stream_ptr()))
+    return stack
+
+
+# ---------------------------------------------------------------------------------------------
+# spray flows
+# ---------------------------------------------------------------------------------------------
+def spray_flat(halos, nside, template, R_mode, host_cols, d_map, d_count=None, inclusive=False):
+    """Arbitrary Python template: device disc query + geometry + scatter, template on the host.
+
+    Follows the reference loop exactly (paint_bucket.py:2380-2389): one call per halo with the
+    halo's full R (or R_vec) array and its catalog row as keyword arguments.
+    """
+    n_pix, _, _, _ = disc_count(halos, nside, inclusive)
+    counts = n_pix.cpu().numpy()
+    bounds = [0]
+    run = 0
+    for h in range(halos.n):
+        if run > 0 and run + counts[h] > FLAT_BATCH_PIXELS:
+            bounds.append(h)
+            run = 0
+        run += counts[h]
+    bounds.append(halos.n)
+    names = list(host_cols.keys())
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        if hi == lo:
+            continue
+        off, pix, R, Rv = disc_pixels(halos, nside, n_pix, lo, hi, want_R=(R_mode == "R"),
+                                      want_vec=(R_mode == "R_vec"))
+        off_h = off.cpu().numpy()
+        geo = (R if R_mode == "R" else Rv).cpu().numpy()
+        vals = np.empty(off_h[-1], dtype=np.float64)
+        for h in range(lo, hi):
+            a, b = off_h[h - lo], off_h[h - lo + 1]
+            kw = {k: host_cols[k][h] for k in names}
+            kw[R_mode] = geo[a:b]
+            v = template(**kw)
+            if np.iscomplexobj(v):
+                v = np.real(v)
+            vals[a:b] = v
+        if off_h[-1] > 0:
+            scatter_add(pix, to_device(vals, halos.device), d_map)
+        if d_count is not None:
+            d_count += int(off_h[-1])
+    return n_pix

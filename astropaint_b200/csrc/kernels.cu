@@ -495,6 +495,33 @@ extern "C" int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double*
   return 0;
 }
 
+// diagnostic: tau_2D(R) with QUADPACK's own error estimate and evaluation count
+__global__ void __launch_bounds__(128) b16_tau_eval_kernel(int64_t n, const double* R, const double* R200,
+                                                           const double* M200, const double* zred, double* result,
+                                                           double* abserr, int32_t* neval) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double ctx[kCtx];
+  b16_setup(R200[t], M200[t], zred[t], ctx);
+  QagiResult q;
+  result[t] = b16_tau_2D(ctx, R[t], &q);
+  if (abserr) abserr[t] = q.abserr;
+  if (neval) neval[t] = q.neval;
+}
+
+extern "C" int ap_b16_tau_eval(int64_t n, const double* d_R, const double* d_R_200c, const double* d_M_200c,
+                               const double* d_redshift, double* d_result, double* d_abserr, int32_t* d_neval,
+                               void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n == 0) return 0;
+  if (!d_R || !d_R_200c || !d_M_200c || !d_redshift || !d_result) return fail("b16_tau_eval: NULL pointer");
+  int threads = 128;
+  b16_tau_eval_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n, d_R, d_R_200c, d_M_200c, d_redshift, d_result, d_abserr, d_neval);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void __launch_bounds__(128) spline_build_kernel(int64_t n, int32_t ns, const double* nodes,
                                                            const double* values, const int32_t* n_nodes, double* coef) {
   int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -25,52 +25,73 @@ struct QagiResult {
 };
 
 // 15-point transformed Gauss-Kronrod rule on (a, b) subset of (0, 1], x = boun + (1-t)/t.
+// The node/weight tables are compile-time scalars and the pair loop is unrolled by hand: with
+// local `const double xgk[8]` arrays nvcc 12.9 (sm_100a, -O3) overlapped the tables' local-memory
+// slots with the caller's epsilon table after inlining (device results diverged from the host
+// build), so no table lives in local memory.
+namespace gk15 {
+constexpr double x0 = 0.991455371120812639206854697526329, x1 = 0.949107912342758524526189684047851,
+                 x2 = 0.864864423359769072789712788640926, x3 = 0.741531185599394439863864773280788,
+                 x4 = 0.586087235467691130294144838258730, x5 = 0.405845151377397166906606412076961,
+                 x6 = 0.207784955007898467600689403773245;
+constexpr double g1 = 0.129484966168869693270611432679082, g3 = 0.279705391489276667901467771423780,
+                 g5 = 0.381830050505118944950369775488975, g7 = 0.417959183673469387755102040816327;
+constexpr double k0 = 0.022935322010529224963732008058970, k1 = 0.063092092629978553290700663189204,
+                 k2 = 0.104790010322250183839876322541518, k3 = 0.140653259715525918745189590510238,
+                 k4 = 0.169004726639267902826583426598550, k5 = 0.190350578064785409913256402421014,
+                 k6 = 0.204432940075298892414161999234649, k7 = 0.209482141084727828012999174891714;
+}  // namespace gk15
+
 template <class F>
-AP_HD_NOINLINE void qk15i(const F& f, double boun, double a, double b, double& result,
-                          double& abserr, double& resabs, double& resasc) {
-  const double wg[8] = {0.0, 0.129484966168869693270611432679082, 0.0,
-                        0.279705391489276667901467771423780, 0.0,
-                        0.381830050505118944950369775488975, 0.0,
-                        0.417959183673469387755102040816327};
-  const double xgk[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
-                         0.864864423359769072789712788640926, 0.741531185599394439863864773280788,
-                         0.586087235467691130294144838258730, 0.405845151377397166906606412076961,
-                         0.207784955007898467600689403773245, 0.0};
-  const double wgk[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
-                         0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
-                         0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
-                         0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
-  double fv1[7], fv2[7];
+AP_HD void qk15i(const F& f, double boun, double a, double b, double& result, double& abserr,
+                 double& resabs, double& resasc) {
   double centr = AP_MUL(0.5, AP_ADD(a, b));
   double hlgth = AP_MUL(0.5, AP_SUB(b, a));
   double tabsc1 = AP_ADD(boun, AP_SUB(1.0, centr) / centr);
   double fval1 = f(tabsc1);
   double fc = (fval1 / centr) / centr;
-  double resg = AP_MUL(wg[7], fc);
-  double resk = AP_MUL(wgk[7], fc);
+  double resg = AP_MUL(gk15::g7, fc);
+  double resk = AP_MUL(gk15::k7, fc);
   resabs = fabs(resk);
-  for (int j = 0; j < 7; ++j) {
-    double absc = AP_MUL(hlgth, xgk[j]);
-    double absc1 = AP_SUB(centr, absc);
-    double absc2 = AP_ADD(centr, absc);
-    double t1 = AP_ADD(boun, AP_SUB(1.0, absc1) / absc1);
-    double t2 = AP_ADD(boun, AP_SUB(1.0, absc2) / absc2);
-    double f1 = f(t1);
-    double f2 = f(t2);
-    f1 = (f1 / absc1) / absc1;
-    f2 = (f2 / absc2) / absc2;
-    fv1[j] = f1;
-    fv2[j] = f2;
-    double fsum = AP_ADD(f1, f2);
-    resg = AP_ADD(resg, AP_MUL(wg[j], fsum));
-    resk = AP_ADD(resk, AP_MUL(wgk[j], fsum));
-    resabs = AP_ADD(resabs, AP_MUL(wgk[j], AP_ADD(fabs(f1), fabs(f2))));
+  double v1_0, v1_1, v1_2, v1_3, v1_4, v1_5, v1_6, v2_0, v2_1, v2_2, v2_3, v2_4, v2_5, v2_6;
+#define AP_GK_PAIR(XGK, WG, WGK, V1, V2)                                                  \
+  {                                                                                       \
+    double absc = AP_MUL(hlgth, XGK);                                                     \
+    double absc1 = AP_SUB(centr, absc);                                                   \
+    double absc2 = AP_ADD(centr, absc);                                                   \
+    double t1 = AP_ADD(boun, AP_SUB(1.0, absc1) / absc1);                                 \
+    double t2 = AP_ADD(boun, AP_SUB(1.0, absc2) / absc2);                                 \
+    double f1 = f(t1);                                                                    \
+    double f2 = f(t2);                                                                    \
+    f1 = (f1 / absc1) / absc1;                                                            \
+    f2 = (f2 / absc2) / absc2;                                                            \
+    V1 = f1;                                                                              \
+    V2 = f2;                                                                              \
+    double fsum = AP_ADD(f1, f2);                                                         \
+    resg = AP_ADD(resg, AP_MUL(WG, fsum));                                                \
+    resk = AP_ADD(resk, AP_MUL(WGK, fsum));                                               \
+    resabs = AP_ADD(resabs, AP_MUL(WGK, AP_ADD(fabs(f1), fabs(f2))));                     \
   }
+  AP_GK_PAIR(gk15::x0, 0.0, gk15::k0, v1_0, v2_0)
+  AP_GK_PAIR(gk15::x1, gk15::g1, gk15::k1, v1_1, v2_1)
+  AP_GK_PAIR(gk15::x2, 0.0, gk15::k2, v1_2, v2_2)
+  AP_GK_PAIR(gk15::x3, gk15::g3, gk15::k3, v1_3, v2_3)
+  AP_GK_PAIR(gk15::x4, 0.0, gk15::k4, v1_4, v2_4)
+  AP_GK_PAIR(gk15::x5, gk15::g5, gk15::k5, v1_5, v2_5)
+  AP_GK_PAIR(gk15::x6, 0.0, gk15::k6, v1_6, v2_6)
+#undef AP_GK_PAIR
   double reskh = AP_MUL(resk, 0.5);
-  resasc = AP_MUL(wgk[7], fabs(AP_SUB(fc, reskh)));
-  for (int j = 0; j < 7; ++j)
-    resasc = AP_ADD(resasc, AP_MUL(wgk[j], AP_ADD(fabs(AP_SUB(fv1[j], reskh)),
-                                                    fabs(AP_SUB(fv2[j], reskh)))));
+  resasc = AP_MUL(gk15::k7, fabs(AP_SUB(fc, reskh)));
+#define AP_GK_ASC(WGK, V1, V2) \
+  resasc = AP_ADD(resasc, AP_MUL(WGK, AP_ADD(fabs(AP_SUB(V1, reskh)), fabs(AP_SUB(V2, reskh)))));
+  AP_GK_ASC(gk15::k0, v1_0, v2_0)
+  AP_GK_ASC(gk15::k1, v1_1, v2_1)
+  AP_GK_ASC(gk15::k2, v1_2, v2_2)
+  AP_GK_ASC(gk15::k3, v1_3, v2_3)
+  AP_GK_ASC(gk15::k4, v1_4, v2_4)
+  AP_GK_ASC(gk15::k5, v1_5, v2_5)
+  AP_GK_ASC(gk15::k6, v1_6, v2_6)
+#undef AP_GK_ASC
   result = AP_MUL(resk, hlgth);
   resasc = AP_MUL(resasc, hlgth);
   resabs = AP_MUL(resabs, hlgth);
@@ -127,6 +148,10 @@ AP_HD_NOINLINE void qelg(int& n, double* epstab, double& result, double& abserr,
     }
     double ss = AP_SUB(AP_ADD(1.0 / delta1, 1.0 / delta2), 1.0 / delta3);
     double epsinf = fabs(AP_MUL(ss, e1));
+#ifdef AP_QAGI_TRACE
+    printf("   qelg i=%d n=%d e0=%.17g e1=%.17g e2=%.17g e3=%.17g d1=%.17g d2=%.17g d3=%.17g ss=%.17g\n", i, n, e0, e1, e2,
+           e3, delta1, delta2, delta3, ss);
+#endif
     if (!(epsinf > 1.0e-4)) {
       n = i + i - 1;
       break;
@@ -317,6 +342,10 @@ AP_HD_NOINLINE QagiResult qagi_upper(const F& f, double bound, double epsabs, do
         elist[last - 1] = error2;
       }
       qpsrt(limit, last, maxerr, errmax, elist, iord, nrmax);
+#ifdef AP_QAGI_TRACE
+      printf(" last=%d a1=%.17g b2=%.17g area1=%.17g e1=%.17g area2=%.17g e2=%.17g errsum=%.17g\n", last, a1, b2, area1,
+             error1, area2, error2, errsum);
+#endif
       if (errsum <= errbnd) { exit_label = 115; break; }
       if (ier != 0) { exit_label = 100; break; }
       if (last == 2) {
@@ -351,6 +380,10 @@ AP_HD_NOINLINE QagiResult qagi_upper(const F& f, double bound, double epsabs, do
       numrl2 += 1;
       rlist2[numrl2 - 1] = area;
       qelg(numrl2, rlist2, reseps, abseps, res3la, nres);
+#ifdef AP_QAGI_TRACE
+      printf("  last=%d area=%.17g errsum=%.17g numrl2=%d nres=%d reseps=%.17g abseps=%.17g\n", last, area, errsum,
+             numrl2, nres, reseps, abseps);
+#endif
       ktmin += 1;
       if (ktmin > 5 && abserr < AP_MUL(1.0e-3, errsum)) ier = 5;
       if (!(abseps >= abserr)) {

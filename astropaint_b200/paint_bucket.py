@@ -1,0 +1,727 @@
+"""Catalog / Canvas / Painter — the reference's object API over the B200 painting path.
+
+Mirrors `astropaint/paint_bucket.py` of syasini/AstroPaint for the hot path only:
+
+    Catalog(data)                              paint_bucket.py:41-364   (host, pandas; once per catalog)
+    Canvas(catalog, nside, R_times, inclusive) paint_bucket.py:773-955, 1175-1323, 1601-1966
+    Painter(template).spray(canvas, **kwargs)  paint_bucket.py:2263-2676
+
+Everything per (halo, pixel) runs in hand-written sm_100a CUDA (csrc/kernels.cu) behind the C ABI
+of include/astropaint_b200.h.  There is no CPU implementation of the path in this package.
+"""
+import inspect
+import os
+import re
+
+import numpy as np
+import pandas as pd
+
+from .lib import transform
+from . import _engine as eng
+
+verbose = True
+
+
+def _say(*a):
+    if verbose:
+        print(*a)
+
+
+#########################################################
+#                  Halo Catalog Object
+#########################################################
+class Catalog:
+    """Halo catalog: positions [Mpc], velocities [km/s], M_200c [M_sun] (+ derived columns)."""
+
+    def __init__(self, data=None, calculate_redshifts=False, default_redshift=0):
+        self._build_counter = 0
+        self.calculate_redshifts = calculate_redshifts
+        self.default_redshift = default_redshift
+        if data is None:
+            self.data = self._initialize_catalog(1)
+        elif isinstance(data, str):
+            if re.match(".*random.*box", data, re.IGNORECASE):
+                self.generate_random_box()
+            elif re.match(".*random.*shell", data, re.IGNORECASE):
+                self.generate_random_shell()
+            elif re.match(".*test.*", data, re.IGNORECASE):
+                self.generate_test_box(configuration=["all"])
+            else:
+                self.load_from_csv(data)
+        else:
+            self.data = data
+
+    # ------------------------ properties ------------------------
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, val):
+        self._data = pd.DataFrame(val).reset_index(drop=True)
+        self.size = len(self._data)
+        self.box_size = self._get_box_size()
+        if self._build_counter > 0:
+            _say("Catalog data has been modified...\n")
+        self.build_dataframe(calculate_redshifts=self.calculate_redshifts,
+                             default_redshift=self.default_redshift)
+
+    # ------------------------ sample data ------------------------
+    @staticmethod
+    def _data_dir():
+        return os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+    def load_from_csv(self, sample_name="MICE"):
+        if not sample_name.endswith(".csv"):
+            sample_name += ".csv"
+        fname = sample_name if os.path.exists(sample_name) else os.path.join(self._data_dir(), sample_name)
+        _say(f"Catalog loaded from:\n{fname}")
+        self.data = pd.read_csv(fname, index_col=0)
+
+    def save_to_csv(self, sample_name):
+        if not sample_name.endswith(".csv"):
+            sample_name += ".csv"
+        fname = sample_name if os.path.dirname(sample_name) else os.path.join(self._data_dir(), sample_name)
+        os.makedirs(os.path.dirname(fname), exist_ok=True)
+        self.data.to_csv(fname)
+        _say(f"Catalog saved to:\n{fname}")
+
+    @staticmethod
+    def _initialize_catalog(n_tot):
+        names = ["x", "y", "z", "v_x", "v_y", "v_z", "M_200c"]
+        return pd.DataFrame(np.zeros(n_tot, {"names": names, "formats": 7 * [np.float32]}))
+
+    def _random_velocities_and_masses(self, catalog, v_max, mass_min, mass_max, n_tot):
+        v = np.random.uniform(low=-v_max, high=v_max, size=(3, n_tot))
+        catalog["v_x"], catalog["v_y"], catalog["v_z"] = v
+        catalog["M_200c"] = np.exp(np.random.uniform(low=np.log(mass_min), high=np.log(mass_max), size=n_tot))
+
+    def generate_random_box(self, box_size=50, v_max=100, mass_min=1E14, mass_max=1E15, n_tot=50000,
+                            put_on_shell=False, inplace=True):
+        """Uniform random halos in a box centred on the observer (legacy np.random call order of the
+        reference: positions, velocities, log-uniform masses)."""
+        catalog = self._initialize_catalog(n_tot)
+        _say("generating random catalog...\n")
+        x, y, z = np.random.uniform(low=-box_size / 2, high=box_size / 2, size=(3, n_tot))
+        if put_on_shell:
+            (x, y, z) = box_size * np.true_divide((x, y, z), np.linalg.norm((x, y, z), axis=0))
+        catalog["x"], catalog["y"], catalog["z"] = x, y, z
+        self._random_velocities_and_masses(catalog, v_max, mass_min, mass_max, n_tot)
+        if inplace:
+            self.data = pd.DataFrame(catalog)
+        else:
+            return pd.DataFrame(catalog)
+
+    def generate_random_shell(self, shell_radius=50, v_max=100, mass_min=1E14, mass_max=1E15, n_tot=50000,
+                              inplace=True):
+        catalog = self._initialize_catalog(n_tot)
+        _say("generating random catalog...\n")
+        u, v = np.random.uniform(low=0, high=1, size=(2, n_tot))
+        phi = 2 * np.pi * u
+        theta = np.arccos(2 * v - 1)
+        catalog["x"] = np.sin(theta) * np.cos(phi) * shell_radius
+        catalog["y"] = np.sin(theta) * np.sin(phi) * shell_radius
+        catalog["z"] = np.cos(theta) * shell_radius
+        self._random_velocities_and_masses(catalog, v_max, mass_min, mass_max, n_tot)
+        if inplace:
+            self.data = pd.DataFrame(catalog)
+        else:
+            return pd.DataFrame(catalog)
+
+    def generate_test_box(self, configuration=["all"], distance=100, mass=1E15, inplace=True):
+        """Up to six halos on the +-x, +-y, +-z axes."""
+        where = {"front": (1, 0, 0), "back": (-1, 0, 0), "left": (0, 1, 0), "right": (0, -1, 0),
+                 "top": (0, 0, 1), "bottom": (0, 0, -1)}
+        if "all" in configuration:
+            configuration = where.keys()
+        rows = []
+        for key in configuration:
+            x, y, z = where[key]
+            rows.append({"x": x * distance, "y": y * distance, "z": z * distance,
+                         "v_x": 0.0, "v_y": 0.0, "v_z": 0.0, "M_200c": mass})
+        catalog = pd.DataFrame(rows, columns=["x", "y", "z", "v_x", "v_y", "v_z", "M_200c"])
+        if inplace:
+            self.data = catalog
+        else:
+            return catalog
+
+    # ------------------------ methods ------------------------
+    def build_dataframe(self, calculate_redshifts=False, default_redshift=0):
+        """Derived columns the painting path reads (reference: paint_bucket.py:308-364)."""
+        self._build_counter = 1
+        d = self.data
+        x, y, z = (d[k].values.astype(np.float64) for k in ("x", "y", "z"))
+        # cartesian -> spherical: D_c, latitude in [-pi/2, pi/2], longitude in [0, 2 pi)
+        s = np.hypot(x, y)
+        d["D_c"] = np.hypot(s, z)
+        lat = np.arctan2(z, s)
+        lon = np.arctan2(y, x)
+        lon = np.where(lon < 0, lon + 2 * np.pi, lon)
+        if calculate_redshifts:
+            d["redshift"] = transform.D_c_to_redshift(d["D_c"].values)
+        elif "redshift" not in d.columns:
+            d["redshift"] = pd.Series([default_redshift] * len(d))
+        d["lat"], d["lon"] = lat, lon
+        d["theta"] = np.pi / 2 - d["lat"]
+        d["phi"] = d["lon"]
+        d["lon"], d["lat"] = np.rad2deg((d["lon"], d["lat"]))
+        d["D_a"] = transform.D_c_to_D_a(d["D_c"], d["redshift"])
+        d["R_200c"] = transform.M_200c_to_R_200c(d["M_200c"], d["redshift"])
+        d["c_200c"] = transform.M_200c_to_c_200c(d["M_200c"], d["redshift"])
+        d["R_ang_200c"] = transform.radius_to_angsize(d["R_200c"], d["D_a"], arcmin=True)
+        d["rho_s"] = transform.M_200c_to_rho_s(d["M_200c"], d["redshift"], d["R_200c"], d["c_200c"])
+        d["R_s"] = np.true_divide(d["R_200c"], d["c_200c"])
+        J = transform.get_cart2sph_jacobian(d["theta"].values, d["phi"].values)
+        v_cart = np.array([d["v_x"], d["v_y"], d["v_z"]])
+        d["v_r"], d["v_th"], d["v_ph"] = np.einsum("ij...,i...->j...", J, v_cart)
+        d["v_lat"] = -d["v_th"]
+        d["v_lon"] = d["v_ph"]
+
+    def _get_box_size(self):
+        return tuple(self.data[k].max() - self.data[k].min() for k in ("x", "y", "z"))
+
+    def move_to_box_center(self):
+        for k in ("x", "y", "z"):
+            self.data[k] -= (self.data[k].max() + self.data[k].min()) / 2
+        self.data = self.data
+
+    def _cut(self, column, lo, hi, inplace):
+        data = self.data[(self.data[column] > lo) & (self.data[column] < hi)]
+        if inplace:
+            self.data = data
+        else:
+            return data
+
+    def cut_M_200c(self, mass_min=0., mass_max=np.inf, inplace=True):
+        return self._cut("M_200c", mass_min, mass_max, inplace)
+
+    def cut_R_200c(self, R_min=0., R_max=np.inf, inplace=True):
+        return self._cut("R_200c", R_min, R_max, inplace)
+
+    def cut_R_ang_200c(self, R_ang_min=0., R_ang_max=np.inf, inplace=True):
+        return self._cut("R_ang_200c", R_ang_min, R_ang_max, inplace)
+
+    def cut_D_c(self, D_min=0., D_max=np.inf, inplace=True):
+        return self._cut("D_c", D_min, D_max, inplace)
+
+    def cut_D_a(self, D_min=0., D_max=np.inf, inplace=True):
+        return self._cut("D_a", D_min, D_max, inplace)
+
+    def cut_redshift(self, redshift_min=0., redshift_max=np.inf, inplace=True):
+        return self._cut("redshift", redshift_min, redshift_max, inplace)
+
+    def cut_lon_lat(self, lon_range=[0, 360], lat_range=[-90, 90], inplace=True):
+        d = self.data
+        data = d[(d.lon > lon_range[0]) & (d.lon < lon_range[1]) & (d.lat > lat_range[0]) & (d.lat < lat_range[1])]
+        if inplace:
+            self.data = data
+        else:
+            return data
+
+    def cut_theta_phi(self, theta_range=[0, np.pi], phi_range=[0, 2 * np.pi], inplace=True):
+        d = self.data
+        data = d[(d.theta > theta_range[0]) & (d.theta < theta_range[1]) &
+                 (d.phi > phi_range[0]) & (d.phi < phi_range[1])]
+        if inplace:
+            self.data = data
+        else:
+            return data
+
+
+#########################################################
+#                  Canvas Object
+#########################################################
+class Canvas:
+    """Full-sky HEALPix (RING) canvas; the fp64 pixel array lives in HBM while painting."""
+
+    def __init__(self, catalog, nside, mode="healpy", R_times=1, inclusive=False):
+        assert mode == "healpy", "currently only full sky is supported"
+        self._nside = int(nside)
+        self._npix = 12 * self._nside * self._nside
+        self._lmax = 3 * self._nside - 1
+        self.R_times = R_times
+        self.inclusive = inclusive
+        self._catalog = Catalog() if catalog is None else catalog
+        self.template_name = None
+        self.stack = None
+        self.clean()
+        self.instantiate_discs()
+
+    # immutables
+    @property
+    def nside(self):
+        return self._nside
+
+    @property
+    def npix(self):
+        return self._npix
+
+    @property
+    def lmax(self):
+        return self._lmax
+
+    @property
+    def ell(self):
+        return np.arange(self._lmax + 1)
+
+    @property
+    def R_max(self):
+        return self.R_times * self.catalog.data["R_200c"].max()
+
+    @property
+    def centers_D_a(self):
+        return self._catalog.data.D_a
+
+    # ---- pixel state: "zero" | "host" | "device" ------------------------------------------------
+    @property
+    def pixels(self):
+        """Host view of the map (np.ndarray, fp64).  Reading it after a spray copies the device map
+        back once; the host array is then authoritative (users index and mutate it in place, e.g.
+        README.md:40-48), so the next spray uploads it again.  `pixels_device` avoids both copies."""
+        if self._state == "zero":
+            self._pixels = np.zeros(self.npix)
+        elif self._state == "device":
+            self._pixels = self._dmap.cpu().numpy()
+            self._dmap = None
+        self._state = "host"
+        return self._pixels
+
+    @pixels.setter
+    def pixels(self, val):
+        self._pixels = val
+        self._dmap = None
+        self._state = "host"
+        self._pixel_is_outdated = False
+        self._alm_is_outdated = True
+        self._Cl_is_outdated = True
+
+    @property
+    def pixels_device(self):
+        """The map as a torch CUDA tensor (fp64[npix]); allocated / uploaded on first use."""
+        import torch
+        dev = eng.require_cuda()
+        if self._state == "zero":
+            self._dmap = torch.zeros(self.npix, dtype=torch.float64, device=dev)
+        elif self._state == "host":
+            host = np.ascontiguousarray(np.broadcast_to(np.asarray(self._pixels, dtype=np.float64), (self.npix,)))
+            self._dmap = torch.from_numpy(host).to(dev)
+            self._pixels = None
+        self._state = "device"
+        return self._dmap
+
+    def _mark_painted(self):
+        # the reference's serial spray leaves alm/Cl flags untouched (:2387) while the threaded one
+        # goes through the setter (:2433); a drop-in marks them stale in both cases.
+        self._pixel_is_outdated = False
+        self._alm_is_outdated = True
+        self._Cl_is_outdated = True
+
+    @property
+    def alm(self):
+        if self._alm_is_outdated:
+            raise NotImplementedError("spherical-harmonic transforms are outside the painting hot path")
+        return self._alm
+
+    @alm.setter
+    def alm(self, val):
+        self._alm = val
+        self._alm_is_outdated = False
+        self._pixel_is_outdated = True
+        self._Cl_is_outdated = True
+
+    @property
+    def Cl(self):
+        if self._Cl_is_outdated:
+            raise NotImplementedError("spherical-harmonic transforms are outside the painting hot path")
+        return self._Cl
+
+    @property
+    def catalog(self):
+        return self._catalog
+
+    @catalog.setter
+    def catalog(self, val):
+        self._catalog = val
+        self.instantiate_discs()
+
+    def clean(self):
+        """Set all pixels to zero (paint_bucket.py:1307-1323)."""
+        self._pixels = None
+        self._dmap = None
+        self._state = "zero"
+        self._pixel_is_outdated = False
+        self._alm = None
+        self._alm_is_outdated = True
+        self._Cl = np.zeros(self._lmax + 1)
+        self._Cl_is_outdated = True
+
+    # ------------------------ Disc inner class ------------------------
+    class Disc:
+        """Per-halo disc generators (paint_bucket.py:1175-1290), computed by the device kernels in
+        batches and yielded as numpy arrays."""
+
+        BATCH = 4096
+
+        def __init__(self, catalog, nside, R_times, inclusive):
+            self.catalog = catalog
+            self.nside = nside
+            self.R_times = R_times
+            self.inclusive = inclusive
+            self.center_D_a = self.catalog.data.D_a
+
+        def _halos(self, halo_list):
+            try:
+                if isinstance(halo_list, str) and halo_list.lower() == "all":
+                    halo_list = range(self.catalog.size)
+            except AttributeError:
+                pass
+            assert hasattr(halo_list, "__iter__")
+            return np.asarray(list(halo_list), dtype=np.int64)
+
+        def _gen(self, halo_list, want_R=False, want_vec=False):
+            idx = self._halos(halo_list)
+            dev = eng.require_cuda()
+            for b in range(0, len(idx), self.BATCH):
+                rows = idx[b:b + self.BATCH]
+                halos = eng.DeviceHalos(self.catalog.data, self.R_times, dev, rows=rows)
+                n_pix, _, _, _ = eng.disc_count(halos, self.nside, self.inclusive)
+                off, pix, R, Rv = eng.disc_pixels(halos, self.nside, n_pix, want_R=want_R, want_vec=want_vec)
+                off = off.cpu().numpy()
+                pix = pix.cpu().numpy()
+                R = R.cpu().numpy() if R is not None else None
+                Rv = Rv.cpu().numpy() if Rv is not None else None
+                for i in range(len(rows)):
+                    a, e = off[i], off[i + 1]
+                    yield rows[i], pix[a:e], (R[a:e] if R is not None else None), (Rv[a:e] if Rv is not None else None)
+
+        def gen_center_ang(self, halo_list="All", snap2pixel=False):
+            if snap2pixel:
+                raise NotImplementedError("snap2pixel=True is not part of the painting path")
+            d = self.catalog.data
+            for halo in self._halos(halo_list):
+                yield (d.theta[halo], d.phi[halo])
+
+        def gen_center_vec(self, halo_list="All"):
+            d = self.catalog.data
+            for halo in self._halos(halo_list):
+                th, ph = d.theta[halo], d.phi[halo]
+                yield np.array([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)])
+
+        def gen_pixel_index(self, halo_list="All"):
+            for _, pix, _, _ in self._gen(halo_list):
+                yield pix
+
+        def gen_cent2pix_rad(self, halo_list="All"):
+            for halo, _, R, _ in self._gen(halo_list, want_R=True):
+                yield R / self.center_D_a[halo]
+
+        def gen_cent2pix_mpc(self, halo_list="All"):
+            for _, _, R, _ in self._gen(halo_list, want_R=True):
+                yield R
+
+        def gen_cent2pix_mpc_vec(self, halo_list="All"):
+            for _, _, _, Rv in self._gen(halo_list, want_vec=True):
+                yield Rv
+
+        def gen_cent2pix_hat(self, halo_list="All"):
+            for _, _, _, Rv in self._gen(halo_list, want_vec=True):
+                yield Canvas._normalize_vec(Rv)
+
+        def gen_pixel_vec(self, halo_list="All"):
+            for (_, _, _, Rv), c, halo in zip(self._gen(halo_list, want_vec=True), self.gen_center_vec(halo_list),
+                                              self._halos(halo_list)):
+                yield Rv / self.center_D_a[halo] + c
+
+    def instantiate_discs(self):
+        self.discs = self.Disc(self.catalog, self.nside, self.R_times, self.inclusive)
+
+    @staticmethod
+    def _normalize_vec(vec, axis=-1):
+        return np.true_divide(vec, np.expand_dims(np.linalg.norm(vec, axis=axis), axis=axis))
+
+    # ------------------------ cutouts / stacking ------------------------
+    def _cutout_setup(self, halo_list, lon_range, lat_range, xpix, ypix):
+        if lat_range is None:
+            lat_range = lon_range
+        try:
+            if isinstance(halo_list, str) and halo_list == "all":
+                halo_list = range(self.catalog.size)
+        except ValueError:
+            pass
+        idx = np.asarray(list(halo_list), dtype=np.int64)
+        lonra = [float(lon_range[0]), float(lon_range[1])]
+        latra = [float(lat_range[0]), float(lat_range[1])]
+        span = np.mod(lonra[1] - lonra[0], 360) or 360.0
+        if ypix is None:
+            ypix = int(round(xpix * (latra[1] - latra[0]) / span))
+        return idx, lonra, latra, int(xpix), int(ypix)
+
+    CUTOUT_BATCH_BYTES = 1 << 28
+
+    def cutouts(self, halo_list="all", lon_range=[-1, 1], lat_range=None, xpix=200, ypix=None,
+                apply_func=None, func_kwargs=dict()):
+        """Generate (ypix, xpix) Cartesian-projection cutouts centred on each halo, optionally passed
+        through `apply_func` with per-halo or shared `func_kwargs` (paint_bucket.py:1601-1743)."""
+        idx, lonra, latra, xpix, ypix = self._cutout_setup(halo_list, lon_range, lat_range, xpix, ypix)
+        if apply_func is not None:
+            if not isinstance(apply_func, list):
+                apply_func = [apply_func]
+                assert not isinstance(func_kwargs, list)
+                func_kwargs = [func_kwargs]
+            else:
+                assert isinstance(func_kwargs, list)
+            for f_kw in func_kwargs:
+                for key, value in f_kw.items():
+                    if not hasattr(value, "__len__"):
+                        f_kw[key] = [value]
+        d_map = self.pixels_device
+        lon = self.catalog.data["lon"].values
+        lat = self.catalog.data["lat"].values
+        batch = max(1, self.CUTOUT_BATCH_BYTES // (8 * xpix * ypix))
+        for b in range(0, len(idx), batch):
+            rows = idx[b:b + batch]
+            d_lon = eng.to_device(lon[rows], d_map.device)
+            d_lat = eng.to_device(lat[rows], d_map.device)
+            cuts = eng.cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix).cpu().numpy()
+            for i, halo in enumerate(rows):
+                cut_out = cuts[i]
+                if apply_func is not None:
+                    for func, f_kw in zip(apply_func, func_kwargs):
+                        func_dict = {key: (value[halo] if len(value) > 1 else value[0])
+                                     for key, value in f_kw.items()}
+                        cut_out = func(cut_out, **func_dict)
+                yield cut_out
+
+    def stack_cutouts(self, halo_list="all", lon_range=[-1, 1], lat_range=None, xpix=200, ypix=None,
+                      inplace=True, parallel=False, apply_func=None, func_kwargs=dict()):
+        """Sum of the cutouts of `halo_list` (paint_bucket.py:1745-1941).  Without `apply_func` the
+        cutouts are never materialised: one fused kernel projects and accumulates.  `parallel` is
+        accepted for compatibility (the GPU path is always parallel)."""
+        if ypix is None:
+            ypix = xpix
+        if apply_func is None:
+            idx, lonra, latra, xpix, ypix = self._cutout_setup(halo_list, lon_range, lat_range, xpix, ypix)
+            d_map = self.pixels_device
+            d_lon = eng.to_device(self.catalog.data["lon"].values[idx], d_map.device)
+            d_lat = eng.to_device(self.catalog.data["lat"].values[idx], d_map.device)
+            stack = eng.stack_cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix).cpu().numpy()
+        else:
+            stack = np.zeros((xpix, ypix))
+            for cut_out in self.cutouts(halo_list, lon_range, lat_range, xpix, ypix, apply_func, func_kwargs):
+                stack += cut_out
+        _say("Checkout the result with canvas.stack")
+        if inplace:
+            self.stack = stack
+        else:
+            return stack
+
+
+#########################################################
+#                   Painter Object
+#########################################################
+class Painter:
+    """Sprays a template (radial profile) over a Canvas."""
+
+    def __init__(self, template):
+        self.template = template
+
+    @property
+    def template(self):
+        return self._template
+
+    @template.setter
+    def template(self, val):
+        self._template = val
+        self.R_arg_indx = self._analyze_template()
+
+    # ------------------------ template introspection / marshalling ------------------------
+    def _analyze_template(self):
+        """Argument names of the template (paint_bucket.py:2542-2596)."""
+        self.template_name = self.template.__name__
+        spec = inspect.getfullargspec(self.template)
+        self.template_args_list = [a for a in spec.args if a not in ("self", "cls")]
+        self.template_kwargs_list = list(spec.kwonlyargs)
+        message = (f"The template '{self.template_name}' takes in the following arguments:\n"
+                   f"{self.template_args_list}\n")
+        if len(self.template_kwargs_list) > 0:
+            message += f"and the following keyword-only arguments:\n{self.template_kwargs_list}"
+        assert sum([arg in self.template_args_list for arg in ['R', 'R_vec']]) == 1, \
+            "Either 'R' or 'R_vec' must be a template argument (only one of them and not both)."
+        R_arg_index = (self.template_args_list.index("R") if "R" in self.template_args_list
+                       else self.template_args_list.index("R_vec"))
+        _say(message)
+        return R_arg_index
+
+    def _shake_canister(self, catalog, template_kwargs):
+        """Per-halo keyword arguments of the template as a dict of host columns: catalog columns
+        named like template_args_list[1:] plus the user's kwargs, scalars (and length-1 values)
+        broadcast to the catalog size (paint_bucket.py:2598-2676)."""
+        cols = {}
+        missing = []
+        self._catalog_cols = set()
+        for name in self.template_args_list[1:]:
+            if name in catalog.data.columns:
+                cols[name] = catalog.data[name].values
+                self._catalog_cols.add(name)
+            else:
+                missing.append(name)
+        if missing:
+            _say("The following parameters were not found in the canvas.catalog.data\n"
+                 f"{missing}\nMake sure you pass them as kwargs (key=value) in the .spray method.")
+        n = catalog.size
+        for key, value in template_kwargs.items():
+            self._catalog_cols.discard(key)
+            if not hasattr(value, "__len__"):
+                cols[key] = np.full(n, value)
+            else:
+                value = np.asarray(value)
+                if len(value) == 1:
+                    cols[key] = np.tile(value, n)
+                elif len(value) == n:
+                    cols[key] = value
+                else:
+                    raise ValueError(f"template kwarg '{key}' has length {len(value)}; expected 1 or {n}")
+        return cols
+
+    # ------------------------ spray ------------------------
+    def spray(self, canvas, distance_units="Mpc", n_cpus=1, cache=False, lazy=False, lazy_grid=None,
+              **template_kwargs):
+        """Paint every halo of canvas.catalog onto canvas.pixels (additively) with the template.
+
+        Same contract as the reference (paint_bucket.py:2296-2495).  `n_cpus` only validates
+        (0 raises ValueError): the halos are painted by CUDA kernels, and when torch.distributed is
+        initialised with more than one rank each rank paints its block of the catalog
+        (np.array_split, as the reference splits across threads) and the partial maps are summed
+        over NVLink.  `cache` is accepted and ignored; `lazy` snaps the template's per-halo
+        arguments to 500-point grids as the reference does.
+        """
+        _say("Painting the canvas...")
+        canvas.template_name = self.template.__name__
+        assert distance_units.lower() in ["mpc", "mpcs", "megaparsecs", "megaparsec"], \
+            "For now the distance unit has to be megaparsecs."
+        R_mode = self.template_args_list[self.R_arg_indx]
+        if cache:
+            assert R_mode == "R", "cache method is not available for profiles that use 'R_vec'"
+        if n_cpus == 0:
+            raise ValueError(f"n_cpus = {n_cpus} is not valid. Please enter a value > 0 for n_cpus or -1 "
+                             "to run on all cores.")
+        host_cols = self._shake_canister(canvas.catalog, template_kwargs)
+        if lazy is True and lazy_grid is None:
+            for key, data in host_cols.items():
+                grid = np.linspace(data.min(), data.max(), 500)
+                host_cols[key] = grid[np.searchsorted(grid, data)]
+            self._catalog_cols = set()
+        from . import parallel
+        stats = parallel.spray_sharded(self, canvas, R_mode, host_cols, template_kwargs)
+        canvas._mark_painted()
+        self.last_spray = stats
+        _say("Your artwork is finished. Check it out with Canvas.show_map()")
+
+    # ------------------------ one rank's share ------------------------
+    def _paint_rows(self, canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned=None):
+        """Paint catalog rows `rows` (None = all) into the device map d_map; returns stats dict."""
+        import torch
+        dev = d_map.device
+        data = canvas.catalog.data
+        halos = eng.DeviceHalos(data, canvas.R_times, dev, rows=rows, pinned=pinned)
+        nside = canvas.nside
+        if canvas.inclusive:
+            raise NotImplementedError("inclusive=True disc queries are not implemented on device yet")
+        d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        tmpl = self.template
+
+        def col(name, defaults=None):
+            """device tensor of a template argument: spray kwarg > catalog column > kw-only default"""
+            if name in host_cols:
+                if name in self._catalog_cols:
+                    return halos.col(name)  # unmodified catalog column: cached / pinned upload
+                v = host_cols[name]
+                return eng.to_device(v if rows is None else v[rows], dev)
+            if defaults and name in defaults:
+                return torch.full((1,), float(defaults[name]), dtype=torch.float64, device=dev)
+            raise TypeError(f"{self.template_name}() missing required argument: '{name}'")
+
+        path = "flat"
+        if getattr(tmpl, "_ap_device", None) is not None and self.R_arg_indx == 0:
+            info = tmpl._ap_device
+            params = [col(a) for a in info["args"]] + [col(k, info["kwonly"]) for k in info["kwonly"]]
+            eng.paint_profile(halos, nside, info["id"], params, d_map, d_count)
+            path = "device_profile"
+        elif getattr(tmpl, "_ap_device_table", None) is not None and self.R_arg_indx == 0:
+            self._paint_device_table(tmpl._ap_device_table, halos, nside, col, template_kwargs, d_map, d_count)
+            path = "device_table"
+        elif self._interp_info() is not None:
+            self._paint_python_table(self._interp_info(), halos, nside, rows, R_mode, host_cols, d_map, d_count)
+            path = "python_table"
+        else:
+            hc = host_cols if rows is None else {k: v[rows] for k, v in host_cols.items()}
+            eng.spray_flat(halos, nside, tmpl, R_mode, hc, d_map, d_count)
+        return {"path": path, "n_halos": halos.n, "d_count": d_count}
+
+    def _interp_info(self):
+        info = getattr(self.template, "_ap_interp", None)
+        if info is None or self.R_arg_indx != 0:
+            return None
+        if info["min_frac"] or info["k"] != 3 or not info["default_interpolator"]:
+            return None  # per-halo node counts / custom interpolators: flat path keeps exact semantics
+        if info["sampling_method"] not in ("linspace", "logspace") or not (4 <= info["n_samples"] <= 32):
+            return None
+        return info
+
+    def _paint_device_table(self, info, halos, nside, col, template_kwargs, d_map, d_count):
+        """Battaglia16.tau_2D_interp / kSZ_T entirely on device (see csrc/kernels.cu, K4)."""
+        import torch
+        ns = info["n_samples"]
+        n_pix, _, rmin, rmax = eng.disc_count(halos, nside, want_range=True)
+        nodes, n_nodes = eng.table_nodes(halos, n_pix, rmin, rmax, ns, info["sampling_method"])
+        assert info["kind"] == "b16_tau"
+        R200, M200, zred = (col(a) for a in info["args"])
+        R200, M200, zred = (t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in (R200, M200, zred))
+        values = eng.b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes)
+        coef = eng.spline_build(nodes, values, n_nodes)
+        scale = None
+        if info["scale"] is not None:
+            sc = info["scale"]
+            cols = {a: col(a) for a in sc["args"]}
+            kw = {k: col(k, sc["kwonly"]) for k in sc["kwonly"]}
+            scale = sc["fn"](cols, kw)
+            scale = scale if scale.numel() == halos.n else scale.expand(halos.n)
+            scale = scale.contiguous()
+        eng.paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count)
+        eng.paint_b16_small(halos, nside, R200, M200, zred, scale, n_pix, ns, d_map, d_count)
+
+    def _paint_python_table(self, info, halos, nside, rows, R_mode, host_cols, d_map, d_count):
+        """A Python template wrapped in @interpolate: nodes, spline and painting on device; the
+        wrapped profile is evaluated on the host at each halo's nodes exactly as the reference's
+        `interpolate` does (lib/utils.py:515-516).  Halos with fewer pixels than n_samples take the
+        flat path (the decorator's direct-evaluation branch, :510-511)."""
+        ns = info["n_samples"]
+        inner = info["inner"]
+        n_pix, _, rmin, rmax = eng.disc_count(halos, nside, want_range=True)
+        nodes, n_nodes = eng.table_nodes(halos, n_pix, rmin, rmax, ns, info["sampling_method"])
+        nodes_h = nodes.cpu().numpy()
+        counts = n_pix.cpu().numpy()
+        hc = host_cols if rows is None else {k: v[rows] for k, v in host_cols.items()}
+        pos = [a for a in self.template_args_list[1:]]
+        kwo = [k for k in self.template_kwargs_list if k in hc]
+        values = np.zeros_like(nodes_h)
+        for h in np.nonzero(counts >= ns)[0]:
+            rest = [hc[a][h] for a in pos]
+            kws = {k: hc[k][h] for k in kwo}
+            values[h] = [inner(x, *rest, **kws) for x in nodes_h[h]]
+        coef = eng.spline_build(nodes, eng.to_device(values.ravel(), halos.device).view(halos.n, ns), n_nodes)
+        eng.paint_table(halos, nside, nodes, coef, n_nodes, None, d_map, d_count)
+        small = np.nonzero((counts > 0) & (counts < ns))[0]
+        if len(small):
+            sub = halos.subset(small)
+            eng.spray_flat(sub, nside, self.template, R_mode, {k: v[small] for k, v in hc.items()}, d_map, d_count)
+
+    # ------------------------ 1-D template helpers ------------------------
+    def calculate_template(self, R, catalog, halo_list=[0, ], **template_kwargs):
+        """1-D profile of the template as a function of R [Mpc] for the given halos (host)."""
+        assert hasattr(halo_list, "__iter__"), "halo_list must be an iterable"
+        cols = self._shake_canister(catalog, template_kwargs)
+        out = []
+        for halo in halo_list:
+            out.append(self.template(**{"R": R, **{k: v[halo] for k, v in cols.items()}}))
+        return np.array(out)

@@ -86,6 +86,12 @@ int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double* d_M_200c, 
                      int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes,
                      double* d_values, void* stream);
 
+/* Diagnostic: Battaglia16.tau_2D at arbitrary (R, halo) pairs with QUADPACK's abserr and neval
+ * (scipy.integrate.quad full_output; lib/utils.py:448).  d_abserr / d_neval may be NULL.       */
+int ap_b16_tau_eval(int64_t n, const double* d_R, const double* d_R_200c, const double* d_M_200c,
+                    const double* d_redshift, double* d_result, double* d_abserr, int32_t* d_neval,
+                    void* stream);
+
 /* InterpolatedUnivariateSpline(nodes, values, k=3) per halo -> piecewise-cubic coefficients
  * d_coef[n*(n_samples-1)*4] (lib/utils.py:519).                                              */
 int ap_spline_build(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,

@@ -1,0 +1,428 @@
+"""GPU parity tests: the CUDA path, called through the reference-shaped API and the C ABI, against
+the CPU oracle (oracle/) on the same seeded inputs.  Bar: pixel sets bit-exact, map values within
+1e-6 relative (fp64), as BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+
+from .conftest import map_close, apply_func_to_cutout
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import reference_loop as ref, profiles_np as oprof, healpix_np as ohp
+    return ref, oprof, ohp
+
+
+def _catalogs():
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    return {
+        "test6": ap.Catalog("test"),
+        "box": ap.Catalog(synthetic.random_box(60, seed=0)),
+        "websky": ap.Catalog(synthetic.websky_like(300, seed=1)),
+    }
+
+
+@pytest.fixture(scope="module")
+def cats():
+    return _catalogs()
+
+
+# ------------------------------------------------------------------ pixel sets and geometry
+@pytest.mark.parametrize("name,nside,R_times", [("test6", 64, 1), ("test6", 64, 20), ("test6", 16, 80),
+                                                ("box", 128, 5), ("box", 512, 5), ("box", 32, 1),
+                                                ("websky", 2048, 5), ("websky", 8192, 5), ("websky", 4096, 1)])
+def test_pixel_sets_bit_exact(cats, name, nside, R_times):
+    import astropaint_b200 as ap
+    ref, _, _ = _oracle()
+    cat = cats[name]
+    canvas = ap.Canvas(cat, nside, R_times=R_times)
+    discs = ref.Discs(cat.data, nside, R_times)
+    n = 0
+    for halo, pix in enumerate(canvas.discs.gen_pixel_index()):
+        want = discs.pixel_index(halo)
+        assert pix.dtype == np.int64
+        assert np.array_equal(pix, want), f"halo {halo}: {len(pix)} vs {len(want)} pixels"
+        n += len(pix)
+    assert n > 0
+
+
+@pytest.mark.parametrize("name,nside,R_times", [("test6", 64, 5), ("box", 128, 5), ("websky", 4096, 5)])
+def test_R_and_R_vec(cats, name, nside, R_times):
+    import astropaint_b200 as ap
+    ref, _, _ = _oracle()
+    cat = cats[name]
+    canvas = ap.Canvas(cat, nside, R_times=R_times)
+    discs = ref.Discs(cat.data, nside, R_times)
+    for halo, (R, Rv) in enumerate(zip(canvas.discs.gen_cent2pix_mpc(), canvas.discs.gen_cent2pix_mpc_vec())):
+        want = discs.cent2pix_mpc(halo)
+        wantv = discs.cent2pix_mpc_vec(halo)
+        if len(want) == 0:
+            assert len(R) == 0
+            continue
+        D_a = cat.data.D_a[halo]
+        assert np.abs(R - want).max() <= 1e-9 * max(want.max(), 1e-300)
+        assert np.abs(Rv - wantv).max() <= 1e-12 * D_a
+
+
+# ------------------------------------------------------------------ spray: device profiles
+def _spray_both(cat, nside, R_times, template, otemplate, **kw):
+    import astropaint_b200 as ap
+    ref, _, _ = _oracle()
+    canvas = ap.Canvas(cat, nside, R_times=R_times)
+    painter = ap.Painter(template)
+    painter.spray(canvas, **kw)
+    want = np.zeros(12 * nside * nside)
+    n_pairs = ref.spray(want, cat.data, nside, otemplate, R_times=R_times, **kw)
+    got = canvas.pixels
+    assert int(painter.last_spray["d_count"].item()) == n_pairs
+    return got, want, painter
+
+
+def test_constant_density_is_coverage_count(cats):
+    from astropaint_b200.profiles import spherical
+    _, oprof, _ = _oracle()
+    got, want, p = _spray_both(cats["box"], 128, 5, spherical.constant_density_2D, oprof.constant_density_2D,
+                               constant=1.0)
+    assert p.last_spray["path"] == "device_profile"
+    assert np.array_equal(got, want)  # sums of 1.0 are exact: pins pixel sets and multiplicity
+    assert got.max() > 1
+
+
+PROFILE_CASES = [
+    ("linear", "box", 128, 5, dict(intercept=0.5, slope=2.0)),
+    ("gaussian", "box", 512, 5, {}),
+    ("gaussian", "test6", 64, 5, {}),
+    ("solid_sphere", "box", 128, 1, {}),
+    ("solid_sphere", "box", 128, 2, {}),      # NaN outside R_200c, exactly like the reference
+    ("nfw_rho", "box", 256, 3, {}),
+    ("nfw_tau", "websky", 4096, 5, {}),
+    ("nfw_ksz", "websky", 4096, 5, {}),
+    ("nfw_ksz", "websky", 4096, 5, dict(T_cmb=3.0)),
+    ("nfw_deflection", "box", 128, 5, {}),
+    ("nfw_bg", "websky", 4096, 5, {}),
+    ("nfw_bg", "box", 128, 5, {}),
+]
+
+
+def _pair(kind):
+    from astropaint_b200.profiles import spherical, NFW
+    _, o, _ = _oracle()
+    return {
+        "linear": (spherical.linear_density_2D, o.linear_density_2D),
+        "gaussian": (spherical.gaussian_2D, o.gaussian_readme),
+        "solid_sphere": (spherical.solid_sphere_2D, o.solid_sphere_2D),
+        "nfw_rho": (NFW.rho_2D_bartlemann, o.nfw_rho_2D_bartlemann),
+        "nfw_tau": (NFW.tau_2D, o.nfw_tau_2D),
+        "nfw_ksz": (NFW.kSZ_T, o.nfw_kSZ_T),
+        "nfw_deflection": (NFW.deflection_angle, o.nfw_deflection_angle),
+        "nfw_bg": (NFW.BG, o.nfw_BG),
+    }[kind]
+
+
+@pytest.mark.parametrize("kind,name,nside,R_times,kw", PROFILE_CASES)
+def test_device_profiles_match_oracle(cats, kind, name, nside, R_times, kw):
+    t, o = _pair(kind)
+    got, want, p = _spray_both(cats[name], nside, R_times, t, o, **kw)
+    assert p.last_spray["path"] == "device_profile"
+    map_close(got, want, 1e-6)
+
+
+def test_spray_is_additive(cats):
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import spherical
+    canvas = ap.Canvas(cats["box"], 64, R_times=3)
+    painter = ap.Painter(spherical.gaussian_2D)
+    painter.spray(canvas)
+    once = canvas.pixels.copy()
+    painter.spray(canvas)          # host array handed out -> re-uploaded, then painted on top
+    map_close(canvas.pixels, 2 * once, 1e-12)
+    canvas.clean()
+    assert (canvas.pixels == 0).all()
+
+
+# ------------------------------------------------------------------ Battaglia16 (device QUADPACK + spline)
+def test_device_quadpack_matches_scipy():
+    """The device qagie against scipy.integrate.quad itself: value, error estimate AND number of
+    integrand evaluations (i.e. the same adaptive decisions) on 3000 (halo, R) pairs."""
+    import torch
+    from scipy import integrate
+    from astropaint_b200 import _capi
+    from astropaint_b200._capi import ptr
+    ref, o, _ = _oracle()
+    rng = np.random.default_rng(7)
+    n = 3000
+    M = 10 ** rng.uniform(13, 15.5, n)
+    z = rng.uniform(0, 4.6, n)
+    R200 = np.asarray(ref.M_200c_to_R_200c(M, z))
+    R = R200 * rng.uniform(0, 5, n) * rng.choice([1.0, 1.0, 0.01, 1e-4], n)
+    R = np.maximum(R, 1e-9)
+    dev = torch.device("cuda", 0)
+    t = [torch.from_numpy(a).to(dev) for a in (R, R200, M, z)]
+    res = torch.empty(n, dtype=torch.float64, device=dev)
+    err = torch.empty_like(res)
+    nev = torch.empty(n, dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().ap_b16_tau_eval(n, *[ptr(a) for a in t], ptr(res), ptr(err), ptr(nev), None))
+    res, err, nev = res.cpu().numpy(), err.cpu().numpy(), nev.cpu().numpy()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(n):
+            f = lambda r: o.b16_tau_3D(r, R200[i], M[i], z[i]) * 2. * r / np.sqrt(r ** 2 - R[i] ** 2)  # noqa: E731
+            v, e, info = integrate.quad(f, R[i], np.inf, epsabs=0., epsrel=1.e-2, full_output=1)[:3]
+            assert nev[i] == info["neval"], (i, R[i] / R200[i], nev[i], info["neval"])
+            assert abs(res[i] - v) <= 1e-10 * abs(v)
+            assert abs(err[i] - e) <= 1e-3 * abs(e) + 1e-300   # error estimates are differences of near-equal sums
+
+
+def test_b16_tau_2D_direct(cats):
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import Battaglia16
+    _, o, _ = _oracle()
+    cat = ap.Catalog(cats["websky"].data[["x", "y", "z", "v_x", "v_y", "v_z", "M_200c", "redshift"]].iloc[:40])
+    got, want, p = _spray_both(cat, 2048, 5, Battaglia16.tau_2D, o.b16_tau_2D)
+    assert p.last_spray["path"] == "device_profile"
+    map_close(got, want, 1e-6)
+
+
+@pytest.mark.parametrize("nside,n,m_min", [(4096, 120, 1e13), (1024, 60, 1e14), (8192, 40, 3e14)])
+def test_b16_tau_2D_interp_and_kSZ(nside, n, m_min):
+    """BASELINE configs 2/3 on sub-samples: discs both above and below the 15-sample bypass."""
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    from astropaint_b200.profiles import Battaglia16
+    _, o, _ = _oracle()
+    cat = ap.Catalog(synthetic.websky_like(n, seed=11, m_min=m_min))
+    got, want, p = _spray_both(cat, nside, 5, Battaglia16.tau_2D_interp, o.b16_tau_2D_interp)
+    assert p.last_spray["path"] == "device_table"
+    map_close(got, want, 1e-6)
+    got, want, p = _spray_both(cat, nside, 5, Battaglia16.kSZ_T, o.b16_kSZ_T)
+    assert p.last_spray["path"] == "device_table"
+    map_close(got, want, 1e-6)
+
+
+# ------------------------------------------------------------------ Python templates
+def test_python_template_flat_path(cats):
+    """The README's user-defined template (README.md:99-101) as plain Python."""
+    def a_nonsense_template(R, R_200c, x, y, z):
+        return np.exp(-(R / R_200c / 3) ** 2) * (x + y + z)
+
+    _, o, _ = _oracle()
+    got, want, p = _spray_both(cats["box"], 128, 5, a_nonsense_template, o.gaussian_readme)
+    assert p.last_spray["path"] == "flat"
+    # summation order differs (atomics vs sequential np.add.at): pixels where halos of opposite
+    # sign cancel lose relative precision, so the bar is the map tolerance, not 1e-9
+    map_close(got, want, 1e-6)
+
+
+def test_python_template_scalar_and_kwargs(cats):
+    def shifted(R, R_200c, *, offset=0.0, gain=1.0):
+        return gain * (R / R_200c) + offset
+
+    gains = np.linspace(1, 2, cats["box"].size)
+    got, want, p = _spray_both(cats["box"], 64, 2, shifted, shifted, offset=0.25, gain=gains)
+    map_close(got, want, 1e-6)
+
+
+def test_python_R_vec_template(cats):
+    def dipole(R_vec, v_x, v_y, v_z):
+        return R_vec[:, 0] * v_x + R_vec[:, 1] * v_y + R_vec[:, 2] * v_z
+
+    got, want, p = _spray_both(cats["box"], 64, 2, dipole, dipole)
+    map_close(got, want, 1e-6)
+
+
+def test_python_interpolate_template(cats):
+    """README.md:170-206: @interpolate(n_samples=20) @LOS_integrate top-hat; the analytic answer
+    2 sqrt(R_200c^2 - R^2) is the known-answer check of the projection operator."""
+    import astropaint_b200 as ap
+    from astropaint_b200 import LOS_integrate, interpolate
+    from scipy import integrate
+    from scipy.interpolate import InterpolatedUnivariateSpline
+
+    def tophat_3D(r, R_200c):
+        return np.where(np.asarray(r) > R_200c, 0.0, 1.0)
+
+    @interpolate(n_samples=20)
+    @LOS_integrate
+    def tophat_2D_interp(R, R_200c):
+        return tophat_3D(R, R_200c)
+
+    def o_tophat(R, R_200c):  # the reference decorators, spelled out
+        def los(Rs):
+            scalar = not hasattr(Rs, "__iter__")
+            out = [integrate.quad(lambda r: tophat_3D(r, R_200c) * 2. * r / np.sqrt(r ** 2 - R_i ** 2),
+                                  R_i, np.inf, epsabs=0., epsrel=1.e-2)[0] for R_i in ([Rs] if scalar else Rs)]
+            return np.asarray(out[0] if scalar else out)
+        if len(R) < 20:
+            return los(R)
+        xs = np.linspace(R.min(), R.max(), 20)
+        return InterpolatedUnivariateSpline(xs, np.array([los(x) for x in xs]), k=3)(R)
+
+    cat = ap.Catalog(cats["box"].data[["x", "y", "z", "v_x", "v_y", "v_z", "M_200c"]].iloc[:12])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, want, p = _spray_both(cat, 64, 1, tophat_2D_interp, o_tophat)
+    assert p.last_spray["path"] == "python_table"
+    map_close(got, want, 1e-6)
+
+
+# ------------------------------------------------------------------ cutouts / stack
+def test_cutouts_and_stack_match_oracle(cats):
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import spherical
+    ref, _, _ = _oracle()
+    cat = cats["box"]
+    nside = 256
+    canvas = ap.Canvas(cat, nside, R_times=5)
+    ap.Painter(spherical.gaussian_2D).spray(canvas)
+    pixels = canvas.pixels.copy()
+    halos = np.arange(0, 40, 3)
+    for lon_range, lat_range, xpix, ypix in [([-1, 1], None, 200, None), ([-3, 2], [-1, 2.5], 50, None),
+                                             ([-0.2, 0.2], [-0.2, 0.2], 17, 17)]:
+        got = list(canvas.cutouts(halos, lon_range=lon_range, lat_range=lat_range, xpix=xpix, ypix=ypix))
+        want = list(ref.cutouts(pixels, cat.data, nside, halos, lon_range, lat_range, xpix, ypix))
+        assert len(got) == len(want) == len(halos)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape
+            assert np.array_equal(g, w)   # nearest-pixel lookups: identical pixels -> identical values
+    stack = canvas.stack_cutouts(halos, lon_range=[-1, 1], xpix=64, inplace=False)
+    want = ref.stack_cutouts(pixels, cat.data, nside, halos, [-1, 1], None, 64)
+    map_close(stack, want, 1e-12)
+    canvas.stack_cutouts("all", lon_range=[-0.5, 0.5], xpix=32)
+    want = ref.stack_cutouts(pixels, cat.data, nside, None, [-0.5, 0.5], None, 32)
+    map_close(canvas.stack, want, 1e-12)
+
+
+@pytest.mark.parametrize("mult_by, add_to", [(1, 1), (1, [1]), ([1], [1]), (1, [1, 2, 3, 4, 5, 6])])
+def test_cutouts_apply_func_kwarg_types(test_canvas, mult_by, add_to):
+    """Reference tests/test_Canvas.py:64-83, plus value checks."""
+    ref, _, _ = _oracle()
+    halo_list = test_canvas.catalog.data.index
+    cuts = list(test_canvas.cutouts(halo_list, apply_func=apply_func_to_cutout,
+                                    func_kwargs={"mult_by": mult_by, "add_to": add_to}))
+    assert len(cuts) == 6
+    a = np.atleast_1d(add_to)
+    for h, c in enumerate(cuts):
+        assert c.shape == (200, 200)
+        assert np.all(c == (a[h] if len(a) > 1 else a[0]))   # canvas is empty
+
+
+def test_cutouts_apply_multiple_funcs(test_canvas):
+    halo_list = test_canvas.catalog.data.index
+    cuts = list(test_canvas.cutouts(halo_list, apply_func=[apply_func_to_cutout] * 2,
+                                    func_kwargs=[{"mult_by": 1, "add_to": 1}] * 2))
+    assert all(np.all(c == 2) for c in cuts)
+
+
+def test_stack_with_apply_func(cats):
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import spherical
+    ref, _, _ = _oracle()
+    cat = cats["box"]
+    canvas = ap.Canvas(cat, 128, R_times=5)
+    ap.Painter(spherical.gaussian_2D).spray(canvas)
+    pixels = canvas.pixels.copy()
+    sign = np.sign(cat.data.v_r.values)
+    halos = np.arange(20)
+    flip = lambda patch, s: patch * s  # noqa: E731
+    got = canvas.stack_cutouts(halos, lon_range=[-2, 2], xpix=40, inplace=False, apply_func=flip,
+                               func_kwargs={"s": sign})
+    want = ref.stack_cutouts(pixels, cat.data, 128, halos, [-2, 2], None, 40, apply_func=flip,
+                             func_kwargs={"s": sign})
+    map_close(got, want, 1e-12)
+
+
+# ------------------------------------------------------------------ API errors
+def test_spray_argument_errors(cats):
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import spherical, NFW
+    canvas = ap.Canvas(cats["test6"], 16)
+    p = ap.Painter(spherical.gaussian_2D)
+    with pytest.raises(ValueError):
+        p.spray(canvas, n_cpus=0)
+    with pytest.raises(AssertionError):
+        p.spray(canvas, distance_units="furlongs")
+    with pytest.raises(AssertionError):
+        ap.Painter(NFW.BG).spray(canvas, cache=True)
+    with pytest.raises(TypeError):
+        ap.Painter(spherical.constant_density_2D).spray(canvas)     # `constant` not provided
+    with pytest.raises(AssertionError):
+        ap.Painter(lambda r: r)                                     # neither R nor R_vec
+    p.spray(canvas, n_cpus=-1)
+
+
+# ------------------------------------------------------------------ raw C ABI
+def test_c_abi_error_codes_and_host_entry(cats):
+    import ctypes as C
+    import torch
+    from astropaint_b200 import _capi, _engine as eng
+    ref, oprof, _ = _oracle()
+    L = _capi.lib()
+    cat = cats["box"]
+    dev = torch.device("cuda", 0)
+    halos = eng.DeviceHalos(cat.data, 5, dev)
+    s = halos.struct()
+    n_pix = torch.empty(halos.n, dtype=torch.int64, device=dev)
+    assert L.ap_disc_count(0, C.byref(s), 0, _capi.ptr(n_pix), None, None, None, None) != 0
+    assert b"nside" in L.ap_last_error()
+    assert L.ap_disc_count(64, C.byref(s), 1, _capi.ptr(n_pix), None, None, None, None) != 0
+    assert L.ap_disc_count(64, C.byref(s), 0, None, None, None, None, None) != 0
+    d_map = torch.zeros(12 * 64 * 64, dtype=torch.float64, device=dev)
+    assert L.ap_paint_profile(3, 64, C.byref(s), None, None, 2, _capi.ptr(d_map), None, None) != 0
+    assert L.ap_paint_profile(77, 64, C.byref(s), None, None, 0, _capi.ptr(d_map), None, None) != 0
+    empty = _capi.ApHalos()
+    assert L.ap_disc_count(64, C.byref(empty), 0, _capi.ptr(n_pix), None, None, None, None) == 0
+    # host-buffer entry point: Gaussian template, all HOST pointers
+    nside = 64
+    d = cat.data
+    cols = [np.ascontiguousarray(d[k].values, dtype=np.float64) for k in ("x", "y", "z")]
+    radius = np.ascontiguousarray(5 * np.deg2rad(d.R_ang_200c.values / 60))
+    geo = [np.ascontiguousarray(d[k].values, dtype=np.float64) for k in ("theta", "phi", "D_a")]
+    params = [np.ascontiguousarray(d[k].values, dtype=np.float64) for k in ("R_200c", "x", "y", "z")]
+    arr = (C.c_void_p * 4)(*[p.ctypes.data for p in params])
+    strides = (C.c_int32 * 4)(1, 1, 1, 1)
+    h_map = np.zeros(12 * nside * nside)
+    cnt = C.c_uint64(0)
+    rc = L.ap_spray_host(3, nside, len(d), *[_capi.ptr(c) for c in cols], _capi.ptr(radius),
+                         *[_capi.ptr(g) for g in geo], arr, strides, 4, _capi.ptr(h_map), C.byref(cnt))
+    assert rc == 0, L.ap_last_error()
+    want = np.zeros_like(h_map)
+    n_pairs = ref.spray(want, d, nside, oprof.gaussian_readme, R_times=5)
+    assert cnt.value == n_pairs
+    map_close(h_map, want, 1e-9)
+
+
+# ------------------------------------------------------------------ full-size properties (nside 8192)
+def test_full_size_properties():
+    """Size-independent properties at BASELINE's nside 8192 on a 2e5-halo Websky-shaped catalog:
+    coverage count is integral and sums to the per-halo disc counts; linearity of the painter."""
+    import torch
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic, _engine as eng
+    from astropaint_b200.profiles import spherical, NFW
+    nside = 8192
+    cat = ap.Catalog(synthetic.websky_like(200000, seed=2))
+    canvas = ap.Canvas(cat, nside, R_times=5)
+    p = ap.Painter(spherical.constant_density_2D)
+    p.spray(canvas, constant=1.0)
+    dmap = canvas.pixels_device
+    total = int(p.last_spray["d_count"].item())
+    halos = eng.DeviceHalos(cat.data, 5, dmap.device)
+    n_pix, _, _, _ = eng.disc_count(halos, nside)
+    assert total == int(n_pix.sum().item())
+    assert float(dmap.sum().item()) == float(total)
+    assert bool((dmap == dmap.round()).all())
+    # linearity: spray(kSZ with T) + spray(kSZ with 2T) == spray(kSZ with 3T)
+    a = ap.Canvas(cat, nside, R_times=5)
+    ap.Painter(NFW.kSZ_T).spray(a, T_cmb=1.0)
+    ap.Painter(NFW.kSZ_T).spray(a, T_cmb=2.0)
+    b = ap.Canvas(cat, nside, R_times=5)
+    ap.Painter(NFW.kSZ_T).spray(b, T_cmb=3.0)
+    da, db = a.pixels_device, b.pixels_device
+    scale = float(db.abs().max().item())
+    assert float((da - db).abs().max().item()) <= 1e-9 * scale
+    del da, db, dmap
+    torch.cuda.empty_cache()
