@@ -5,8 +5,13 @@ compute step is a call into libastropaint_b200.so (csrc/kernels.cu) through `_ca
 """
 import ctypes as C
 
+import warnings
+
 import numpy as np
 import torch
+
+# pandas hands out read-only column views; they are only ever read (copied to pinned memory / HBM)
+warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
 
 from . import _capi
 from ._capi import ApHalos, c_ptr, c_i32, ptr, check
@@ -62,17 +67,26 @@ class DeviceHalos:
         for k in GEOMETRY_COLUMNS:
             self.col(k)
 
+    def _take(self, v):
+        """rows of a host column: a view for all rows / a contiguous block, a gather otherwise"""
+        if self._rows is None:
+            return v
+        r = self._rows
+        if len(r) and r[-1] - r[0] + 1 == len(r):
+            return v[int(r[0]):int(r[-1]) + 1]
+        return v[torch.as_tensor(r)] if isinstance(v, torch.Tensor) else v[r]
+
     def _host_col(self, name):
         if name in self._pinned:
-            v = self._pinned[name]
-            return v if self._rows is None else v[self._rows]
-        v = self._data[name].values
-        return v if self._rows is None else v[self._rows]
+            return self._take(self._pinned[name]).numpy()
+        return self._take(self._data[name].values)
 
     def col(self, name):
         if name not in self.cols:
-            if name in self._pinned and self._rows is None:
-                self.cols[name] = self._pinned[name].to(self.device, non_blocking=True)
+            if name in self._pinned:
+                v = self._take(self._pinned[name])
+                v = v if v.is_pinned() else v.pin_memory()
+                self.cols[name] = v.to(self.device, non_blocking=True)
             else:
                 self.cols[name] = to_device(self._host_col(name), self.device)
         return self.cols[name]

@@ -58,6 +58,7 @@ class Catalog:
 
     @data.setter
     def data(self, val):
+        self._pinned = None
         self._data = pd.DataFrame(val).reset_index(drop=True)
         self.size = len(self._data)
         self.box_size = self._get_box_size()
@@ -65,6 +66,15 @@ class Catalog:
             _say("Catalog data has been modified...\n")
         self.build_dataframe(calculate_redshifts=self.calculate_redshifts,
                              default_redshift=self.default_redshift)
+
+    def pin_memory(self):
+        """Stage every numeric column in page-locked host memory (torch pinned tensors) so that each
+        spray uploads its inputs with one DMA per column instead of pageable copies.  Optional;
+        invalidated whenever `data` is reassigned."""
+        import torch
+        self._pinned = {k: torch.from_numpy(np.ascontiguousarray(self._data[k].values, dtype=np.float64)).pin_memory()
+                        for k in self._data.columns if np.issubdtype(self._data[k].dtype, np.number)}
+        return self
 
     # ------------------------ sample data ------------------------
     @staticmethod
@@ -244,6 +254,7 @@ class Canvas:
         self._catalog = Catalog() if catalog is None else catalog
         self.template_name = None
         self.stack = None
+        self._host_buf = None
         self.clean()
         self.instantiate_discs()
 
@@ -281,7 +292,12 @@ class Canvas:
         if self._state == "zero":
             self._pixels = np.zeros(self.npix)
         elif self._state == "device":
-            self._pixels = self._dmap.cpu().numpy()
+            import torch
+            if self._host_buf is None:  # page-locked, reused across clean(): one DMA per read-back
+                self._host_buf = torch.empty(self.npix, dtype=torch.float64, pin_memory=True)
+            self._host_buf.copy_(self._dmap)
+            self._pixels = self._host_buf.numpy()
+            self._dmap_spare = self._dmap
             self._dmap = None
         self._state = "host"
         return self._pixels
@@ -301,7 +317,11 @@ class Canvas:
         import torch
         dev = eng.require_cuda()
         if self._state == "zero":
-            self._dmap = torch.zeros(self.npix, dtype=torch.float64, device=dev)
+            if self._dmap_spare is not None and self._dmap_spare.device == dev:
+                self._dmap = self._dmap_spare.zero_()
+                self._dmap_spare = None
+            else:
+                self._dmap = torch.zeros(self.npix, dtype=torch.float64, device=dev)
         elif self._state == "host":
             host = np.ascontiguousarray(np.broadcast_to(np.asarray(self._pixels, dtype=np.float64), (self.npix,)))
             self._dmap = torch.from_numpy(host).to(dev)
@@ -347,6 +367,9 @@ class Canvas:
     def clean(self):
         """Set all pixels to zero (paint_bucket.py:1307-1323)."""
         self._pixels = None
+        # keep the HBM allocation for the next spray instead of returning 8*npix bytes to the allocator
+        self._dmap_spare = getattr(self, "_dmap", None) if getattr(self, "_dmap", None) is not None \
+            else getattr(self, "_dmap_spare", None)
         self._dmap = None
         self._state = "zero"
         self._pixel_is_outdated = False
@@ -612,7 +635,8 @@ class Painter:
                 host_cols[key] = grid[np.searchsorted(grid, data)]
             self._catalog_cols = set()
         from . import parallel
-        stats = parallel.spray_sharded(self, canvas, R_mode, host_cols, template_kwargs)
+        stats = parallel.spray_sharded(self, canvas, R_mode, host_cols, template_kwargs,
+                                       pinned=getattr(canvas.catalog, "_pinned", None))
         canvas._mark_painted()
         self.last_spray = stats
         _say("Your artwork is finished. Check it out with Canvas.show_map()")

@@ -47,7 +47,7 @@ def spray_sharded(painter, canvas, R_mode, host_cols, template_kwargs, pinned=No
     rows = shard_rows(canvas.catalog.size, rank, ws)
     base = canvas.pixels_device
     partial = torch.zeros_like(base)
-    stats = painter._paint_rows(canvas, rows, R_mode, host_cols, template_kwargs, partial)
+    stats = painter._paint_rows(canvas, rows, R_mode, host_cols, template_kwargs, partial, pinned=pinned)
     reduce_partial_map(partial, "all")
     base += partial
     stats["world_size"] = ws
