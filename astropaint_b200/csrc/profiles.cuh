@@ -102,13 +102,21 @@ AP_HD double nfw_g(double x) {
 
 // ---- Battaglia16 tau_3D(r) * 2r / sqrt(r^2 - R^2): the @LOS_integrate integrand ----
 struct B16Integrand {
-  double inv_R200xc, alpha, expo, K, R;  // K carries rho0 * rho_c(z) * f_b / factor * sigma_T
+  double inv_R200xc, alpha, expo, K2, RR;  // K2 = 2 rho0 rho_c(z) f_b / factor * sigma_T ; RR = R^2
+  // fit = (1 + y^alpha)^expo * y^gamma evaluated as exp(expo * log(1 + e^(alpha L)) + gamma L),
+  // L = log y: two logs and two exps instead of three pow() calls (each ~4x a log+exp pair on
+  // sm_100a).  Relative error ~1e-15, far inside the distance at which QUADPACK's decisions flip
+  // (tests compare value AND neval against scipy on host and device).
   AP_HD double operator()(double r) const {
-    double y = AP_MUL(r, inv_R200xc);                 // (r / R_200c) / xc
-    double ya = pow(y, alpha);
-    double fit = AP_MUL(pow(AP_ADD(1.0, ya), expo), pow(y, -0.2));
-    double tau3 = AP_MUL(fit, K);
-    return AP_MUL(AP_MUL(tau3, 2.0), r) / sqrt(AP_SUB(AP_MUL(r, r), AP_MUL(R, R)));
+    double L = log(AP_MUL(r, inv_R200xc));             // log((r / R_200c) / xc)
+    double ya = exp(AP_MUL(alpha, L));
+    double fit = exp(AP_ADD(AP_MUL(expo, log(AP_ADD(1.0, ya))), AP_MUL(-0.2, L)));
+    double w = AP_SUB(AP_MUL(r, r), RR);
+#if defined(__CUDA_ARCH__)
+    return AP_MUL(AP_MUL(AP_MUL(fit, K2), r), rsqrt(w));
+#else
+    return AP_MUL(AP_MUL(fit, K2), r) / sqrt(w);
+#endif
   }
 };
 
@@ -134,8 +142,8 @@ AP_HD double b16_tau_2D(const double* ctx, double R, QagiResult* info = nullptr)
   f.inv_R200xc = ctx[0];
   f.alpha = ctx[1];
   f.expo = ctx[2];
-  f.K = ctx[3];
-  f.R = R;
+  f.K2 = 2.0 * ctx[3];
+  f.RR = AP_MUL(R, R);
   QagiResult q = qagi_upper(f, R, 0.0, 1.0e-2);  // utils.py:448
   if (info) *info = q;
   return q.result;

@@ -25,73 +25,84 @@ struct QagiResult {
 };
 
 // 15-point transformed Gauss-Kronrod rule on (a, b) subset of (0, 1], x = boun + (1-t)/t.
-// The node/weight tables are compile-time scalars and the pair loop is unrolled by hand: with
-// local `const double xgk[8]` arrays nvcc 12.9 (sm_100a, -O3) overlapped the tables' local-memory
-// slots with the caller's epsilon table after inlining (device results diverged from the host
-// build), so no table lives in local memory.
-namespace gk15 {
-constexpr double x0 = 0.991455371120812639206854697526329, x1 = 0.949107912342758524526189684047851,
-                 x2 = 0.864864423359769072789712788640926, x3 = 0.741531185599394439863864773280788,
-                 x4 = 0.586087235467691130294144838258730, x5 = 0.405845151377397166906606412076961,
-                 x6 = 0.207784955007898467600689403773245;
-constexpr double g1 = 0.129484966168869693270611432679082, g3 = 0.279705391489276667901467771423780,
-                 g5 = 0.381830050505118944950369775488975, g7 = 0.417959183673469387755102040816327;
-constexpr double k0 = 0.022935322010529224963732008058970, k1 = 0.063092092629978553290700663189204,
-                 k2 = 0.104790010322250183839876322541518, k3 = 0.140653259715525918745189590510238,
-                 k4 = 0.169004726639267902826583426598550, k5 = 0.190350578064785409913256402421014,
-                 k6 = 0.204432940075298892414161999234649, k7 = 0.209482141084727828012999174891714;
-}  // namespace gk15
+//
+// Code-size note (measured, profiles/): fully inlining the rule at its three call sites with the 15
+// integrand evaluations unrolled produced a 270 KB kernel that thrashed the instruction cache.
+// The rule is therefore ONE out-of-line device function with a rolled pair loop, and its
+// node/weight tables live in __constant__ memory (uniform broadcast loads).  An earlier version
+// kept the tables as function-local arrays: after inlining, nvcc 12.9 (-O3, sm_100a) overlapped
+// their local-memory slots with the caller's epsilon table and the device results diverged from
+// the host build — tests/test_gpu_parity.py::test_device_quadpack_matches_scipy guards this.
+#if defined(__CUDACC__)
+#define AP_TABLE_DECL static __constant__
+#define AP_NOINLINE __noinline__
+#else
+#define AP_TABLE_DECL static const
+#define AP_NOINLINE
+#endif
+#if defined(__CUDA_ARCH__) || !defined(__CUDACC__)
+#define AP_GK(t) gk15_##t
+#else
+#define AP_GK(t) gk15h_##t
+#endif
+#define AP_GK15_XGK {0.991455371120812639206854697526329, 0.949107912342758524526189684047851, \
+                     0.864864423359769072789712788640926, 0.741531185599394439863864773280788, \
+                     0.586087235467691130294144838258730, 0.405845151377397166906606412076961, \
+                     0.207784955007898467600689403773245, 0.0}
+#define AP_GK15_WG {0.0, 0.129484966168869693270611432679082, 0.0, 0.279705391489276667901467771423780, \
+                    0.0, 0.381830050505118944950369775488975, 0.0, 0.417959183673469387755102040816327}
+#define AP_GK15_WGK {0.022935322010529224963732008058970, 0.063092092629978553290700663189204, \
+                     0.104790010322250183839876322541518, 0.140653259715525918745189590510238, \
+                     0.169004726639267902826583426598550, 0.190350578064785409913256402421014, \
+                     0.204432940075298892414161999234649, 0.209482141084727828012999174891714}
+AP_TABLE_DECL double gk15_xgk[8] = AP_GK15_XGK;
+AP_TABLE_DECL double gk15_wg[8] = AP_GK15_WG;
+AP_TABLE_DECL double gk15_wgk[8] = AP_GK15_WGK;
+#if defined(__CUDACC__)
+// host pass of nvcc (the host-buffer entry points never integrate, but the templates must compile)
+static const double gk15h_xgk[8] = AP_GK15_XGK;
+static const double gk15h_wg[8] = AP_GK15_WG;
+static const double gk15h_wgk[8] = AP_GK15_WGK;
+#endif
 
 template <class F>
-AP_HD void qk15i(const F& f, double boun, double a, double b, double& result, double& abserr,
-                 double& resabs, double& resasc) {
+AP_NOINLINE AP_HD_NOINLINE void qk15i(const F& f, double boun, double a, double b, double& result,
+                                      double& abserr, double& resabs, double& resasc) {
+  double fv1[7], fv2[7];
   double centr = AP_MUL(0.5, AP_ADD(a, b));
   double hlgth = AP_MUL(0.5, AP_SUB(b, a));
-  double tabsc1 = AP_ADD(boun, AP_SUB(1.0, centr) / centr);
-  double fval1 = f(tabsc1);
-  double fc = (fval1 / centr) / centr;
-  double resg = AP_MUL(gk15::g7, fc);
-  double resk = AP_MUL(gk15::k7, fc);
+  // x = boun + (1 - t) / t and the Jacobian 1 / t^2 share one reciprocal (QUADPACK divides three
+  // times; the results differ by <= 1 ulp)
+  double ic = 1.0 / centr;
+  double fval1 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, centr), ic)));
+  double fc = AP_MUL(AP_MUL(fval1, ic), ic);
+  double resg = AP_MUL(AP_GK(wg)[7], fc);
+  double resk = AP_MUL(AP_GK(wgk)[7], fc);
   resabs = fabs(resk);
-  double v1_0, v1_1, v1_2, v1_3, v1_4, v1_5, v1_6, v2_0, v2_1, v2_2, v2_3, v2_4, v2_5, v2_6;
-#define AP_GK_PAIR(XGK, WG, WGK, V1, V2)                                                  \
-  {                                                                                       \
-    double absc = AP_MUL(hlgth, XGK);                                                     \
-    double absc1 = AP_SUB(centr, absc);                                                   \
-    double absc2 = AP_ADD(centr, absc);                                                   \
-    double t1 = AP_ADD(boun, AP_SUB(1.0, absc1) / absc1);                                 \
-    double t2 = AP_ADD(boun, AP_SUB(1.0, absc2) / absc2);                                 \
-    double f1 = f(t1);                                                                    \
-    double f2 = f(t2);                                                                    \
-    f1 = (f1 / absc1) / absc1;                                                            \
-    f2 = (f2 / absc2) / absc2;                                                            \
-    V1 = f1;                                                                              \
-    V2 = f2;                                                                              \
-    double fsum = AP_ADD(f1, f2);                                                         \
-    resg = AP_ADD(resg, AP_MUL(WG, fsum));                                                \
-    resk = AP_ADD(resk, AP_MUL(WGK, fsum));                                               \
-    resabs = AP_ADD(resabs, AP_MUL(WGK, AP_ADD(fabs(f1), fabs(f2))));                     \
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int j = 0; j < 7; ++j) {
+    double absc = AP_MUL(hlgth, AP_GK(xgk)[j]);
+    double absc1 = AP_SUB(centr, absc);
+    double absc2 = AP_ADD(centr, absc);
+    double i1 = 1.0 / absc1, i2 = 1.0 / absc2;
+    double f1 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, absc1), i1)));
+    double f2 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, absc2), i2)));
+    f1 = AP_MUL(AP_MUL(f1, i1), i1);
+    f2 = AP_MUL(AP_MUL(f2, i2), i2);
+    fv1[j] = f1;
+    fv2[j] = f2;
+    double fsum = AP_ADD(f1, f2);
+    resg = AP_ADD(resg, AP_MUL(AP_GK(wg)[j], fsum));
+    resk = AP_ADD(resk, AP_MUL(AP_GK(wgk)[j], fsum));
+    resabs = AP_ADD(resabs, AP_MUL(AP_GK(wgk)[j], AP_ADD(fabs(f1), fabs(f2))));
   }
-  AP_GK_PAIR(gk15::x0, 0.0, gk15::k0, v1_0, v2_0)
-  AP_GK_PAIR(gk15::x1, gk15::g1, gk15::k1, v1_1, v2_1)
-  AP_GK_PAIR(gk15::x2, 0.0, gk15::k2, v1_2, v2_2)
-  AP_GK_PAIR(gk15::x3, gk15::g3, gk15::k3, v1_3, v2_3)
-  AP_GK_PAIR(gk15::x4, 0.0, gk15::k4, v1_4, v2_4)
-  AP_GK_PAIR(gk15::x5, gk15::g5, gk15::k5, v1_5, v2_5)
-  AP_GK_PAIR(gk15::x6, 0.0, gk15::k6, v1_6, v2_6)
-#undef AP_GK_PAIR
   double reskh = AP_MUL(resk, 0.5);
-  resasc = AP_MUL(gk15::k7, fabs(AP_SUB(fc, reskh)));
-#define AP_GK_ASC(WGK, V1, V2) \
-  resasc = AP_ADD(resasc, AP_MUL(WGK, AP_ADD(fabs(AP_SUB(V1, reskh)), fabs(AP_SUB(V2, reskh)))));
-  AP_GK_ASC(gk15::k0, v1_0, v2_0)
-  AP_GK_ASC(gk15::k1, v1_1, v2_1)
-  AP_GK_ASC(gk15::k2, v1_2, v2_2)
-  AP_GK_ASC(gk15::k3, v1_3, v2_3)
-  AP_GK_ASC(gk15::k4, v1_4, v2_4)
-  AP_GK_ASC(gk15::k5, v1_5, v2_5)
-  AP_GK_ASC(gk15::k6, v1_6, v2_6)
-#undef AP_GK_ASC
+  resasc = AP_MUL(AP_GK(wgk)[7], fabs(AP_SUB(fc, reskh)));
+  for (int j = 0; j < 7; ++j)
+    resasc = AP_ADD(resasc, AP_MUL(AP_GK(wgk)[j], AP_ADD(fabs(AP_SUB(fv1[j], reskh)),
+                                                         fabs(AP_SUB(fv2[j], reskh)))));
   result = AP_MUL(resk, hlgth);
   resasc = AP_MUL(resasc, hlgth);
   resabs = AP_MUL(resabs, hlgth);
@@ -105,7 +116,7 @@ AP_HD void qk15i(const F& f, double boun, double a, double b, double& result, do
 }
 
 // epsilon algorithm (dqelg).  epstab has 52 entries, 1-based in the original.
-AP_HD_NOINLINE void qelg(int& n, double* epstab, double& result, double& abserr, double* res3la,
+AP_NOINLINE AP_HD_NOINLINE void qelg(int& n, double* epstab, double& result, double& abserr, double* res3la,
                          int& nres) {
   nres += 1;
   abserr = kOflow;
@@ -195,7 +206,7 @@ AP_HD_NOINLINE void qelg(int& n, double* epstab, double& result, double& abserr,
 }
 
 // dqpsrt: keep iord (1-based indices stored in a 0-based array) sorted by decreasing elist.
-AP_HD_NOINLINE void qpsrt(int limit, int last, int& maxerr, double& ermax, const double* elist,
+AP_NOINLINE AP_HD_NOINLINE void qpsrt(int limit, int last, int& maxerr, double& ermax, const double* elist,
                           int* iord, int& nrmax) {
   if (last <= 2) {
     iord[0] = 1;
@@ -254,7 +265,7 @@ AP_HD_NOINLINE void qpsrt(int limit, int last, int& maxerr, double& ermax, const
 
 // dqagie with inf = 1: integral of f over (bound, +inf).
 template <class F>
-AP_HD_NOINLINE QagiResult qagi_upper(const F& f, double bound, double epsabs, double epsrel) {
+AP_NOINLINE AP_HD_NOINLINE QagiResult qagi_upper(const F& f, double bound, double epsabs, double epsrel) {
   const int limit = kQagiLimit;
   double alist[kQagiLimit], blist[kQagiLimit], rlist[kQagiLimit], elist[kQagiLimit];
   int iord[kQagiLimit];
