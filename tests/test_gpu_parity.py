@@ -426,3 +426,47 @@ def test_full_size_properties():
     assert float((da - db).abs().max().item()) <= 1e-9 * scale
     del da, db, dmap
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------ committed golden fixtures
+def test_cuda_path_matches_golden_fixtures():
+    """tests/golden/golden_small.npz (made by tests/golden/make_golden.py from the oracle)."""
+    import hashlib
+    import os
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    from astropaint_b200.profiles import spherical, NFW, Battaglia16
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.npz"))
+    cat = ap.Catalog("test")
+    canvas = ap.Canvas(cat, 64, R_times=5)
+    pix = list(canvas.discs.gen_pixel_index())
+    assert np.array_equal(g["test6_counts"], [len(p) for p in pix])
+    sha = np.frombuffer(hashlib.sha256(np.concatenate(pix).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(g["test6_sha256"], sha)
+    ap.Painter(spherical.gaussian_2D).spray(canvas)
+    map_close(canvas.pixels, g["test6_gaussian_map"], 1e-6)
+    cat = ap.Catalog(synthetic.random_box(50, seed=0))
+    canvas = ap.Canvas(cat, 128, R_times=5)
+    p = ap.Painter(spherical.gaussian_2D)
+    p.spray(canvas)
+    assert int(p.last_spray["d_count"].item()) == int(g["box_pairs"])
+    map_close(canvas.pixels, g["box_gaussian_map"], 1e-6)
+    stack = canvas.stack_cutouts(np.arange(10), lon_range=[-2, 2], xpix=32, inplace=False)
+    map_close(stack, g["box_stack"], 1e-6)
+    for tmpl, key in [(NFW.kSZ_T, "box_nfw_ksz_map"), (NFW.BG, "box_nfw_bg_map")]:
+        canvas = ap.Canvas(cat, 128, R_times=3)
+        ap.Painter(tmpl).spray(canvas)
+        map_close(canvas.pixels, g[key], 1e-6)
+    cat = ap.Catalog(synthetic.websky_like(16, seed=5, m_min=2e14))
+    canvas = ap.Canvas(cat, 1024, R_times=5)
+    p = ap.Painter(Battaglia16.kSZ_T)
+    p.spray(canvas)
+    assert int(p.last_spray["d_count"].item()) == int(g["websky_pairs"])
+    want = np.zeros(12 * 1024 * 1024)
+    want[g["websky_ksz_idx"]] = g["websky_ksz_val"]
+    map_close(canvas.pixels, want, 1e-6)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()

@@ -1,0 +1,172 @@
+"""CPU tests of the host-side mirror of the reference API (no compute calls: no GPU here)."""
+import ctypes as C
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from astropaint_b200 import _capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "astropaint_b200.h")).read()
+    declared = set(re.findall(r"\b(ap_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 14
+    lib = C.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/astropaint_b200.h but not exported"
+    assert declared == set(_capi.SIGNATURES), "ctypes SIGNATURES out of sync with the header"
+    assert _capi.lib().ap_version() == 100
+
+
+def test_no_cpu_fallback_product_path_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import spherical
+    canvas = ap.Canvas(ap.Catalog("test"), 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ap.Painter(spherical.gaussian_2D).spray(canvas)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        next(canvas.discs.gen_pixel_index())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        canvas.stack_cutouts()
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "astropaint_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_import_surface_matches_reference():
+    import astropaint_b200 as ap
+    from astropaint_b200 import Catalog, Canvas, Painter, transform, utils, LOS_integrate, interpolate  # noqa: F401
+    from astropaint_b200.lib.utils import LOS_integrate as L2, interpolate as I2  # noqa: F401
+    from astropaint_b200.profiles import NFW, Battaglia16, spherical  # noqa: F401
+    assert inspect.signature(Canvas.__init__).parameters.keys() >= {"catalog", "nside", "mode", "R_times", "inclusive"}
+    sig = inspect.signature(Painter.spray)
+    assert list(sig.parameters)[:7] == ["self", "canvas", "distance_units", "n_cpus", "cache", "lazy", "lazy_grid"]
+    sig = inspect.signature(Canvas.stack_cutouts)
+    assert list(sig.parameters)[1:] == ["halo_list", "lon_range", "lat_range", "xpix", "ypix", "inplace",
+                                        "parallel", "apply_func", "func_kwargs"]
+
+
+def test_catalog_fixture_and_columns(test_catalog):
+    """reference tests/test_Catalog.py:7-26"""
+    d = test_catalog.data
+    for c in ["x", "y", "z", "v_x", "v_y", "v_z", "M_200c", "redshift", "D_c", "lat", "lon", "theta", "phi", "D_a",
+              "R_200c", "c_200c", "R_ang_200c", "rho_s", "R_s", "v_r", "v_th", "v_ph", "v_lat", "v_lon"]:
+        assert c in d.columns
+    assert test_catalog.size == len(d) == 6
+    assert np.allclose(d.D_c, 100) and np.allclose(d.redshift, 0)
+    assert np.allclose(sorted(d.lat), [-90, 0, 0, 0, 0, 90])
+
+
+def test_random_box_uses_reference_rng_order():
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    np.random.seed(0)
+    cat = ap.Catalog()
+    cat.generate_random_box(n_tot=100)
+    want = synthetic.random_box(100, seed=0)
+    for c in want.columns:
+        assert np.array_equal(cat.data[c].values, want[c].values)
+
+
+def test_canvas_state_flags(test_canvas):
+    """reference tests/test_Canvas.py:9-61 (the parts that do not need spherical harmonics)"""
+    test_canvas.clean()
+    assert not test_canvas._pixel_is_outdated and test_canvas._alm_is_outdated and test_canvas._Cl_is_outdated
+    assert (test_canvas.pixels == 0).all() and test_canvas.pixels.shape == (12 * 64 * 64,)
+    test_canvas.pixels = 1
+    assert not test_canvas._pixel_is_outdated and test_canvas._alm_is_outdated and test_canvas._Cl_is_outdated
+    test_canvas.alm = 1
+    assert test_canvas._pixel_is_outdated and not test_canvas._alm_is_outdated and test_canvas._Cl_is_outdated
+    with pytest.raises(AttributeError):
+        test_canvas.Cl = 1
+    assert test_canvas.lmax == 3 * 64 - 1 and test_canvas.npix == 12 * 64 * 64
+    assert test_canvas.R_max == test_canvas.catalog.data.R_200c.max()
+
+
+def test_painter_introspection_and_marshalling(test_catalog):
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import NFW, Battaglia16
+
+    p = ap.Painter(NFW.kSZ_T)
+    assert p.template_args_list == ["R", "rho_s", "R_s", "v_r"] and p.template_kwargs_list == ["T_cmb"]
+    assert p.R_arg_indx == 0 and p.template_name == "kSZ_T"
+    p = ap.Painter(NFW.BG)
+    assert p.template_args_list[0] == "R_vec"
+    p = ap.Painter(Battaglia16.tau_2D_interp)       # decorators keep the wrapped signature
+    assert p.template_args_list == ["R", "R_200c", "M_200c", "redshift"]
+    with pytest.raises(AssertionError):
+        ap.Painter(lambda r, M_200c: r)
+    with pytest.raises(AssertionError):
+        ap.Painter(lambda R, R_vec: R)
+
+    def tmpl(R, R_200c, amplitude, *, power=2.0):
+        return amplitude * (R / R_200c) ** power
+
+    p = ap.Painter(tmpl)
+    cols = p._shake_canister(test_catalog, {"amplitude": 3.0, "power": [1.0, 2, 3, 4, 5, 6]})
+    assert set(cols) == {"R_200c", "amplitude", "power"}
+    assert np.array_equal(cols["amplitude"], np.full(6, 3.0)) and cols["power"][5] == 6
+    with pytest.raises(ValueError):
+        p._shake_canister(test_catalog, {"amplitude": [1.0, 2.0]})
+    vals = p.calculate_template(np.linspace(0, 1, 5), test_catalog, halo_list=[0, 2], amplitude=2.0)
+    assert vals.shape == (2, 5)
+    canvas = ap.Canvas(test_catalog, 16)
+    with pytest.raises(ValueError):
+        p.spray(canvas, n_cpus=0, amplitude=1.0)
+    with pytest.raises(AssertionError):
+        p.spray(canvas, distance_units="km", amplitude=1.0)
+    with pytest.raises(AssertionError):
+        ap.Painter(NFW.BG).spray(canvas, cache=True)
+
+
+def test_decorators_keep_reference_semantics():
+    from astropaint_b200 import LOS_integrate, interpolate
+    from oracle import profiles_np as oprof
+
+    def g3(r, a):
+        return np.exp(-(r / a) ** 2)
+
+    @LOS_integrate
+    def g2(R, a):
+        return g3(R, a)
+
+    @interpolate(n_samples=12, sampling_method="logspace")
+    @LOS_integrate
+    def g2i(R, a):
+        return g3(R, a)
+
+    @interpolate
+    def bare(R, a):
+        return g3(R, a)
+
+    assert inspect.getfullargspec(g2i).args == ["R", "a"]
+    assert g2i._ap_interp["n_samples"] == 12 and g2i._ap_interp["sampling_method"] == "logspace"
+    assert bare._ap_interp["n_samples"] == 20
+    R = np.linspace(0.05, 2, 40)
+    assert np.allclose(g2(R, 0.8), np.sqrt(np.pi) * 0.8 * np.exp(-(R / 0.8) ** 2), rtol=2e-2)   # analytic Abel pair
+    want = oprof.interpolate(lambda RR, a: oprof.los_integrate(g3, RR, a), R, 0.8, n_samples=12,
+                             sampling_method="logspace")
+    assert np.allclose(g2i(R, 0.8), want, rtol=1e-12)
+    assert np.allclose(g2i(R[:5], 0.8), g2(R[:5], 0.8))      # len(R) < n_samples: direct evaluation
+    assert np.isscalar(float(g2(0.3, 0.8)))
+
+
+def test_shard_rows_is_array_split():
+    from astropaint_b200 import parallel
+    for n, w in [(10, 3), (7, 8), (1000, 8), (0, 2)]:
+        parts = [parallel.shard_rows(n, r, w) for r in range(w)]
+        assert np.array_equal(np.concatenate(parts), np.arange(n))
+        want = np.array_split(np.arange(n), w)
+        assert all(np.array_equal(a, b) for a, b in zip(parts, want))

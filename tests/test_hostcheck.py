@@ -1,0 +1,177 @@
+"""CPU tests of the DEVICE arithmetic: csrc/{healpix,geom,qagi,profiles,spline}.cuh compiled for
+the host (libap_hostcheck.so, test-only) against the oracle and scipy.  Integer results (pixel
+sets, vec2pix) must be bit-exact; QUADPACK must reproduce scipy's decisions (same neval)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import healpix_np as H, profiles_np as oprof, reference_loop as ref
+
+d, i64 = C.c_double, C.c_int64
+
+
+@pytest.fixture(scope="module")
+def hc():
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L = C.CDLL(os.path.join(here, "astropaint_b200", "_native", "libap_hostcheck.so"))
+    L.hc_query_disc.restype = i64
+    L.hc_query_disc.argtypes = [i64, d, d, d, d, C.c_void_p, i64]
+    L.hc_disc_R.restype = i64
+    L.hc_disc_R.argtypes = [i64, d, d, d, d, d, d, d, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    L.hc_vec2pix.argtypes = [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hc_qagi_b16.argtypes = [d, d, d, d, C.POINTER(d), C.POINTER(d), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.hc_critical_density.restype = d
+    L.hc_critical_density.argtypes = [d]
+    L.hc_b16_tau_3D.restype = d
+    L.hc_b16_tau_3D.argtypes = [d, d, d, d]
+    L.hc_profile_R.argtypes = [C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    L.hc_profile_vec.argtypes = [C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    L.hc_spline.argtypes = [C.c_int, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("nside", [1, 2, 8, 64, 512, 8192])
+def test_disc_pixel_sets_bit_exact(hc, nside):
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(100 + nside)
+    axes = [np.array(v, dtype=float) for v in [(0, 0, 1), (0, 0, -1), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0)]]
+    n_cases = 300 if nside <= 512 else 120
+    buf = np.empty(min(hp.npix, 1 << 24), dtype=np.int64)
+    for t in range(n_cases):
+        v = axes[t] * 100 if t < 6 else rng.normal(size=3) * rng.uniform(0.1, 100)
+        if nside <= 512:
+            r = rng.choice([rng.uniform(0, 0.2), rng.uniform(0, np.pi * 1.05), rng.uniform(0, 3 / nside)])
+        else:
+            r = rng.choice([rng.uniform(0, 5e-3), rng.uniform(0, 3 / nside)])
+        want = hp.query_disc(v, r)
+        n = hc.hc_query_disc(nside, v[0], v[1], v[2], r, _p(buf), len(buf))
+        assert n == len(want)
+        assert np.array_equal(buf[:n], want)
+
+
+def test_R_and_R_vec_match_healpy_formulas(hc):
+    rng = np.random.default_rng(5)
+    for nside in (8, 64, 512):
+        hp = H.HealpixRing(nside)
+        for _ in range(100):
+            v = rng.normal(size=3) * rng.uniform(1, 100)
+            r = rng.choice([rng.uniform(0, 0.2), rng.uniform(0, np.pi), rng.uniform(0, 5 / nside)])
+            th = np.arctan2(np.hypot(v[0], v[1]), v[2])
+            ph = np.arctan2(v[1], v[0]) % (2 * np.pi)
+            Da = np.linalg.norm(v)
+            q = hp.query_disc(v, r)
+            if len(q) == 0:
+                continue
+            R = np.empty(len(q))
+            Rv = np.empty((len(q), 3))
+            rmin, rmax = d(), d()
+            hc.hc_disc_R(nside, v[0], v[1], v[2], r, th, ph, Da, _p(R), _p(Rv), len(q), C.byref(rmin), C.byref(rmax))
+            Rref = Da * H.angdist(np.array(hp.pix2ang(q)), (th, ph))
+            Rvref = Da * (np.asarray(hp.pix2vec(q)).T - H.ang2vec(th, ph))
+            ok = Rref > 0
+            assert np.abs(R[ok] - Rref[ok]).max() <= 1e-10 * Rref.max()
+            assert np.abs(Rv - Rvref).max() <= 1e-13 * Da
+            assert abs(rmin.value - Rref.min()) <= 1e-10 * Rref.max()
+            assert abs(rmax.value - Rref.max()) <= 1e-10 * Rref.max()
+
+
+@pytest.mark.parametrize("nside", [1, 4, 64, 8192])
+def test_vec2pix_bit_exact(hc, nside):
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(nside)
+    v = rng.normal(size=(3, 20000))
+    v[:, :100] = np.array([[0, 0, 1.0]]).T + 1e-3 * rng.normal(size=(3, 100))     # polar caps
+    v[:, 100:200] = np.array([[0, 0, -1.0]]).T + 1e-3 * rng.normal(size=(3, 100))
+    x, y, z = (np.ascontiguousarray(a) for a in v)
+    out = np.empty(x.size, dtype=np.int64)
+    hc.hc_vec2pix(nside, x.size, _p(x), _p(y), _p(z), _p(out))
+    assert np.array_equal(out, hp.vec2pix(x, y, z))
+
+
+def test_quadpack_restatement_equals_scipy(hc):
+    from scipy import integrate
+    import warnings
+    rng = np.random.default_rng(2)
+    n_checked = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(120):
+            M = 10 ** rng.uniform(13, 15.5)
+            z = rng.uniform(0, 4.6)
+            R200 = float(ref.M_200c_to_R_200c(M, z))
+            for R in np.linspace(rng.uniform(0, 0.1) * R200 * rng.choice([1, 0.01]), 5 * R200 * rng.uniform(0.2, 1), 8):
+                if R <= 0:
+                    continue
+                f = lambda r: oprof.b16_tau_3D(r, R200, M, z) * 2. * r / np.sqrt(r ** 2 - R ** 2)  # noqa: E731
+                v, e, info = integrate.quad(f, R, np.inf, epsabs=0., epsrel=1e-2, full_output=1)[:3]
+                res, ae, ne, ier = d(), d(), C.c_int(), C.c_int()
+                hc.hc_qagi_b16(R, R200, M, z, C.byref(res), C.byref(ae), C.byref(ne), C.byref(ier))
+                assert ne.value == info["neval"]
+                assert abs(res.value - v) <= 1e-10 * abs(v)
+                n_checked += 1
+    assert n_checked > 800
+
+
+def test_cosmology_and_tau3d(hc):
+    for z in (0.0, 0.3, 1.0, 4.6):
+        assert abs(hc.hc_critical_density(z) / oprof.critical_density(z) - 1) < 1e-14
+        assert abs(hc.hc_b16_tau_3D(0.3, 1.1, 3e14, z) / oprof.b16_tau_3D(0.3, 1.1, 3e14, z) - 1) < 1e-13
+
+
+def test_spline_is_scipy_not_a_knot(hc):
+    from scipy.interpolate import InterpolatedUnivariateSpline
+    rng = np.random.default_rng(9)
+    for t in range(100):
+        n = int(rng.integers(4, 30))
+        x = np.sort(rng.uniform(0, 5, n))
+        if t % 2:
+            x = np.linspace(x[0], x[-1], n)
+        if t % 5 == 0:
+            x = np.logspace(-3, 0.5, n)
+        y = np.exp(-x) * (1 + 0.1 * rng.normal(size=n))
+        X = rng.uniform(x[0], x[-1], 200)
+        out = np.empty(200)
+        assert hc.hc_spline(n, _p(x), _p(y), 200, _p(X), _p(out)) == 0
+        want = InterpolatedUnivariateSpline(x, y, k=3)(X)
+        assert np.abs(out - want).max() <= 1e-9 * np.abs(y).max()
+
+
+PROFILES = [
+    (0, [2.5], lambda R, p: np.full_like(R, p[0])),
+    (1, [0.5, 2.0], lambda R, p: oprof.linear_density_2D(R, *p)),
+    (2, [1e15, 2.0], lambda R, p: oprof.solid_sphere_2D(R, *p)),
+    (3, [1.3, 4.0, -2.0, 7.0], lambda R, p: oprof.gaussian_readme(R, *p)),
+    (4, [1e15, 0.4], lambda R, p: oprof.nfw_rho_2D_bartlemann(R, *p)),
+    (5, [1e15, 0.4], lambda R, p: oprof.nfw_tau_2D(R, *p)),
+    (6, [1e15, 0.4, -320.0, 2.7251], lambda R, p: oprof.nfw_kSZ_T(R, p[0], p[1], p[2], T_cmb=p[3])),
+    (7, [4.5, 1.6, 8e14], lambda R, p: oprof.nfw_deflection_angle(R, *p)),
+]
+
+
+@pytest.mark.parametrize("pid,params,fn", PROFILES)
+def test_device_profiles_equal_reference_formulas(hc, pid, params, fn):
+    R = np.concatenate([np.linspace(0.01, 1.9, 40), np.linspace(2.1, 9, 20)])
+    p = np.array(params, dtype=np.float64)
+    out = np.empty_like(R)
+    assert hc.hc_profile_R(pid, _p(p), R.size, _p(R), _p(out)) == 0
+    with np.errstate(invalid="ignore"):
+        want = np.asarray(fn(R, params), dtype=np.float64)
+    assert np.array_equal(np.isnan(out), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.allclose(out[ok], want[ok], rtol=1e-12, atol=0)
+
+
+def test_device_BG_equals_reference_formula(hc):
+    rng = np.random.default_rng(4)
+    Rv = rng.normal(size=(50, 3)) * 2
+    p = np.array([4.5, 1.6, 8e14, 0.7, 2.1, 150.0, -90.0, 2.7251])
+    out = np.empty(50)
+    assert hc.hc_profile_vec(8, _p(p), 50, _p(Rv), _p(out)) == 0
+    want = oprof.nfw_BG(Rv, *p[:7], T_cmb=p[7])
+    assert np.allclose(out, want, rtol=1e-12)

@@ -1,0 +1,142 @@
+"""CPU tests of the oracle itself.  The reference's tests pin no numbers for this path and healpy
+is absent (parity unpinned), so the oracle is pinned by construction-true properties and by the
+committed golden vectors (tests/golden/, generated from it: a regression pin)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import healpix_np as H, reference_loop as ref, profiles_np as oprof
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.npz")
+
+
+@pytest.mark.parametrize("nside", [1, 2, 4, 16, 64])
+def test_pix_vec_ang_round_trips(nside):
+    hp = H.HealpixRing(nside)
+    pix = np.arange(hp.npix)
+    x, y, z = hp.pix2vec(pix)
+    assert np.allclose(x * x + y * y + z * z, 1.0, atol=1e-14)
+    assert np.array_equal(hp.vec2pix(x, y, z), pix)
+    assert np.array_equal(hp.vec2pix(3.7 * x, 3.7 * y, 3.7 * z), pix)   # un-normalised input
+    th, ph = hp.pix2ang(pix)
+    assert np.array_equal(hp.ang2pix(th, ph), pix)
+    # ring structure: startpix/ringpix tile [0, npix) and z decreases ring by ring
+    total, zs = 0, []
+    for r in range(1, 4 * nside):
+        sp, rp, _ = hp.ring_info(r)
+        assert sp == total
+        total += rp
+        zs.append(hp.ring2z(r))
+    assert total == hp.npix
+    assert np.all(np.diff(zs) < 0)
+
+
+@pytest.mark.parametrize("nside", [1, 4, 16, 64])
+def test_query_disc_is_brute_force_disc(nside):
+    """{p : angdist(p, c) <= r} over ALL pixels, 250 random discs incl. poles / whole sky / empty."""
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(nside)
+    pix = np.arange(hp.npix)
+    th, ph = hp.pix2ang(pix)
+    for t in range(250):
+        v = rng.normal(size=3) * rng.uniform(0.1, 100)
+        if t % 25 == 0:
+            v = np.array([0.0, 0.0, 1.0 if t % 50 else -1.0])
+        r = rng.choice([rng.uniform(0, 0.2), rng.uniform(0, np.pi * 1.05), rng.uniform(0, 3 / nside)])
+        q = hp.query_disc(v, r)
+        assert np.all(np.diff(q) > 0)
+        thc = np.arctan2(np.hypot(v[0], v[1]), v[2])
+        phc = np.arctan2(v[1], v[0])
+        d = H.angdist(np.array([th, ph]), (thc, phc))
+        diff = np.setxor1d(q, pix[d <= r])
+        assert len(diff) == 0 or np.abs(d[diff] - r).max() < 1e-9   # only exact boundary ties may differ
+
+
+def test_cartesian_projection_orientation():
+    """centre of the cutout is the halo; +y is north; +x is west (astro flip)."""
+    nside = 256
+    hp = H.HealpixRing(nside)
+    m = np.arange(hp.npix, dtype=np.float64)
+    lon, lat = 40.0, 25.0
+    img = H.cartesian_projmap(hp, m, lon, lat, [-1, 1], [-1, 1], 101)
+    assert img.shape == (101, 101)
+    th, ph = hp.pix2ang(img[50, 50].astype(np.int64))
+    assert abs(np.degrees(ph[0]) - lon) < 0.3 and abs(90 - np.degrees(th[0]) - lat) < 0.3
+    th_n, _ = hp.pix2ang(img[100, 50].astype(np.int64))
+    assert (90 - np.degrees(th_n[0])) > lat + 0.7
+    _, ph_w = hp.pix2ang(img[50, 100].astype(np.int64))
+    assert np.degrees(ph_w[0]) < lon - 0.7
+    # ysize=None follows the lat/lon aspect ratio
+    assert H.cartesian_projmap(hp, m, lon, lat, [-2, 2], [-1, 1], 40).shape == (20, 40)
+
+
+def test_los_projection_of_tophat_is_analytic():
+    """README.md:170-218: LOS_integrate(tophat_3D) == 2 sqrt(R_200c^2 - R^2) (known answer)."""
+    R200 = 1.7
+
+    def tophat(r, R_200c):
+        return np.where(np.asarray(r) > R_200c, 0.0, 1.0)
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        R = np.linspace(0.05, 1.6, 12)
+        got = oprof.los_integrate(tophat, R, R200)
+    assert np.allclose(got, 2 * np.sqrt(R200 ** 2 - R ** 2), rtol=2e-2)   # quad runs at epsrel=1e-2
+
+
+def test_nfw_complex_forms_equal_real_closed_forms():
+    R = np.concatenate([np.linspace(0.01, 0.95, 30), np.linspace(1.05, 8, 30)]) * 0.4
+    x = R / 0.4
+    f_lt = 1 - 2 / np.sqrt(1 - x[x < 1] ** 2) * np.arctanh(np.sqrt((1 - x[x < 1]) / (1 + x[x < 1])))
+    f_gt = 1 - 2 / np.sqrt(x[x > 1] ** 2 - 1) * np.arctan(np.sqrt((x[x > 1] - 1) / (x[x > 1] + 1)))
+    want = 8 * 1e15 * 0.4 * np.concatenate([f_lt, f_gt]) / (x ** 2 - 1)
+    assert np.allclose(oprof.nfw_rho_2D_bartlemann(R, 1e15, 0.4), want, rtol=1e-12)
+
+
+def test_oracle_reproduces_golden_vectors():
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    g = np.load(GOLD)
+    cat = ap.Catalog("test")
+    discs = ref.Discs(cat.data, 64, 5)
+    pix = [discs.pixel_index(h) for h in range(6)]
+    assert np.array_equal(g["test6_counts"], [len(p) for p in pix])
+    sha = np.frombuffer(hashlib.sha256(np.concatenate(pix).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(g["test6_sha256"], sha)
+    # symmetry of the fixture: the four equatorial discs map onto each other under 90-degree
+    # rotations about z, the two polar discs under the north-south mirror
+    c = g["test6_counts"].tolist()
+    assert len(set(c[:4])) == 1 and c[4] == c[5]
+    m = np.zeros(12 * 64 * 64)
+    ref.spray(m, cat.data, 64, oprof.gaussian_readme, R_times=5)
+    assert np.allclose(m, g["test6_gaussian_map"], rtol=1e-13, atol=1e-13 * np.abs(m).max())
+    cat = ap.Catalog(synthetic.random_box(50, seed=0))
+    m = np.zeros(12 * 128 * 128)
+    n = ref.spray(m, cat.data, 128, oprof.nfw_kSZ_T, R_times=3)
+    assert np.allclose(m, g["box_nfw_ksz_map"], rtol=1e-12, atol=1e-13 * np.abs(m).max())
+    assert n > 0
+    cat = ap.Catalog(synthetic.websky_like(16, seed=5, m_min=2e14))
+    m = np.zeros(12 * 1024 * 1024)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n = ref.spray(m, cat.data, 1024, oprof.b16_kSZ_T, R_times=5)
+    assert n == int(g["websky_pairs"])
+    idx = np.nonzero(m)[0]
+    assert np.array_equal(idx, g["websky_ksz_idx"])
+    assert np.allclose(m[idx], g["websky_ksz_val"], rtol=1e-12)
+
+
+def test_catalog_columns_match_oracle_build_dataframe():
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    df = synthetic.websky_like(500, seed=3)
+    cat = ap.Catalog(df)
+    want = ref.build_dataframe(df)
+    assert list(cat.data.columns) == list(want.columns)
+    assert len(cat.data.columns) == 24
+    for c in want.columns:
+        assert np.allclose(cat.data[c].values, want[c].values, rtol=1e-14, atol=0), c
