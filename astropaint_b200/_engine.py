@@ -196,9 +196,10 @@ def spline_build(nodes, values, n_nodes):
     return coef
 
 
-def paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count=None):
+def paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count=None, uniform=False):
     s = halos.struct()
-    check(_capi.lib().ap_paint_table(nside, C.byref(s), nodes.shape[1], ptr(nodes), ptr(coef), ptr(n_nodes),
+    check(_capi.lib().ap_paint_table(nside, C.byref(s), nodes.shape[1], int(bool(uniform)), ptr(nodes), ptr(coef),
+                                     ptr(n_nodes),
                                      ptr(scale), ptr(d_map), ptr(d_count), stream_ptr()))
 
 

@@ -35,8 +35,9 @@ AP_HD HaloCenter make_center(double theta, double phi, double D_a, bool need_vec
 }
 
 struct RingGeom {
-  double A, B;           // hav = A + B sin^2(dphi/2)
-  double phi_step, phi_off;  // phi_p = (ip + phi_off) * phi_step
+  double A, B;           // hav = A + B sin^2(d / 2)
+  double phi_step, d0;   // d(j) = d0 + j * phi_step : azimuth of span pixel j minus phi_c, d0 in [-pi, pi)
+  double phi0;           // azimuth of span pixel 0 (R_vec mode)
   double z, sth;
 };
 
@@ -49,58 +50,92 @@ AP_HD RingGeom ring_geom(const Hpx& h, int64_t iz, const RingSpan& s, const Halo
   g.A = sh * sh;
   g.B = g.sth * c.sin_t;
   g.phi_step = kTwoPi / (double)s.nr;
-  g.phi_off = s.shifted ? 0.5 : 0.0;
+  g.phi0 = ((double)s.ip_lo + (s.shifted ? 0.5 : 0.0)) * g.phi_step;
+  double d = g.phi0 - c.phi;
+  g.d0 = d - kTwoPi * rint(d * kInvTwoPi);
   return g;
 }
 
-AP_HD double pixel_phi(const RingGeom& g, int32_t ip_raw) { return ((double)ip_raw + g.phi_off) * g.phi_step; }
+// span-local index (painting order, pixel = startpix + (ip_lo + j) mod nr) of ring-local index ip
+AP_HD int32_t span_j_of_ip(const RingSpan& s, int32_t ip) {
+  int32_t j = ip - s.ip_lo;
+  return j >= s.nr ? j - s.nr : j;
+}
 
-// angular separation [rad] between pixel ip_raw of the ring and the halo centre
-AP_HD double pixel_sep(const RingGeom& g, int32_t ip_raw, double phi_c) {
-  double S = sin(0.5 * (pixel_phi(g, ip_raw) - phi_c));
-  double hav = g.A + g.B * (S * S);
+// sin^2(d / 2); small arguments (every disc that is not polar or sky-sized) take a 5-term series
+AP_HD double sin2_half(double d) {
+  double x = 0.5 * d, s;
+  if (fabs(x) < 0.125) {
+    double x2 = x * x;  // next term x^10 / 39916800 < 2.4e-17 relative
+    s = x * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0 + x2 * (-1.0 / 5040.0 + x2 * (1.0 / 362880.0)))));
+  } else {
+    s = sin(x);
+  }
+  return s * s;
+}
+
+AP_HD double hav_of(const RingGeom& g, int32_t j) { return g.A + g.B * sin2_half(g.d0 + (double)j * g.phi_step); }
+
+// separation [rad] from its haversine: theta = 2 asin(sqrt(hav)); series below hav = 1e-4
+AP_HD double sep_from_hav(double hav) {
+  if (hav < 1.0e-4) {
+    if (!(hav > 0.0)) return 0.0;
+#if defined(__CUDA_ARCH__)
+    double sq = hav * rsqrt(hav);
+#else
+    double sq = sqrt(hav);
+#endif
+    // asin(s)/s = 1 + h/6 + 3h^2/40 + 15h^3/336 + 105h^4/3456 + ..., h = s^2 (next term < 3e-22)
+    return 2.0 * sq * (1.0 + hav * (1.0 / 6.0 + hav * (3.0 / 40.0 + hav * (15.0 / 336.0 + hav * (105.0 / 3456.0)))));
+  }
   if (hav < 0.5) return 2.0 * asin(sqrt(hav));
   double co = 1.0 - hav;
   if (co < 0.0) co = 0.0;
   return kPi - 2.0 * asin(sqrt(co));
 }
 
+// angular separation [rad] between span pixel j of the ring and the halo centre
+AP_HD double pixel_sep(const RingGeom& g, int32_t j) { return sep_from_hav(hav_of(g, j)); }
+
 // chord vector D_a * (p - c)
-AP_HD void pixel_chord(const RingGeom& g, int32_t ip_raw, const HaloCenter& c, double& rx, double& ry,
-                       double& rz) {
-  double sp, cp;
+AP_HD void pixel_chord(const RingGeom& g, int32_t j, const HaloCenter& c, double& rx, double& ry, double& rz) {
+  double sp, cp, phi = g.phi0 + (double)j * g.phi_step;
 #if defined(__CUDA_ARCH__)
-  sincos(pixel_phi(g, ip_raw), &sp, &cp);
+  sincos(phi, &sp, &cp);
 #else
-  sp = sin(pixel_phi(g, ip_raw));
-  cp = cos(pixel_phi(g, ip_raw));
+  sp = sin(phi);
+  cp = cos(phi);
 #endif
   rx = c.D_a * (g.sth * cp - c.cx);
   ry = c.D_a * (g.sth * sp - c.cy);
   rz = c.D_a * (g.z - c.cz);
 }
 
-// min / max separation over the pixels of one span (sin^2(dphi/2) is monotone in the azimuthal
-// distance, so only the span ends, the pixels next to phi_c and the pixels next to phi_c + pi
-// can be extremal).  Feeds R.min() / R.max() of @interpolate's sample_array (utils.py:411-412).
-AP_HD void span_sep_range(const RingGeom& g, const RingSpan& s, double phi_c, double& smin, double& smax) {
-  int32_t lo = s.ip_lo, hi = s.ip_lo + s.len - 1;
-  double a = pixel_sep(g, lo, phi_c), b = pixel_sep(g, hi, phi_c);
-  smin = fmin(a, b);
-  smax = fmax(a, b);
-  double t = phi_c / g.phi_step - g.phi_off;
-  for (int pass = 0; pass < 2; ++pass) {
-    int32_t k0 = (int32_t)floor(t + (pass ? 0.5 * (double)s.nr : 0.0));
-    for (int d = 0; d < 2; ++d) {
-      int32_t k = k0 + d;
-      while (k > hi) k -= s.nr;
-      while (k < lo) k += s.nr;
-      if (k > hi) continue;
-      double v = pixel_sep(g, k, phi_c);
-      smin = fmin(smin, v);
-      smax = fmax(smax, v);
+// min / max haversine over the len pixels of one span.  sin^2(d/2) is monotone in the azimuthal
+// distance |d mod 2pi|, so only the span ends and the pixels next to d = 0, 2pi (minimum) and
+// d = pi (maximum) can be extremal; they are ranked by |d| and only the two winners are evaluated.
+// Feeds R.min() / R.max() of @interpolate's sample_array (lib/utils.py:411-412).
+AP_HD void span_hav_range(const RingGeom& g, int32_t len, double& hmin, double& hmax) {
+  int32_t jmin = 0, jmax = 0;
+  double wmin = INFINITY, wmax = -INFINITY;
+  const double inv_step = 1.0 / g.phi_step;
+  for (int c = 0; c < 8; ++c) {
+    int32_t j;
+    if (c == 0) j = 0;
+    else if (c == 1) j = len - 1;
+    else {
+      double target = (c < 4) ? 0.0 : (c < 6 ? kTwoPi : kPi);
+      j = (int32_t)floor((target - g.d0) * inv_step) + (c & 1);
+      if (j < 0) j = 0;
+      if (j > len - 1) j = len - 1;
     }
+    double d = g.d0 + (double)j * g.phi_step;
+    double w = fabs(d - kTwoPi * rint(d * kInvTwoPi));
+    if (w < wmin) { wmin = w; jmin = j; }
+    if (w > wmax) { wmax = w; jmax = j; }
   }
+  hmin = hav_of(g, jmin);
+  hmax = hav_of(g, jmax);
 }
 
 }  // namespace ap

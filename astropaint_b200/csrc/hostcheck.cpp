@@ -45,27 +45,27 @@ int64_t hc_disc_R(int64_t nside, double x, double y, double z, double radius, do
   DiscHeader d = disc_header(h, x, y, z, radius);
   HaloCenter c = make_center(theta, phi, D_a, true);
   int64_t n = 0;
-  double smin = INFINITY, smax = -INFINITY;
+  double hmin = INFINITY, hmax = -INFINITY;
   for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
     RingSpan s = ring_span(h, d, iz);
     if (s.len <= 0) continue;
     RingGeom g = ring_geom(h, iz, s, c);
     double a, b;
-    span_sep_range(g, s, c.phi, a, b);
-    smin = fmin(smin, a);
-    smax = fmax(smax, b);
-    for (int32_t j = 0; j < s.len; ++j) {
-      int64_t p = span_pixel_sorted(s, j);
-      int32_t ip = (int32_t)(p - s.startpix);
+    span_hav_range(g, s.len, a, b);
+    hmin = fmin(hmin, a);
+    hmax = fmax(hmax, b);
+    for (int32_t jj = 0; jj < s.len; ++jj) {
+      int64_t p = span_pixel_sorted(s, jj);
+      int32_t j = span_j_of_ip(s, (int32_t)(p - s.startpix));
       if (n < cap) {
-        if (R) R[n] = c.D_a * pixel_sep(g, ip, c.phi);
-        if (Rvec) pixel_chord(g, ip, c, Rvec[3 * n], Rvec[3 * n + 1], Rvec[3 * n + 2]);
+        if (R) R[n] = c.D_a * pixel_sep(g, j);
+        if (Rvec) pixel_chord(g, j, c, Rvec[3 * n], Rvec[3 * n + 1], Rvec[3 * n + 2]);
       }
       ++n;
     }
   }
-  if (rmin) *rmin = D_a * smin;
-  if (rmax) *rmax = D_a * smax;
+  if (rmin) *rmin = D_a * sep_from_hav(hmin);
+  if (rmax) *rmax = D_a * sep_from_hav(hmax);
   return n;
 }
 

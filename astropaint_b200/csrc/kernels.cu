@@ -71,56 +71,6 @@ static int check_nside(int64_t nside) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: disc count (+ R range)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) disc_count_kernel(Hpx hpx, HalosDev H, int64_t* n_pix, int32_t* n_rings,
-                                                         double* rmin, double* rmax) {
-  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H.n) return;
-  DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
-  bool want_r = (rmin != nullptr);
-  HaloCenter c;
-  if (want_r) c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
-  int64_t total = 0;
-  double smin = INFINITY, smax = -INFINITY;
-  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
-    RingSpan s = ring_span(hpx, d, iz);
-    if (s.len <= 0) continue;
-    total += s.len;
-    if (want_r) {
-      RingGeom g = ring_geom(hpx, iz, s, c);
-      double a, b;
-      span_sep_range(g, s, c.phi, a, b);
-      smin = fmin(smin, a);
-      smax = fmax(smax, b);
-    }
-  }
-  n_pix[h] = total;
-  if (n_rings) n_rings[h] = (int32_t)disc_n_rings(d);
-  if (want_r) {
-    rmin[h] = (total > 0) ? c.D_a * smin : INFINITY;
-    rmax[h] = (total > 0) ? c.D_a * smax : -INFINITY;
-  }
-}
-
-extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
-                             int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream) {
-  if (check_nside(nside)) return 1;
-  bool want_r = d_rmin || d_rmax;
-  if (check_halos(halos, want_r)) return 1;
-  if (inclusive) return fail("inclusive=True disc query is not implemented");
-  if (want_r && (!d_rmin || !d_rmax)) return fail("d_rmin and d_rmax must both be given");
-  if (!d_n_pix) return fail("d_n_pix == NULL");
-  if (halos->n == 0) return 0;
-  int threads = 128;
-  int64_t blocks = (halos->n + threads - 1) / threads;
-  disc_count_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), d_n_pix,
-                                                                            d_n_rings, d_rmin, d_rmax);
-  AP_LAUNCH_CHECK();
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------
 // K1b: flat pixel list (+R, +R_vec); one warp per halo
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) disc_pixels_kernel(Hpx hpx, HalosDev H, const int64_t* pix_off, int64_t* pix,
@@ -143,11 +93,11 @@ __global__ void __launch_bounds__(256) disc_pixels_kernel(Hpx hpx, HalosDev H, c
       int64_t o = run + j;
       pix[o] = p;
       if (want) {
-        int32_t ip = (int32_t)(p - s.startpix);
-        if (R) R[o] = c.D_a * pixel_sep(g, ip, c.phi);
+        int32_t js = span_j_of_ip(s, (int32_t)(p - s.startpix));
+        if (R) R[o] = c.D_a * pixel_sep(g, js);
         if (Rvec) {
           double rx, ry, rz;
-          pixel_chord(g, ip, c, rx, ry, rz);
+          pixel_chord(g, js, c, rx, ry, rz);
           Rvec[3 * o + 0] = rx;
           Rvec[3 * o + 1] = ry;
           Rvec[3 * o + 2] = rz;
@@ -197,8 +147,9 @@ extern "C" int ap_scatter_add(int64_t n, const int64_t* d_pix, const double* d_v
 // K3: fused painter
 // ------------------------------------------------------------------------------------------
 constexpr int kPaintThreads = 256;
-constexpr int kMaxHalosPerBlock = 32;
-constexpr int P_TABLE = 100;
+constexpr int kMaxHalosPerBlock = 128;
+constexpr int P_TABLE = 100;   // tabulated template (spline of per-halo nodes)
+constexpr int P_STATS = 101;   // no painting: per-halo pixel count and R range (K1)
 
 struct ParamPtrs {
   const double* p[kMaxParams];
@@ -212,36 +163,69 @@ struct TableArgs {
   const int32_t* n_nodes;
   const double* scale;
   int32_t n_samples;
+  int32_t uniform;  // nodes are linspace: interval index by multiplication
+};
+
+struct StatsArgs {
+  int64_t* n_pix;
+  int32_t* n_rings;
+  double* rmin;
+  double* rmax;
+};
+
+struct HaloHdr {  // DiscHeader with 32-bit ring numbers (nside <= 2^18)
+  double phi, z0, xa, cosr;
+  int32_t irmin, irmax, ir_first, ir_last;
 };
 
 struct RingItem {
   int64_t startpix;
   int32_t nr, ip_lo, len, hl;
-  double A, B, phi_step, phi_off, z, sth;
+  double A, B, phi_step, d0;
 };
-
-struct PaintShared {
-  DiscHeader hdr[kMaxHalosPerBlock];
-  HaloCenter cen[kMaxHalosPerBlock];
-  double ctx[kMaxHalosPerBlock][kCtx];
-  int32_t ring_off[kMaxHalosPerBlock + 1];
-  RingItem item[kPaintThreads];
-  int32_t pix_off[kPaintThreads + 1];
-  int32_t warp_sum[kPaintThreads / 32];
+struct RingItemVec {  // extra per-ring data of R_vec templates
+  double phi0, z, sth;
 };
 
 template <int P>
+struct PaintShared {
+  static constexpr bool VEC = (P == P_NFW_BG);
+  static constexpr int NCTX = (P == P_TABLE) ? 3 : ((P == P_STATS) ? 1 : kCtx);
+  HaloHdr hdr[kMaxHalosPerBlock];
+  double cen_theta[kMaxHalosPerBlock], cen_phi[kMaxHalosPerBlock], cen_sin[kMaxHalosPerBlock],
+      cen_Da[kMaxHalosPerBlock];
+  double cen_vec[VEC ? kMaxHalosPerBlock : 1][3];
+  double ctx[kMaxHalosPerBlock][NCTX];
+  int32_t ring_off[kMaxHalosPerBlock + 1];
+  RingItem item[kPaintThreads];
+  RingItemVec itemv[VEC ? kPaintThreads : 1];
+  int32_t pix_off[kPaintThreads + 1];
+  int32_t warp_sum[kPaintThreads / 32];
+  // P_STATS accumulators
+  unsigned long long cnt[P == P_STATS ? kMaxHalosPerBlock : 1];
+  unsigned long long hmin[P == P_STATS ? kMaxHalosPerBlock : 1], hmax[P == P_STATS ? kMaxHalosPerBlock : 1];
+};
+
+// One block paints `halos_per_block` consecutive halos.  Phase 0: per-halo disc header, centre and
+// template constants (one thread per halo).  Then, 256 ring items at a time: phase 1 computes one
+// ring span per thread (query_disc's per-ring work) and its ring-constant geometry, a block scan of
+// the span lengths gives the flat pixel numbering; phase 2 walks the pixels with consecutive lanes
+// on consecutive pixels of a ring (sector-coalesced fp64 RED traffic), evaluates separation,
+// template and accumulates.  No work list ever touches HBM.
+template <int P>
 __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
-                                                               int halos_per_block, double* __restrict__ map,
+                                                               StatsArgs st, int halos_per_block,
+                                                               double* __restrict__ map,
                                                                unsigned long long* n_painted) {
   constexpr bool VEC = (P == P_NFW_BG);
-  __shared__ PaintShared sm;
+  constexpr bool STATS = (P == P_STATS);
+  __shared__ PaintShared<P> sm;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int64_t h0 = (int64_t)blockIdx.x * halos_per_block;
   const int G = (int)min((int64_t)halos_per_block, H.n - h0);
 
-  // phase 0: per-halo headers, centres and template constants
+  // phase 0
   if (tid < G) {
     int64_t h = h0 + tid;
     DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
@@ -249,16 +233,31 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       d.ir_first = 1;
       d.ir_last = 0;
     }
-    sm.hdr[tid] = d;
-    sm.cen[tid] = make_center(H.theta[h], H.phi[h], H.D_a[h], VEC);
-    if (P != P_TABLE) {
+    HaloHdr hh;
+    hh.phi = d.phi; hh.z0 = d.z0; hh.xa = d.xa; hh.cosr = d.cosr;
+    hh.irmin = (int32_t)d.irmin; hh.irmax = (int32_t)d.irmax;
+    hh.ir_first = (int32_t)d.ir_first; hh.ir_last = (int32_t)d.ir_last;
+    sm.hdr[tid] = hh;
+    if (!STATS || st.rmin) {
+      HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], VEC);
+      sm.cen_theta[tid] = c.theta; sm.cen_phi[tid] = c.phi; sm.cen_sin[tid] = c.sin_t; sm.cen_Da[tid] = c.D_a;
+      if (VEC) { sm.cen_vec[tid][0] = c.cx; sm.cen_vec[tid][1] = c.cy; sm.cen_vec[tid][2] = c.cz; }
+    }
+    if (STATS) {
+      sm.cnt[tid] = 0ull;
+      sm.hmin[tid] = 0x7ff0000000000000ull;  // +inf
+      sm.hmax[tid] = 0ull;                   // haversines are >= 0: their bit patterns order like uint64
+    } else if (P == P_TABLE) {
+      const double* x = tab.nodes + h * tab.n_samples;
+      sm.ctx[tid][0] = tab.scale ? tab.scale[h] : 1.0;
+      sm.ctx[tid][1] = x[0];
+      sm.ctx[tid][2] = (double)(tab.n_samples - 1) / (x[tab.n_samples - 1] - x[0]);
+    } else {
       double p[kMaxParams];
 #pragma unroll
       for (int i = 0; i < kMaxParams; ++i)
         if (i < pp.n) p[i] = pp.p[i][h * pp.stride[i]];
       profile_setup<P>(p, sm.ctx[tid]);
-    } else {
-      sm.ctx[tid][0] = tab.scale ? tab.scale[h] : 1.0;
     }
   }
   __syncthreads();
@@ -266,7 +265,8 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
     int32_t run = 0;
     for (int i = 0; i < G; ++i) {
       sm.ring_off[i] = run;
-      run += (int32_t)disc_n_rings(sm.hdr[i]);
+      int32_t n = sm.hdr[i].ir_last - sm.hdr[i].ir_first + 1;
+      run += n > 0 ? n : 0;
     }
     sm.ring_off[G] = run;
   }
@@ -284,21 +284,34 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
         int mid = (lo + hi) >> 1;
         if (sm.ring_off[mid] <= it) lo = mid; else hi = mid;
       }
-      const DiscHeader& d = sm.hdr[lo];
+      const HaloHdr& hh = sm.hdr[lo];
+      DiscHeader d;
+      d.phi = hh.phi; d.z0 = hh.z0; d.xa = hh.xa; d.cosr = hh.cosr;
+      d.irmin = hh.irmin; d.irmax = hh.irmax; d.ir_first = hh.ir_first; d.ir_last = hh.ir_last;
       int64_t iz = d.ir_first + (it - sm.ring_off[lo]);
       RingSpan s = ring_span(hpx, d, iz);
       len = s.len;
       RingItem& r = sm.item[tid];
-      r.startpix = s.startpix;
-      r.nr = s.nr;
-      r.ip_lo = s.ip_lo;
       r.len = s.len;
-      r.hl = lo;
-      if (len > 0) {
-        RingGeom g = ring_geom(hpx, iz, s, sm.cen[lo]);
-        r.A = g.A; r.B = g.B; r.phi_step = g.phi_step; r.phi_off = g.phi_off; r.z = g.z; r.sth = g.sth;
+      if (len > 0 && (!STATS || st.rmin)) {
+        HaloCenter c;
+        c.theta = sm.cen_theta[lo]; c.phi = sm.cen_phi[lo]; c.sin_t = sm.cen_sin[lo]; c.D_a = sm.cen_Da[lo];
+        RingGeom g = ring_geom(hpx, iz, s, c);
+        if (STATS) {
+          double a, b;
+          span_hav_range(g, s.len, a, b);
+          atomicMin(&sm.hmin[lo], (unsigned long long)__double_as_longlong(a));
+          atomicMax(&sm.hmax[lo], (unsigned long long)__double_as_longlong(b));
+        } else {
+          r.startpix = s.startpix; r.nr = s.nr; r.ip_lo = s.ip_lo; r.hl = lo;
+          r.A = g.A; r.B = g.B; r.phi_step = g.phi_step; r.d0 = g.d0;
+          if (VEC) { sm.itemv[tid].phi0 = g.phi0; sm.itemv[tid].z = g.z; sm.itemv[tid].sth = g.sth; }
+        }
       }
+      if (STATS && len > 0) atomicAdd(&sm.cnt[lo], (unsigned long long)len);
     }
+    if (STATS) continue;  // counts and ranges only: no pixel walk (no barrier needed either)
+
     // block exclusive scan of len
     int32_t v = len;
 #pragma unroll
@@ -326,36 +339,69 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
         if (sm.pix_off[mid] <= k) lo = mid; else hi = mid;
       }
       const RingItem& r = sm.item[lo];
-      int32_t ip = r.ip_lo + (k - sm.pix_off[lo]);
-      const HaloCenter& c = sm.cen[r.hl];
-      RingGeom g;
-      g.A = r.A; g.B = r.B; g.phi_step = r.phi_step; g.phi_off = r.phi_off; g.z = r.z; g.sth = r.sth;
+      const int32_t j = k - sm.pix_off[lo];
+      const int hl = r.hl;
       double val;
       if (VEC) {
+        RingGeom g;
+        g.phi_step = r.phi_step; g.phi0 = sm.itemv[lo].phi0; g.z = sm.itemv[lo].z; g.sth = sm.itemv[lo].sth;
+        HaloCenter c;
+        c.D_a = sm.cen_Da[hl]; c.cx = sm.cen_vec[hl][0]; c.cy = sm.cen_vec[hl][1]; c.cz = sm.cen_vec[hl][2];
         double rx, ry, rz;
-        pixel_chord(g, ip, c, rx, ry, rz);
-        val = profile_eval_vec<P>(sm.ctx[r.hl], rx, ry, rz);
+        pixel_chord(g, j, c, rx, ry, rz);
+        val = profile_eval_vec<P>(sm.ctx[hl], rx, ry, rz);
       } else {
-        double R = c.D_a * pixel_sep(g, ip, c.phi);
+        double hav = r.A + r.B * sin2_half(r.d0 + (double)j * r.phi_step);
+        double R = sm.cen_Da[hl] * sep_from_hav(hav);
         if (P == P_TABLE) {
-          int64_t h = h0 + r.hl;
-          val = spline_eval(tab.n_samples, tab.nodes + h * tab.n_samples,
-                            tab.coef + h * (int64_t)(tab.n_samples - 1) * 4, R) * sm.ctx[r.hl][0];
+          const int64_t h = h0 + hl;
+          const int ns = tab.n_samples;
+          const double* x = tab.nodes + h * ns;
+          int i;
+          if (tab.uniform) {  // linspace nodes: the spline is C2, so +-1 ulp at a knot picks an equal piece
+            i = (int)((R - sm.ctx[hl][1]) * sm.ctx[hl][2]);
+            i = i < 0 ? 0 : (i > ns - 2 ? ns - 2 : i);
+          } else {
+            i = spline_interval(ns, x, R);
+          }
+          const double t = R - x[i];
+          const double2* c2 = reinterpret_cast<const double2*>(tab.coef + (h * (int64_t)(ns - 1) + i) * 4);
+          const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1);
+          val = (c01.x + t * (c01.y + t * (c23.x + t * c23.y))) * sm.ctx[hl][0];
         } else {
-          val = profile_eval_R<P>(sm.ctx[r.hl], R);
+          val = profile_eval_R<P>(sm.ctx[hl], R);
         }
       }
+      int32_t ip = r.ip_lo + j;
       int64_t pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
       atomicAdd(&map[pix], val);
     }
     __syncthreads();
+  }
+  if (STATS) {
+    __syncthreads();
+    if (tid < G) {
+      int64_t h = h0 + tid;
+      unsigned long long c = sm.cnt[tid];
+      st.n_pix[h] = (int64_t)c;
+      if (st.n_rings) {
+        int32_t n = sm.hdr[tid].ir_last - sm.hdr[tid].ir_first + 1;
+        st.n_rings[h] = n > 0 ? n : 0;
+      }
+      if (st.rmin) {
+        double a = __longlong_as_double((long long)sm.hmin[tid]), b = __longlong_as_double((long long)sm.hmax[tid]);
+        st.rmin[h] = c ? sm.cen_Da[tid] * sep_from_hav(a) : INFINITY;
+        st.rmax[h] = c ? sm.cen_Da[tid] * sep_from_hav(b) : -INFINITY;
+      }
+    }
+    return;
   }
   if (n_painted && tid == 0 && painted) atomicAdd(n_painted, painted);
 }
 
 static int pick_halos_per_block(int64_t n) {
   // enough blocks to fill 148 SMs several times over; many halos per block amortise phase 0
-  int64_t g = n / (148 * 16);
+  int64_t g = n / (148 * 8);
   if (g < 1) g = 1;
   if (g > kMaxHalosPerBlock) g = kMaxHalosPerBlock;
   return (int)g;
@@ -363,14 +409,36 @@ static int pick_halos_per_block(int64_t n) {
 
 template <int P>
 static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& pp, const TableArgs& tab, double* d_map,
-                        unsigned long long* d_n_painted, void* stream) {
+                        unsigned long long* d_n_painted, void* stream, const StatsArgs* stats = nullptr) {
   int g = pick_halos_per_block(halos->n);
   int64_t blocks = (halos->n + g - 1) / g;
   if (blocks > 0x7fffffffLL) return fail("too many blocks");
-  paint_kernel<P><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), pp, tab, g,
-                                                                                d_map, d_n_painted);
+  StatsArgs st;
+  memset(&st, 0, sizeof(st));
+  if (stats) st = *stats;
+  paint_kernel<P><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), pp, tab, st,
+                                                                                g, d_map, d_n_painted);
   AP_LAUNCH_CHECK();
   return 0;
+}
+
+// K1: hp.query_disc counts (+ R range) with the painter's block structure, phase 2 skipped
+extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
+                             int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream) {
+  if (check_nside(nside)) return 1;
+  bool want_r = d_rmin || d_rmax;
+  if (check_halos(halos, want_r)) return 1;
+  if (inclusive) return fail("inclusive=True disc query is not implemented");
+  if (want_r && (!d_rmin || !d_rmax)) return fail("d_rmin and d_rmax must both be given");
+  if (!d_n_pix) return fail("d_n_pix == NULL");
+  if (halos->n == 0) return 0;
+  ParamPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  TableArgs tab;
+  memset(&tab, 0, sizeof(tab));
+  StatsArgs st;
+  st.n_pix = d_n_pix; st.n_rings = d_n_rings; st.rmin = d_rmin; st.rmax = d_rmax;
+  return launch_paint<P_STATS>(nside, halos, pp, tab, nullptr, nullptr, stream, &st);
 }
 
 extern "C" int ap_paint_profile(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
@@ -409,9 +477,9 @@ extern "C" int ap_paint_profile(int profile, int64_t nside, const ap_halos* halo
   return fail("unknown profile id");
 }
 
-extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, const double* d_nodes,
-                              const double* d_coef, const int32_t* d_n_nodes, const double* d_scale, double* d_map,
-                              unsigned long long* d_n_painted, void* stream) {
+extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
+                              const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes,
+                              const double* d_scale, double* d_map, unsigned long long* d_n_painted, void* stream) {
   if (check_nside(nside)) return 1;
   if (check_halos(halos, true)) return 1;
   if (n_samples < 4 || n_samples > kMaxNodes) return fail("n_samples must be in [4, 32]");
@@ -421,6 +489,7 @@ extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_sa
   memset(&pp, 0, sizeof(pp));
   TableArgs tab;
   tab.nodes = d_nodes; tab.coef = d_coef; tab.n_nodes = d_n_nodes; tab.scale = d_scale; tab.n_samples = n_samples;
+  tab.uniform = uniform_nodes ? 1 : 0;
   return launch_paint<P_TABLE>(nside, halos, pp, tab, d_map, d_n_painted, stream);
 }
 
@@ -571,8 +640,9 @@ __global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev 
     if (s.len <= 0) continue;
     if (lane < run + s.len) {
       RingGeom g = ring_geom(hpx, iz, s, c);
-      int32_t ip = s.ip_lo + (int32_t)(lane - run);
-      double R = c.D_a * pixel_sep(g, ip, c.phi);
+      int32_t js = (int32_t)(lane - run);
+      int32_t ip = s.ip_lo + js;
+      double R = c.D_a * pixel_sep(g, js);
       double ctx[kCtx];
       b16_setup(R200[h], M200[h], zred[h], ctx);
       double val = b16_tau_2D(ctx, R) * (scale ? scale[h] : 1.0);

@@ -52,14 +52,19 @@ AP_HD_NOINLINE void spline_build_nak(int n, const double* x, const double* y, do
   }
 }
 
-// Evaluate; X outside [x_0, x_{n-1}] extrapolates the end pieces (FITPACK splev, ext=0).
-AP_HD double spline_eval(int n, const double* x, const double* c, double X) {
-  // uniform guess, then fix up (nodes may be log-spaced)
+// interval i with x_i <= X < x_{i+1} (clamped): uniform guess, then fix up (nodes may be log-spaced)
+AP_HD int spline_interval(int n, const double* x, double X) {
   int i = (int)((X - x[0]) / (x[n - 1] - x[0]) * (double)(n - 1));
   if (i < 0) i = 0;
   if (i > n - 2) i = n - 2;
   while (i > 0 && X < x[i]) --i;
   while (i < n - 2 && X >= x[i + 1]) ++i;
+  return i;
+}
+
+// Evaluate; X outside [x_0, x_{n-1}] extrapolates the end pieces (FITPACK splev, ext=0).
+AP_HD double spline_eval(int n, const double* x, const double* c, double X) {
+  int i = spline_interval(n, x, X);
   double t = X - x[i];
   const double* k = c + 4 * i;
   return k[0] + t * (k[1] + t * (k[2] + t * k[3]));

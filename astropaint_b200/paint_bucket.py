@@ -711,7 +711,8 @@ class Painter:
             scale = sc["fn"](cols, kw)
             scale = scale if scale.numel() == halos.n else scale.expand(halos.n)
             scale = scale.contiguous()
-        eng.paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count)
+        eng.paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count,
+                        uniform=(info["sampling_method"] == "linspace"))
         eng.paint_b16_small(halos, nside, R200, M200, zred, scale, n_pix, ns, d_map, d_count)
 
     def _paint_python_table(self, info, halos, nside, rows, R_mode, host_cols, d_map, d_count):
@@ -734,7 +735,8 @@ class Painter:
             kws = {k: hc[k][h] for k in kwo}
             values[h] = [inner(x, *rest, **kws) for x in nodes_h[h]]
         coef = eng.spline_build(nodes, eng.to_device(values.ravel(), halos.device).view(halos.n, ns), n_nodes)
-        eng.paint_table(halos, nside, nodes, coef, n_nodes, None, d_map, d_count)
+        eng.paint_table(halos, nside, nodes, coef, n_nodes, None, d_map, d_count,
+                        uniform=(info["sampling_method"] == "linspace"))
         small = np.nonzero((counts > 0) & (counts < ns))[0]
         if len(small):
             sub = halos.subset(small)

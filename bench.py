@@ -220,7 +220,7 @@ def run_b200(args):
         coef = eng.spline_build(nodes, values, n_nodes)
         scale = (-cols["v_r"] / c_kms * T_cmb * (1 + cols["redshift"])).contiguous()
         mark(4)
-        eng.paint_table(halos, NSIDE, nodes, coef, n_nodes, scale, d_map, d_count)
+        eng.paint_table(halos, NSIDE, nodes, coef, n_nodes, scale, d_map, d_count, uniform=True)
         mark(5)
         eng.paint_b16_small(halos, NSIDE, cols["R_200c"], cols["M_200c"], cols["redshift"], scale, n_pix, ns, d_map,
                             d_count)

@@ -98,11 +98,12 @@ int ap_spline_build(int64_t n, int32_t n_samples, const double* d_nodes, const d
                     const int32_t* d_n_nodes, double* d_coef, void* stream);
 
 /* Painter.spray for a tabulated template: value = spline_h(R) * d_scale[h] (d_scale optional).
+ * uniform_nodes = 1 when the nodes are linspace (method 0 of ap_table_nodes).
  * Halos with d_n_nodes[h] == 0 are skipped (bypass halos are painted by ap_paint_b16_small or
  * through the flat work list).                                                               */
-int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, const double* d_nodes,
-                   const double* d_coef, const int32_t* d_n_nodes, const double* d_scale, double* d_map,
-                   unsigned long long* d_n_painted, void* stream);
+int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
+                   const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes, const double* d_scale,
+                   double* d_map, unsigned long long* d_n_painted, void* stream);
 
 /* The `len(R) < n_samples` branch of Battaglia16.tau_2D_interp / kSZ_T: halos with
  * 0 < n_pix < n_samples get tau_2D (QUADPACK) evaluated at every pixel (lib/utils.py:510-511). */
