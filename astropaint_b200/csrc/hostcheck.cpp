@@ -96,6 +96,13 @@ double hc_b16_tau_3D(double r, double R_200c, double M_200c, double redshift) {
 
 double hc_critical_density(double z) { return critical_density(z); }
 
+void hc_fast_log_exp(int64_t n, const double* x, double* lg, double* ex) {
+  for (int64_t i = 0; i < n; ++i) {
+    if (lg) lg[i] = fast_log(x[i]);
+    if (ex) ex[i] = fast_exp(x[i]);
+  }
+}
+
 int hc_profile_R(int profile, const double* p, int64_t n, const double* R, double* out) {
   switch (profile) {
     case P_CONSTANT: eval_R<P_CONSTANT>(p, n, R, out); return 0;

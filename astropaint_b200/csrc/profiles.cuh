@@ -10,6 +10,7 @@
 #pragma once
 #include "common.cuh"
 #include "qagi.cuh"
+#include "fastmath.cuh"
 
 namespace ap {
 
@@ -108,9 +109,9 @@ struct B16Integrand {
   // sm_100a).  Relative error ~1e-15, far inside the distance at which QUADPACK's decisions flip
   // (tests compare value AND neval against scipy on host and device).
   AP_HD double operator()(double r) const {
-    double L = log(AP_MUL(r, inv_R200xc));             // log((r / R_200c) / xc)
-    double ya = exp(AP_MUL(alpha, L));
-    double fit = exp(AP_ADD(AP_MUL(expo, log(AP_ADD(1.0, ya))), AP_MUL(-0.2, L)));
+    double L = fast_log(AP_MUL(r, inv_R200xc));        // log((r / R_200c) / xc)
+    double ya = fast_exp(AP_MUL(alpha, L));
+    double fit = fast_exp(AP_ADD(AP_MUL(expo, fast_log(AP_ADD(1.0, ya))), AP_MUL(-0.2, L)));
     double w = AP_SUB(AP_MUL(r, r), RR);
 #if defined(__CUDA_ARCH__)
     return AP_MUL(AP_MUL(AP_MUL(fit, K2), r), rsqrt(w));
