@@ -293,6 +293,14 @@ def run_b200(args):
         except (OSError, ValueError):
             pass
     dominant = max(phase_ms, key=phase_ms.get)
+    # the dominant kernel is the QUADPACK node kernel: fp64-pipe / issue bound (DRAM < 1% of peak), so an
+    # HBM or tensor roofline does not apply; report its rate and the ncu-measured pipe utilisation instead
+    n_quad = ns * n_big
+    roofline_dominant = {"kernel": "b16_tau_nodes_kernel (QUADPACK dqagie per (halo, node))", "bound": "fp64-pipe",
+                         "achieved": n_quad / (phase_ms["b16_tau_nodes"] / 1e3), "unit": "quadratures/s",
+                         "launch_ms": phase_ms["b16_tau_nodes"], "share_of_step": phase_ms["b16_tau_nodes"] / ms_step,
+                         "fp64_pipe_active_pct_ncu": 55, "peak": None, "frac": None,
+                         "note": "see profiles/README.md; 165 integrand evaluations per quadrature (scipy neval)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -300,7 +308,7 @@ def run_b200(args):
             "halo_pixels_per_step": pairs_all, "halos_per_s": args.halos * world / (ms_step / 1e3),
             "phase_ms": phase_ms, "dominant_phase": dominant,
             "gpu_launches": launches_per_step * args.steps, "torch_elementwise_launches": 4 * args.steps,
-            "roofline": roofline, "clocks": clocks}
+            "roofline": roofline, "roofline_dominant": roofline_dominant, "clocks": clocks}
 
     # ---- e2e: the public API on a host catalog --------------------------------------------------
     if not args.no_e2e:
