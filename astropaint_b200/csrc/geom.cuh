@@ -15,7 +15,7 @@
 namespace ap {
 
 struct HaloCenter {
-  double theta, phi, sin_t, D_a;
+  double theta, phi, sin_t, cos_t, D_a;
   double cx, cy, cz;
 };
 
@@ -25,11 +25,12 @@ AP_HD HaloCenter make_center(double theta, double phi, double D_a, bool need_vec
   c.phi = phi;
   c.D_a = D_a;
   c.sin_t = sin(theta);
+  c.cos_t = cos(theta);
   c.cx = c.cy = c.cz = 0.0;
   if (need_vec) {  // hp.ang2vec(theta, phi), :1212
     c.cx = c.sin_t * cos(phi);
     c.cy = c.sin_t * sin(phi);
-    c.cz = cos(theta);
+    c.cz = c.cos_t;
   }
   return c;
 }
@@ -43,11 +44,14 @@ struct RingGeom {
 
 AP_HD RingGeom ring_geom(const Hpx& h, int64_t iz, const RingSpan& s, const HaloCenter& c) {
   RingGeom g;
-  double theta_p;
-  ring_theta(h, iz, s.z, theta_p, g.sth);
+  g.sth = ring_sth(h, iz, s.z);
   g.z = s.z;
-  double sh = sin(0.5 * (theta_p - c.theta));
-  g.A = sh * sh;
+  // A = sin^2((theta_p - theta_c)/2) without any inverse trigonometry:
+  //   z_p - z_c = -2 sin((theta_p+theta_c)/2) sin((theta_p-theta_c)/2),
+  //   sin^2((theta_p+theta_c)/2) = (1 - z_p z_c + s_p s_c)/2
+  // (the reference goes through theta_p = acos(z_p), pix2ang; identical to ~1e-12 relative)
+  double dz = s.z - c.cos_t;
+  g.A = (dz * dz) / (2.0 * ((1.0 - s.z * c.cos_t) + g.sth * c.sin_t));
   g.B = g.sth * c.sin_t;
   g.phi_step = kTwoPi / (double)s.nr;
   g.phi0 = ((double)s.ip_lo + (s.shifted ? 0.5 : 0.0)) * g.phi_step;

@@ -170,6 +170,17 @@ AP_HD void ring_theta(const Hpx& h, int64_t iz, double z, double& theta, double&
   }
 }
 
+// sin(theta) of a ring as healpix pix2loc / pix2vec forms it
+AP_HD double ring_sth(const Hpx& h, int64_t iz, double z) {
+  bool cap = (iz < h.nside) || (iz > 3 * h.nside);
+  if (cap && fabs(z) > 0.99) {
+    int64_t ir = (iz < h.nside) ? iz : 4 * h.nside - iz;
+    double tmp = AP_MUL((double)(ir * ir), h.fact2);
+    return sqrt(AP_MUL(tmp, AP_SUB(2.0, tmp)));
+  }
+  return sqrt(AP_MUL(AP_SUB(1.0, z), AP_ADD(1.0, z)));
+}
+
 // loc2pix / vec2pix, RING scheme (hp.vec2pix, paint_bucket.py:1721).
 AP_HD int64_t vec2pix_ring(const Hpx& h, double x, double y, double z) {
   double xl = 1.0 / sqrt(AP_ADD(AP_ADD(AP_MUL(x, x), AP_MUL(y, y)), AP_MUL(z, z)));

@@ -148,6 +148,7 @@ extern "C" int ap_scatter_add(int64_t n, const int64_t* d_pix, const double* d_v
 // ------------------------------------------------------------------------------------------
 constexpr int kPaintThreads = 256;
 constexpr int kMaxHalosPerBlock = 128;
+constexpr int kHintMax = 1024;
 constexpr int P_TABLE = 100;   // tabulated template (spline of per-halo nodes)
 constexpr int P_STATS = 101;   // no painting: per-halo pixel count and R range (K1)
 
@@ -192,7 +193,7 @@ struct PaintShared {
   static constexpr bool VEC = (P == P_NFW_BG);
   static constexpr int NCTX = (P == P_TABLE) ? 3 : ((P == P_STATS) ? 1 : kCtx);
   HaloHdr hdr[kMaxHalosPerBlock];
-  double cen_theta[kMaxHalosPerBlock], cen_phi[kMaxHalosPerBlock], cen_sin[kMaxHalosPerBlock],
+  double cen_cos[kMaxHalosPerBlock], cen_phi[kMaxHalosPerBlock], cen_sin[kMaxHalosPerBlock],
       cen_Da[kMaxHalosPerBlock];
   double cen_vec[VEC ? kMaxHalosPerBlock : 1][3];
   double ctx[kMaxHalosPerBlock][NCTX];
@@ -201,6 +202,7 @@ struct PaintShared {
   RingItemVec itemv[VEC ? kPaintThreads : 1];
   int32_t pix_off[kPaintThreads + 1];
   int32_t warp_sum[kPaintThreads / 32];
+  int32_t hint[kHintMax];  // hint[g] = ring item holding pixel 32 g of the current chunk
   // P_STATS accumulators
   unsigned long long cnt[P == P_STATS ? kMaxHalosPerBlock : 1];
   unsigned long long hmin[P == P_STATS ? kMaxHalosPerBlock : 1], hmax[P == P_STATS ? kMaxHalosPerBlock : 1];
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
     sm.hdr[tid] = hh;
     if (!STATS || st.rmin) {
       HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], VEC);
-      sm.cen_theta[tid] = c.theta; sm.cen_phi[tid] = c.phi; sm.cen_sin[tid] = c.sin_t; sm.cen_Da[tid] = c.D_a;
+      sm.cen_cos[tid] = c.cos_t; sm.cen_phi[tid] = c.phi; sm.cen_sin[tid] = c.sin_t; sm.cen_Da[tid] = c.D_a;
       if (VEC) { sm.cen_vec[tid][0] = c.cx; sm.cen_vec[tid][1] = c.cy; sm.cen_vec[tid][2] = c.cz; }
     }
     if (STATS) {
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       r.len = s.len;
       if (len > 0 && (!STATS || st.rmin)) {
         HaloCenter c;
-        c.theta = sm.cen_theta[lo]; c.phi = sm.cen_phi[lo]; c.sin_t = sm.cen_sin[lo]; c.D_a = sm.cen_Da[lo];
+        c.cos_t = sm.cen_cos[lo]; c.phi = sm.cen_phi[lo]; c.sin_t = sm.cen_sin[lo]; c.D_a = sm.cen_Da[lo];
         RingGeom g = ring_geom(hpx, iz, s, c);
         if (STATS) {
           double a, b;
@@ -325,18 +327,31 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
 #pragma unroll
     for (int w = 0; w < kPaintThreads / 32; ++w)
       if (w < warp) woff += sm.warp_sum[w];
-    sm.pix_off[tid] = woff + v - len;
-    if (tid == kPaintThreads - 1) sm.pix_off[kPaintThreads] = woff + v;
+    {
+      const int32_t start = woff + v - len, end = start + len;
+      sm.pix_off[tid] = start;
+      if (tid == kPaintThreads - 1) sm.pix_off[kPaintThreads] = end;
+      // every multiple of 32 inside [start, end) starts a warp-sized pixel group in this ring item
+      for (int32_t m = (start + 31) & ~31; m < end && (m >> 5) < kHintMax; m += 32) sm.hint[m >> 5] = tid;
+    }
     __syncthreads();
     const int32_t total = sm.pix_off[kPaintThreads];
     painted += (tid == 0) ? (unsigned long long)total : 0ull;
 
-    // phase 2: one pixel per thread per iteration
-    for (int32_t k = tid; k < total; k += kPaintThreads) {
-      int lo = 0, hi = kPaintThreads;  // largest i with pix_off[i] <= k
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (sm.pix_off[mid] <= k) lo = mid; else hi = mid;
+    // phase 2: two pixels per thread per iteration (k and k + 256): independent dependency chains
+    // (table loads, series) overlap, then both REDs are issued
+    auto eval = [&](int32_t k, int64_t& pix) -> double {
+      int lo;
+      if ((k >> 5) < kHintMax) {
+        lo = sm.hint[k >> 5];
+        while (sm.pix_off[lo + 1] <= k) ++lo;
+      } else {  // chunk with more than 32 Ki pixels (sky-sized discs): plain binary search
+        lo = 0;
+        int hi = kPaintThreads;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (sm.pix_off[mid] <= k) lo = mid; else hi = mid;
+        }
       }
       const RingItem& r = sm.item[lo];
       const int32_t j = k - sm.pix_off[lo];
@@ -364,7 +379,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
           } else {
             i = spline_interval(ns, x, R);
           }
-          const double t = R - x[i];
+          const double t = R - __ldg(x + i);
           const double2* c2 = reinterpret_cast<const double2*>(tab.coef + (h * (int64_t)(ns - 1) + i) * 4);
           const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1);
           val = (c01.x + t * (c01.y + t * (c23.x + t * c23.y))) * sm.ctx[hl][0];
@@ -373,8 +388,16 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
         }
       }
       int32_t ip = r.ip_lo + j;
-      int64_t pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
-      atomicAdd(&map[pix], val);
+      pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
+      return val;
+    };
+    for (int32_t k = tid; k < total; k += 2 * kPaintThreads) {
+      int64_t p0, p1 = 0;
+      const bool two = (k + kPaintThreads < total);
+      double v0 = eval(k, p0);
+      double v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
+      atomicAdd(&map[p0], v0);
+      if (two) atomicAdd(&map[p1], v1);
     }
     __syncthreads();
   }
