@@ -35,6 +35,7 @@ SIGNATURES = {
     "ap_b16_tau_nodes": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_b16_tau_eval": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spline_build": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_spline_build_uniform": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_paint_table": (C.c_int, [c_i64, C.POINTER(ApHalos), c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                  c_ptr]),
     "ap_paint_b16_small": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,

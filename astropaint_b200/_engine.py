@@ -189,10 +189,11 @@ def b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes):
     return values
 
 
-def spline_build(nodes, values, n_nodes):
+def spline_build(nodes, values, n_nodes, uniform=False):
     n, ns = nodes.shape
     coef = torch.empty((n, ns - 1, 4), dtype=torch.float64, device=nodes.device)
-    check(_capi.lib().ap_spline_build(n, ns, ptr(nodes), ptr(values), ptr(n_nodes), ptr(coef), stream_ptr()))
+    fn = _capi.lib().ap_spline_build_uniform if uniform else _capi.lib().ap_spline_build
+    check(fn(n, ns, ptr(nodes), ptr(values), ptr(n_nodes), ptr(coef), stream_ptr()))
     return coef
 
 

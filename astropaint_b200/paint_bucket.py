@@ -702,7 +702,7 @@ class Painter:
         R200, M200, zred = (col(a) for a in info["args"])
         R200, M200, zred = (t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in (R200, M200, zred))
         values = eng.b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes)
-        coef = eng.spline_build(nodes, values, n_nodes)
+        coef = eng.spline_build(nodes, values, n_nodes, uniform=(info["sampling_method"] == "linspace"))
         scale = None
         if info["scale"] is not None:
             sc = info["scale"]
@@ -734,7 +734,8 @@ class Painter:
             rest = [hc[a][h] for a in pos]
             kws = {k: hc[k][h] for k in kwo}
             values[h] = [inner(x, *rest, **kws) for x in nodes_h[h]]
-        coef = eng.spline_build(nodes, eng.to_device(values.ravel(), halos.device).view(halos.n, ns), n_nodes)
+        coef = eng.spline_build(nodes, eng.to_device(values.ravel(), halos.device).view(halos.n, ns), n_nodes,
+                                uniform=(info["sampling_method"] == "linspace"))
         eng.paint_table(halos, nside, nodes, coef, n_nodes, None, d_map, d_count,
                         uniform=(info["sampling_method"] == "linspace"))
         small = np.nonzero((counts > 0) & (counts < ns))[0]

@@ -219,7 +219,7 @@ def run_b200(args):
         mark(2)
         values = eng.b16_tau_nodes(halos, cols["R_200c"], cols["M_200c"], cols["redshift"], nodes, n_nodes)
         mark(3)
-        coef = eng.spline_build(nodes, values, n_nodes)
+        coef = eng.spline_build(nodes, values, n_nodes, uniform=True)
         scale = (-cols["v_r"] / c_kms * T_cmb * (1 + cols["redshift"])).contiguous()
         mark(4)
         eng.paint_table(halos, NSIDE, nodes, coef, n_nodes, scale, d_map, d_count, uniform=True)

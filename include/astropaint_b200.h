@@ -97,6 +97,11 @@ int ap_b16_tau_eval(int64_t n, const double* d_R, const double* d_R_200c, const 
 int ap_spline_build(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,
                     const int32_t* d_n_nodes, double* d_coef, void* stream);
 
+/* Same result for np.linspace nodes (ap_table_nodes method 0): constant-coefficient solve kept in
+ * registers for n_samples 15 and 20, other sizes fall through to ap_spline_build.             */
+int ap_spline_build_uniform(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,
+                            const int32_t* d_n_nodes, double* d_coef, void* stream);
+
 /* Painter.spray for a tabulated template: value = spline_h(R) * d_scale[h] (d_scale optional).
  * uniform_nodes = 1 when the nodes are linspace (method 0 of ap_table_nodes).
  * Halos with d_n_nodes[h] == 0 are skipped (bypass halos are painted by ap_paint_b16_small or

@@ -470,3 +470,34 @@ def test_cuda_path_matches_golden_fixtures():
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_uniform_spline_kernel_equals_generic_and_scipy():
+    import torch
+    from scipy.interpolate import InterpolatedUnivariateSpline
+    from astropaint_b200 import _engine as eng
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    for ns in (15, 20, 9):
+        n = 1000
+        a = rng.uniform(0.01, 1.0, n)
+        b = a + rng.uniform(0.1, 5.0, n)
+        nodes = np.stack([np.linspace(a[i], b[i], ns) for i in range(n)])
+        vals = np.exp(-nodes) * (1 + 0.05 * rng.normal(size=nodes.shape))
+        nn = np.full(n, ns, dtype=np.int32)
+        nn[::7] = 0
+        t_nodes, t_vals = torch.from_numpy(nodes).to(dev), torch.from_numpy(vals).to(dev)
+        t_nn = torch.from_numpy(nn).to(dev)
+        c_gen = eng.spline_build(t_nodes, t_vals, t_nn, uniform=False).cpu().numpy()
+        c_uni = eng.spline_build(t_nodes, t_vals, t_nn, uniform=True).cpu().numpy()
+        scale = np.abs(c_gen).max(axis=(1, 2), keepdims=True) + 1e-300
+        assert np.abs(c_uni - c_gen).max() <= 1e-9 * scale.max()
+        assert np.all(c_uni[::7] == 0)
+        for i in (1, 2, 500):
+            X = np.linspace(a[i], b[i], 50)
+            k = np.clip(np.searchsorted(nodes[i], X, side="right") - 1, 0, ns - 2)
+            t = X - nodes[i][k]
+            c = c_uni[i][k]
+            got = c[:, 0] + t * (c[:, 1] + t * (c[:, 2] + t * c[:, 3]))
+            want = InterpolatedUnivariateSpline(nodes[i], vals[i], k=3)(X)
+            assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
