@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_native", "libastropaint_b200.so")
+LIB_PATH = os.environ.get("AP_LIB_PATH") or os.path.join(_HERE, "_native", "libastropaint_b200.so")
 
 _lib = None
 
