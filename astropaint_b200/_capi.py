@@ -40,6 +40,13 @@ SIGNATURES = {
                                  c_ptr]),
     "ap_paint_b16_small": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
                                      c_ptr, c_ptr, c_ptr]),
+    "ap_scatter_add_f32": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_paint_profile_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), C.POINTER(c_ptr), C.POINTER(c_i32),
+                                       c_i32, c_ptr, c_ptr, c_ptr]),
+    "ap_paint_table_f32": (C.c_int, [c_i64, C.POINTER(ApHalos), c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                     c_ptr]),
+    "ap_paint_b16_small_f32": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
+                                         c_ptr, c_ptr, c_ptr]),
     "ap_cutouts": (C.c_int, [c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_dbl, c_dbl, c_i32, c_i32,
                              c_ptr, c_ptr]),
     "ap_stack_cutouts": (C.c_int, [c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_dbl, c_dbl, c_i32,

@@ -151,8 +151,13 @@ def disc_pixels(halos, nside, n_pix, lo=0, hi=None, want_R=False, want_vec=False
     return off, pix, R, Rv
 
 
+def _fn(name, d_map):
+    """fp64 or fp32-accumulate entry point according to the map's dtype"""
+    return getattr(_capi.lib(), name + ("_f32" if d_map.dtype == torch.float32 else ""))
+
+
 def scatter_add(pix, val, d_map):
-    check(_capi.lib().ap_scatter_add(pix.numel(), ptr(pix), ptr(val), ptr(d_map), stream_ptr()))
+    check(_fn("ap_scatter_add", d_map)(pix.numel(), ptr(pix), ptr(val), ptr(d_map), stream_ptr()))
 
 
 def paint_profile(halos, nside, profile_id, params, d_map, d_count=None):
@@ -168,8 +173,8 @@ def paint_profile(halos, nside, profile_id, params, d_map, d_count=None):
         if strides[i] == 1 and t.numel() != halos.n:
             raise ValueError(f"template argument #{i} has {t.numel()} values for {halos.n} halos")
     s = halos.struct()
-    check(L.ap_paint_profile(int(profile_id), nside, C.byref(s), arr, strides, n, ptr(d_map), ptr(d_count),
-                             stream_ptr()))
+    check(_fn("ap_paint_profile", d_map)(int(profile_id), nside, C.byref(s), arr, strides, n, ptr(d_map),
+                                         ptr(d_count), stream_ptr()))
 
 
 def table_nodes(halos, n_pix, rmin, rmax, n_samples, method):
@@ -199,18 +204,19 @@ def spline_build(nodes, values, n_nodes, uniform=False):
 
 def paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count=None, uniform=False):
     s = halos.struct()
-    check(_capi.lib().ap_paint_table(nside, C.byref(s), nodes.shape[1], int(bool(uniform)), ptr(nodes), ptr(coef),
-                                     ptr(n_nodes),
+    check(_fn("ap_paint_table", d_map)(nside, C.byref(s), nodes.shape[1], int(bool(uniform)), ptr(nodes), ptr(coef),
+                                       ptr(n_nodes),
                                      ptr(scale), ptr(d_map), ptr(d_count), stream_ptr()))
 
 
 def paint_b16_small(halos, nside, R200, M200, zred, scale, n_pix, n_samples, d_map, d_count=None):
     s = halos.struct()
-    check(_capi.lib().ap_paint_b16_small(nside, C.byref(s), ptr(R200), ptr(M200), ptr(zred), ptr(scale),
-                                         ptr(n_pix), n_samples, ptr(d_map), ptr(d_count), stream_ptr()))
+    check(_fn("ap_paint_b16_small", d_map)(nside, C.byref(s), ptr(R200), ptr(M200), ptr(zred), ptr(scale),
+                                           ptr(n_pix), n_samples, ptr(d_map), ptr(d_count), stream_ptr()))
 
 
 def cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize):
+    d_map = d_map if d_map.dtype == torch.float64 else d_map.double()
     out = torch.empty((lon.numel(), ysize, xsize), dtype=torch.float64, device=d_map.device)
     check(_capi.lib().ap_cutouts(nside, ptr(d_map), lon.numel(), ptr(lon), ptr(lat), float(lon_range[0]),
                                  float(lon_range[1]), float(lat_range[0]), float(lat_range[1]), xsize, ysize,
@@ -219,6 +225,7 @@ def cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize):
 
 
 def stack_cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize, weight=None, stack=None):
+    d_map = d_map if d_map.dtype == torch.float64 else d_map.double()
     if stack is None:
         stack = torch.zeros((ysize, xsize), dtype=torch.float64, device=d_map.device)
     check(_capi.lib().ap_stack_cutouts(nside, ptr(d_map), lon.numel(), ptr(lon), ptr(lat), float(lon_range[0]),

@@ -125,22 +125,32 @@ extern "C" int ap_disc_pixels(int64_t nside, const ap_halos* halos, const int64_
 // ------------------------------------------------------------------------------------------
 // scatter-add of a flat work list
 // ------------------------------------------------------------------------------------------
-__global__ void scatter_add_kernel(int64_t n, const int64_t* pix, const double* val, double* map) {
+template <class MapT>
+__global__ void scatter_add_kernel(int64_t n, const int64_t* pix, const double* val, MapT* map) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) atomicAdd(&map[pix[i]], val[i]);
+  for (; i < n; i += stride) atomicAdd(&map[pix[i]], (MapT)val[i]);
 }
 
-extern "C" int ap_scatter_add(int64_t n, const int64_t* d_pix, const double* d_val, double* d_map, void* stream) {
+static int scatter_add_impl(int64_t n, const int64_t* d_pix, const double* d_val, void* d_map, bool f32, void* stream) {
   if (n < 0) return fail("n < 0");
   if (n == 0) return 0;
   if (!d_pix || !d_val || !d_map) return fail("scatter_add: NULL pointer");
   int threads = 256;
   int64_t blocks = (n + threads - 1) / threads;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  scatter_add_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(n, d_pix, d_val, d_map);
+  if (f32)
+    scatter_add_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(n, d_pix, d_val, (float*)d_map);
+  else
+    scatter_add_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(n, d_pix, d_val, (double*)d_map);
   AP_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int ap_scatter_add(int64_t n, const int64_t* d_pix, const double* d_val, double* d_map, void* stream) {
+  return scatter_add_impl(n, d_pix, d_val, d_map, false, stream);
+}
+extern "C" int ap_scatter_add_f32(int64_t n, const int64_t* d_pix, const double* d_val, float* d_map, void* stream) {
+  return scatter_add_impl(n, d_pix, d_val, d_map, true, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -214,10 +224,10 @@ struct PaintShared {
 // the span lengths gives the flat pixel numbering; phase 2 walks the pixels with consecutive lanes
 // on consecutive pixels of a ring (sector-coalesced fp64 RED traffic), evaluates separation,
 // template and accumulates.  No work list ever touches HBM.
-template <int P>
+template <int P, class MapT>
 __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
                                                                StatsArgs st, int halos_per_block,
-                                                               double* __restrict__ map,
+                                                               MapT* __restrict__ map,
                                                                unsigned long long* n_painted) {
   constexpr bool VEC = (P == P_NFW_BG);
   constexpr bool STATS = (P == P_STATS);
@@ -396,8 +406,8 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       const bool two = (k + kPaintThreads < total);
       double v0 = eval(k, p0);
       double v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
-      atomicAdd(&map[p0], v0);
-      if (two) atomicAdd(&map[p1], v1);
+      atomicAdd(&map[p0], (MapT)v0);
+      if (two) atomicAdd(&map[p1], (MapT)v1);
     }
     __syncthreads();
   }
@@ -431,16 +441,21 @@ static int pick_halos_per_block(int64_t n) {
 }
 
 template <int P>
-static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& pp, const TableArgs& tab, double* d_map,
-                        unsigned long long* d_n_painted, void* stream, const StatsArgs* stats = nullptr) {
+static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& pp, const TableArgs& tab, void* d_map,
+                        unsigned long long* d_n_painted, void* stream, const StatsArgs* stats = nullptr,
+                        bool f32 = false) {
   int g = pick_halos_per_block(halos->n);
   int64_t blocks = (halos->n + g - 1) / g;
   if (blocks > 0x7fffffffLL) return fail("too many blocks");
   StatsArgs st;
   memset(&st, 0, sizeof(st));
   if (stats) st = *stats;
-  paint_kernel<P><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), pp, tab, st,
-                                                                                g, d_map, d_n_painted);
+  if (f32 && P != P_STATS)
+    paint_kernel<P, float><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(
+        make_hpx(nside), to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+  else
+    paint_kernel<P, double><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(
+        make_hpx(nside), to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
   AP_LAUNCH_CHECK();
   return 0;
 }
@@ -464,9 +479,9 @@ extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive
   return launch_paint<P_STATS>(nside, halos, pp, tab, nullptr, nullptr, stream, &st);
 }
 
-extern "C" int ap_paint_profile(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
-                                const int32_t* h_strides, int32_t n_params, double* d_map,
-                                unsigned long long* d_n_painted, void* stream) {
+static int paint_profile_impl(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
+                              const int32_t* h_strides, int32_t n_params, void* d_map, bool f32,
+                              unsigned long long* d_n_painted, void* stream) {
   if (check_nside(nside)) return 1;
   if (check_halos(halos, true)) return 1;
   if (!d_map) return fail("d_map == NULL");
@@ -486,23 +501,34 @@ extern "C" int ap_paint_profile(int profile, int64_t nside, const ap_halos* halo
   TableArgs tab;
   memset(&tab, 0, sizeof(tab));
   switch (profile) {
-    case P_CONSTANT: return launch_paint<P_CONSTANT>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_LINEAR: return launch_paint<P_LINEAR>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_SOLID_SPHERE: return launch_paint<P_SOLID_SPHERE>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_GAUSSIAN: return launch_paint<P_GAUSSIAN>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_NFW_RHO2D: return launch_paint<P_NFW_RHO2D>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_NFW_TAU2D: return launch_paint<P_NFW_TAU2D>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_NFW_KSZ: return launch_paint<P_NFW_KSZ>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_NFW_DEFLECTION: return launch_paint<P_NFW_DEFLECTION>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_NFW_BG: return launch_paint<P_NFW_BG>(nside, halos, pp, tab, d_map, d_n_painted, stream);
-    case P_B16_TAU2D: return launch_paint<P_B16_TAU2D>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+    case P_CONSTANT: return launch_paint<P_CONSTANT>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_LINEAR: return launch_paint<P_LINEAR>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_SOLID_SPHERE: return launch_paint<P_SOLID_SPHERE>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_GAUSSIAN: return launch_paint<P_GAUSSIAN>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_NFW_RHO2D: return launch_paint<P_NFW_RHO2D>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_NFW_TAU2D: return launch_paint<P_NFW_TAU2D>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_NFW_KSZ: return launch_paint<P_NFW_KSZ>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_NFW_DEFLECTION: return launch_paint<P_NFW_DEFLECTION>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_NFW_BG: return launch_paint<P_NFW_BG>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_B16_TAU2D: return launch_paint<P_B16_TAU2D>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
   }
   return fail("unknown profile id");
 }
+extern "C" int ap_paint_profile(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
+                                const int32_t* h_strides, int32_t n_params, double* d_map,
+                                unsigned long long* d_n_painted, void* stream) {
+  return paint_profile_impl(profile, nside, halos, h_params, h_strides, n_params, d_map, false, d_n_painted, stream);
+}
+extern "C" int ap_paint_profile_f32(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
+                                    const int32_t* h_strides, int32_t n_params, float* d_map,
+                                    unsigned long long* d_n_painted, void* stream) {
+  return paint_profile_impl(profile, nside, halos, h_params, h_strides, n_params, d_map, true, d_n_painted, stream);
+}
 
-extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
-                              const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes,
-                              const double* d_scale, double* d_map, unsigned long long* d_n_painted, void* stream) {
+static int paint_table_impl(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
+                            const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes,
+                            const double* d_scale, void* d_map, bool f32, unsigned long long* d_n_painted,
+                            void* stream) {
   if (check_nside(nside)) return 1;
   if (check_halos(halos, true)) return 1;
   if (n_samples < 4 || n_samples > kMaxNodes) return fail("n_samples must be in [4, 32]");
@@ -513,7 +539,19 @@ extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_sa
   TableArgs tab;
   tab.nodes = d_nodes; tab.coef = d_coef; tab.n_nodes = d_n_nodes; tab.scale = d_scale; tab.n_samples = n_samples;
   tab.uniform = uniform_nodes ? 1 : 0;
-  return launch_paint<P_TABLE>(nside, halos, pp, tab, d_map, d_n_painted, stream);
+  return launch_paint<P_TABLE>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+}
+extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
+                              const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes,
+                              const double* d_scale, double* d_map, unsigned long long* d_n_painted, void* stream) {
+  return paint_table_impl(nside, halos, n_samples, uniform_nodes, d_nodes, d_coef, d_n_nodes, d_scale, d_map, false,
+                          d_n_painted, stream);
+}
+extern "C" int ap_paint_table_f32(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
+                                  const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes,
+                                  const double* d_scale, float* d_map, unsigned long long* d_n_painted, void* stream) {
+  return paint_table_impl(nside, halos, n_samples, uniform_nodes, d_nodes, d_coef, d_n_nodes, d_scale, d_map, true,
+                          d_n_painted, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -733,9 +771,10 @@ extern "C" int ap_spline_build_uniform(int64_t n, int32_t n_samples, const doubl
 }
 
 // bypass: halos with 0 < n_pix < n_samples; one warp per halo, lane k owns pixel k
+template <class MapT>
 __global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev H, const double* R200, const double* M200,
                                                               const double* zred, const double* scale, const int64_t* n_pix,
-                                                              int32_t ns, double* map, unsigned long long* n_painted) {
+                                                              int32_t ns, MapT* map, unsigned long long* n_painted) {
   int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (h >= H.n) return;
@@ -757,7 +796,7 @@ __global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev 
       b16_setup(R200[h], M200[h], zred[h], ctx);
       double val = b16_tau_2D(ctx, R) * (scale ? scale[h] : 1.0);
       int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
-      atomicAdd(&map[pix], val);
+      atomicAdd(&map[pix], (MapT)val);
       break;
     }
     run += s.len;
@@ -765,9 +804,9 @@ __global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev 
   if (n_painted && lane == 0) atomicAdd(n_painted, (unsigned long long)np);
 }
 
-extern "C" int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
-                                  const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
-                                  int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream) {
+static int paint_b16_small_impl(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
+                                const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
+                                int32_t n_samples, void* d_map, bool f32, unsigned long long* d_n_painted, void* stream) {
   if (check_nside(nside)) return 1;
   if (check_halos(halos, true)) return 1;
   if (n_samples < 2 || n_samples > 32) return fail("n_samples must be in [2, 32]");
@@ -775,10 +814,29 @@ extern "C" int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const do
   if (!d_R_200c || !d_M_200c || !d_redshift || !d_n_pix || !d_map) return fail("paint_b16_small: NULL pointer");
   int threads = 128;
   int64_t blocks = (halos->n * 32 + threads - 1) / threads;
-  paint_b16_small_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-      make_hpx(nside), to_dev(halos), d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted);
+  if (f32)
+    paint_b16_small_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        make_hpx(nside), to_dev(halos), d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, (float*)d_map,
+        d_n_painted);
+  else
+    paint_b16_small_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        make_hpx(nside), to_dev(halos), d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, (double*)d_map,
+        d_n_painted);
   AP_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
+                                  const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
+                                  int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream) {
+  return paint_b16_small_impl(nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, false,
+                              d_n_painted, stream);
+}
+extern "C" int ap_paint_b16_small_f32(int64_t nside, const ap_halos* halos, const double* d_R_200c,
+                                      const double* d_M_200c, const double* d_redshift, const double* d_scale,
+                                      const int64_t* d_n_pix, int32_t n_samples, float* d_map,
+                                      unsigned long long* d_n_painted, void* stream) {
+  return paint_b16_small_impl(nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, true,
+                              d_n_painted, stream);
 }
 
 // ------------------------------------------------------------------------------------------

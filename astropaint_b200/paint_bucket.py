@@ -244,8 +244,12 @@ class Catalog:
 class Canvas:
     """Full-sky HEALPix (RING) canvas; the fp64 pixel array lives in HBM while painting."""
 
-    def __init__(self, catalog, nside, mode="healpy", R_times=1, inclusive=False):
+    def __init__(self, catalog, nside, mode="healpy", R_times=1, inclusive=False, *, accumulate="fp64"):
+        """`accumulate="fp32"` (extra, keyword-only) keeps the map in float32: templates are still
+        evaluated in fp64, each value is rounded once before it is accumulated (parity bar 1e-4)."""
         assert mode == "healpy", "currently only full sky is supported"
+        assert accumulate in ("fp64", "fp32")
+        self.accumulate = accumulate
         self._nside = int(nside)
         self._npix = 12 * self._nside * self._nside
         self._lmax = 3 * self._nside - 1
@@ -290,11 +294,11 @@ class Canvas:
         back once; the host array is then authoritative (users index and mutate it in place, e.g.
         README.md:40-48), so the next spray uploads it again.  `pixels_device` avoids both copies."""
         if self._state == "zero":
-            self._pixels = np.zeros(self.npix)
+            self._pixels = np.zeros(self.npix, dtype=self._np_dtype)
         elif self._state == "device":
             import torch
             if self._host_buf is None:  # page-locked, reused across clean(): one DMA per read-back
-                self._host_buf = torch.empty(self.npix, dtype=torch.float64, pin_memory=True)
+                self._host_buf = torch.empty(self.npix, dtype=self._dmap.dtype, pin_memory=True)
             self._host_buf.copy_(self._dmap)
             self._pixels = self._host_buf.numpy()
             self._dmap_spare = self._dmap
@@ -312,18 +316,23 @@ class Canvas:
         self._Cl_is_outdated = True
 
     @property
+    def _np_dtype(self):
+        return np.float32 if self.accumulate == "fp32" else np.float64
+
+    @property
     def pixels_device(self):
         """The map as a torch CUDA tensor (fp64[npix]); allocated / uploaded on first use."""
         import torch
         dev = eng.require_cuda()
+        tdt = torch.float32 if self.accumulate == "fp32" else torch.float64
         if self._state == "zero":
             if self._dmap_spare is not None and self._dmap_spare.device == dev:
                 self._dmap = self._dmap_spare.zero_()
                 self._dmap_spare = None
             else:
-                self._dmap = torch.zeros(self.npix, dtype=torch.float64, device=dev)
+                self._dmap = torch.zeros(self.npix, dtype=tdt, device=dev)
         elif self._state == "host":
-            host = np.ascontiguousarray(np.broadcast_to(np.asarray(self._pixels, dtype=np.float64), (self.npix,)))
+            host = np.ascontiguousarray(np.broadcast_to(np.asarray(self._pixels, dtype=self._np_dtype), (self.npix,)))
             self._dmap = torch.from_numpy(host).to(dev)
             self._pixels = None
         self._state = "device"

@@ -128,6 +128,19 @@ int ap_stack_cutouts(int64_t nside, const double* d_map, int64_t n_sel, const do
                      const double* d_lat_deg, double lon0, double lon1, double lat0, double lat1,
                      int32_t xsize, int32_t ysize, const double* d_weight, double* d_stack, void* stream);
 
+/* fp32-accumulate mode (BASELINE north_star: 1e-4 parity bar): the same kernels accumulating into a
+ * float32 map (templates are still evaluated in fp64; the value is rounded once before the RED).  */
+int ap_scatter_add_f32(int64_t n, const int64_t* d_pix, const double* d_val, float* d_map, void* stream);
+int ap_paint_profile_f32(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
+                         const int32_t* h_strides, int32_t n_params, float* d_map,
+                         unsigned long long* d_n_painted, void* stream);
+int ap_paint_table_f32(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
+                       const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes, const double* d_scale,
+                       float* d_map, unsigned long long* d_n_painted, void* stream);
+int ap_paint_b16_small_f32(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
+                           const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
+                           int32_t n_samples, float* d_map, unsigned long long* d_n_painted, void* stream);
+
 /* Host-buffer convenience entry (what bench.py's e2e leg and INTEGRATION.md's stub call):
  * copies the halo columns and parameters host->device, paints into a device map initialised
  * from h_map, and copies the map back.  All pointers are HOST pointers.                      */

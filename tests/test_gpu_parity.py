@@ -501,3 +501,44 @@ def test_uniform_spline_kernel_equals_generic_and_scipy():
             got = c[:, 0] + t * (c[:, 1] + t * (c[:, 2] + t * c[:, 3]))
             want = InterpolatedUnivariateSpline(nodes[i], vals[i], k=3)(X)
             assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("kind,name,nside", [("gaussian", "box", 128), ("nfw_ksz", "websky", 4096), ("nfw_bg", "box", 128)])
+def test_fp32_accumulate_mode(cats, kind, name, nside):
+    """BASELINE north_star: map values within 1e-4 in fp32-accumulate mode (max-abs, relative to the map's
+    maximum: single-precision sums of opposite-sign contributions cannot hold a per-pixel relative bar)."""
+    import astropaint_b200 as ap
+    ref, _, _ = _oracle()
+    t, o = _pair(kind)
+    cat = cats[name]
+    canvas = ap.Canvas(cat, nside, R_times=5, accumulate="fp32")
+    ap.Painter(t).spray(canvas)
+    got = canvas.pixels
+    assert got.dtype == np.float32
+    want = np.zeros(12 * nside * nside)
+    ref.spray(want, cat.data, nside, o, R_times=5)
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+    stack = canvas.stack_cutouts(np.arange(5), lon_range=[-1, 1], xpix=16, inplace=False)
+    assert stack.shape == (16, 16) and np.isfinite(stack).all()
+
+
+def test_fp32_accumulate_battaglia_and_python_paths():
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    from astropaint_b200.profiles import Battaglia16
+    ref, o, _ = _oracle()
+    cat = ap.Catalog(synthetic.websky_like(80, seed=11, m_min=1e14))
+    canvas = ap.Canvas(cat, 1024, R_times=5, accumulate="fp32")
+    ap.Painter(Battaglia16.kSZ_T).spray(canvas)
+    want = np.zeros(12 * 1024 * 1024)
+    ref.spray(want, cat.data, 1024, o.b16_kSZ_T, R_times=5)
+    assert np.abs(canvas.pixels - want).max() <= 1e-4 * np.abs(want).max()
+
+    def tmpl(R, R_200c):
+        return 1.0 / (1.0 + (R / R_200c) ** 2)
+
+    canvas = ap.Canvas(cat, 1024, R_times=5, accumulate="fp32")
+    ap.Painter(tmpl).spray(canvas)
+    want = np.zeros(12 * 1024 * 1024)
+    ref.spray(want, cat.data, 1024, tmpl, R_times=5)
+    assert np.abs(canvas.pixels - want).max() <= 1e-4 * np.abs(want).max()
