@@ -181,39 +181,29 @@ AP_HD double ring_sth(const Hpx& h, int64_t iz, double z) {
   return sqrt(AP_MUL(AP_SUB(1.0, z), AP_ADD(1.0, z)));
 }
 
-// loc2pix / vec2pix, RING scheme (hp.vec2pix, paint_bucket.py:1721).
-AP_HD int64_t vec2pix_ring(const Hpx& h, double x, double y, double z) {
-  double xl = 1.0 / sqrt(AP_ADD(AP_ADD(AP_MUL(x, x), AP_MUL(y, y)), AP_MUL(z, z)));
-  double phi = atan2(y, x);
-  double nz = AP_MUL(z, xl);
+// loc2pix (RING) from nz = z/|v|, tt = fmodulo(phi / (pi/2), 4) and, for |nz| >= 0.99, sth = sin(theta).
+AP_HD int64_t loc2pix_ring(const Hpx& h, double nz, double tt, double sth) {
   double za = fabs(nz);
-  // tt = fmodulo(phi / halfpi, 4)
-  double tt = AP_MUL(phi, 1.0 / kHalfPi);
-  if (tt < 0) {
-    tt = AP_ADD(fmod(tt, 4.0), 4.0);
-    if (tt == 4.0) tt = 0.0;
-  } else if (tt >= 4.0) {
-    tt = fmod(tt, 4.0);
-  }
   int64_t ns = h.nside;
   if (za <= kTwoThird) {
-    int64_t nl4 = 4 * ns;
+    // ring / in-ring indices fit 32 bits (nside <= 2^18 is enforced by the C ABI); only the pixel
+    // number needs 64
+    int32_t n32 = (int32_t)ns, nl4 = 4 * n32;
     double t1 = AP_MUL((double)ns, AP_ADD(0.5, tt));
     double t2 = AP_MUL(AP_MUL((double)ns, nz), 0.75);
-    int64_t jp = (int64_t)AP_SUB(t1, t2);
-    int64_t jm = (int64_t)AP_ADD(t1, t2);
-    int64_t ir = ns + 1 + jp - jm;
-    int64_t kshift = 1 - (ir & 1);
-    int64_t t = jp + jm - ns + kshift + 1 + nl4 + nl4;
-    int64_t ip = (t >> 1) % nl4;
-    return h.ncap + (ir - 1) * nl4 + ip;
+    int32_t jp = (int32_t)AP_SUB(t1, t2);
+    int32_t jm = (int32_t)AP_ADD(t1, t2);
+    int32_t ir = n32 + 1 + jp - jm;
+    int32_t kshift = 1 - (ir & 1);
+    int32_t t = jp + jm - n32 + kshift + 1 + nl4 + nl4;
+    int32_t ip = ((n32 & (n32 - 1)) == 0) ? ((t >> 1) & (nl4 - 1)) : ((t >> 1) % nl4);
+    return h.ncap + (int64_t)(ir - 1) * nl4 + ip;
   }
   double tp = AP_SUB(tt, (double)(int64_t)tt);
   double tmp;
   if (za < 0.99) {
     tmp = AP_MUL((double)ns, sqrt(AP_MUL(3.0, AP_SUB(1.0, za))));
   } else {
-    double sth = AP_MUL(sqrt(AP_ADD(AP_MUL(x, x), AP_MUL(y, y))), xl);
     tmp = AP_MUL((double)ns, sth) / sqrt(AP_ADD(1.0, za) / 3.0);
   }
   int64_t jp = (int64_t)AP_MUL(tp, tmp);
@@ -222,6 +212,64 @@ AP_HD int64_t vec2pix_ring(const Hpx& h, double x, double y, double z) {
   int64_t ip = (int64_t)AP_MUL(tt, (double)ir);
   if (ip >= 4 * ir) ip -= 4 * ir;
   return (nz > 0) ? 2 * ir * (ir - 1) + ip : h.npix - 2 * ir * (ir + 1) + ip;
+}
+
+AP_HD double tt_of_phi(double phi) {  // fmodulo(phi / halfpi, 4)
+  double tt = AP_MUL(phi, 1.0 / kHalfPi);
+  if (tt < 0) {
+    tt = AP_ADD(fmod(tt, 4.0), 4.0);
+    if (tt == 4.0) tt = 0.0;
+  } else if (tt >= 4.0) {
+    tt = fmod(tt, 4.0);
+  }
+  return tt;
+}
+
+// loc2pix / vec2pix, RING scheme (hp.vec2pix, paint_bucket.py:1721).
+AP_HD int64_t vec2pix_ring(const Hpx& h, double x, double y, double z) {
+  double xl = 1.0 / sqrt(AP_ADD(AP_ADD(AP_MUL(x, x), AP_MUL(y, y)), AP_MUL(z, z)));
+  double phi = atan2(y, x);
+  double nz = AP_MUL(z, xl);
+  double sth = (fabs(nz) < 0.99) ? 0.0 : AP_MUL(sqrt(AP_ADD(AP_MUL(x, x), AP_MUL(y, y))), xl);
+  return loc2pix_ring(h, nz, tt_of_phi(phi), sth);
+}
+
+// vec2pix for a direction known to lie close in azimuth to a reference azimuth phi_c (a cutout sample
+// around its halo): phi = phi_c + atan(u), u = tan(phi - phi_c) from one cross and one dot product,
+// atan by its series for |u| <= 1/8; otherwise the general atan2.  Identical to vec2pix_ring except
+// where tt lies within ~1e-15 of a pixel boundary (phi carries one extra rounding).
+AP_HD int64_t vec2pix_ring_near(const Hpx& h, double x, double y, double z, double phi_c, double cphi, double sphi) {
+#if defined(__CUDA_ARCH__)
+  double xl = rsqrt(AP_ADD(AP_ADD(AP_MUL(x, x), AP_MUL(y, y)), AP_MUL(z, z)));  // <= 1 ulp from 1/sqrt
+#else
+  double xl = 1.0 / sqrt(AP_ADD(AP_ADD(AP_MUL(x, x), AP_MUL(y, y)), AP_MUL(z, z)));
+#endif
+  double dot = x * cphi + y * sphi;
+  double crs = y * cphi - x * sphi;
+  double phi;
+  if (dot > 0.0 && fabs(crs) <= 0.125 * dot) {
+#if defined(__CUDA_ARCH__)
+    double u = crs * __drcp_rn(dot), u2 = u * u;
+#else
+    double u = crs / dot, u2 = u * u;
+#endif
+    // atan(u)/u = 1 - u^2/3 + u^4/5 - ... - u^18/19 (next term 8^-20/21 < 5e-20)
+    double p = -1.0 / 19.0;
+    p = p * u2 + 1.0 / 17.0;
+    p = p * u2 - 1.0 / 15.0;
+    p = p * u2 + 1.0 / 13.0;
+    p = p * u2 - 1.0 / 11.0;
+    p = p * u2 + 1.0 / 9.0;
+    p = p * u2 - 1.0 / 7.0;
+    p = p * u2 + 1.0 / 5.0;
+    p = p * u2 - 1.0 / 3.0;
+    phi = phi_c + (u + u * u2 * p);
+  } else {
+    phi = atan2(y, x);
+  }
+  double nz = AP_MUL(z, xl);
+  double sth = (fabs(nz) < 0.99) ? 0.0 : AP_MUL(sqrt(AP_ADD(AP_MUL(x, x), AP_MUL(y, y))), xl);
+  return loc2pix_ring(h, nz, tt_of_phi(phi), sth);
 }
 
 }  // namespace ap

@@ -74,6 +74,13 @@ void hc_vec2pix(int64_t nside, int64_t n, const double* x, const double* y, cons
   for (int64_t i = 0; i < n; ++i) out[i] = vec2pix_ring(h, x[i], y[i], z[i]);
 }
 
+void hc_vec2pix_near(int64_t nside, int64_t n, const double* x, const double* y, const double* z, double phi_c,
+                     int64_t* out) {
+  Hpx h = make_hpx(nside);
+  double c = cos(phi_c), s = sin(phi_c);
+  for (int64_t i = 0; i < n; ++i) out[i] = vec2pix_ring_near(h, x[i], y[i], z[i], phi_c, c, s);
+}
+
 void hc_qagi_b16(double R, double R_200c, double M_200c, double redshift, double* result, double* abserr, int* neval,
                  int* ier) {
   double ctx[kCtx];

@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kStackThreads) cutout_kernel(Hpx hpx, const do
                                                                const double* lon, const double* lat, CutGrid grid,
                                                                const double* weight, double* out) {
   __shared__ double rot[kStackHalos][9];
-  __shared__ double wgt[kStackHalos];
+  __shared__ double wgt[kStackHalos], phic[kStackHalos], cphi[kStackHalos], sphi[kStackHalos];
   const int32_t nsamp = grid.xsize * grid.ysize;
   const int32_t s = blockIdx.x * kStackThreads + threadIdx.x;
   const int64_t hbase = (int64_t)blockIdx.y * kStackHalos;
@@ -889,6 +889,9 @@ __global__ void __launch_bounds__(kStackThreads) cutout_kernel(Hpx hpx, const do
   for (int i = threadIdx.x; i < nh; i += kStackThreads) {
     rot_matrix(lon[hbase + i], lat[hbase + i], rot[i]);
     wgt[i] = weight ? weight[hbase + i] : 1.0;
+    double pc = lon[hbase + i] * (kPi / 180.0);  // the halo's azimuth: every sample of its cutout is close to it
+    phic[i] = pc;
+    sincos(pc, &sphi[i], &cphi[i]);
   }
   __syncthreads();
   if (s >= nsamp) return;
@@ -900,7 +903,7 @@ __global__ void __launch_bounds__(kStackThreads) cutout_kernel(Hpx hpx, const do
     double sx = m[0] * vx + m[1] * vy + m[2] * vz;
     double sy = m[3] * vx + m[4] * vy + m[5] * vz;
     double sz = m[6] * vx + m[7] * vy + m[8] * vz;
-    int64_t pix = vec2pix_ring(hpx, sx, sy, sz);
+    int64_t pix = vec2pix_ring_near(hpx, sx, sy, sz, phic[i], cphi[i], sphi[i]);
     double v = __ldg(&map[pix]);
     if (STACK)
       acc += wgt[i] * v;

@@ -175,3 +175,27 @@ def test_device_BG_equals_reference_formula(hc):
     assert hc.hc_profile_vec(8, _p(p), 50, _p(Rv), _p(out)) == 0
     want = oprof.nfw_BG(Rv, *p[:7], T_cmb=p[7])
     assert np.allclose(out, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("nside", [64, 8192])
+def test_vec2pix_near_azimuth_equals_vec2pix(hc, nside):
+    """the cutout kernel's small-angle azimuth path (phi = phi_c + atan series) against the oracle"""
+    hc.hc_vec2pix_near.argtypes = [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, d, C.c_void_p]
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(nside + 1)
+    bad = 0
+    for t in range(60):
+        lon = rng.uniform(0, 2 * np.pi)
+        lat = np.arcsin(rng.uniform(-1, 1)) if t % 6 else rng.choice([1.55, -1.56, 1.2, -0.73])
+        n = 4000
+        dl = rng.uniform(-0.01, 0.01, n) / max(np.cos(lat), 1e-3)
+        db = rng.uniform(-0.01, 0.01, n)
+        if t % 10 == 0:
+            dl = rng.uniform(-np.pi, np.pi, n)          # far in azimuth: general atan2 branch
+        th, ph = np.pi / 2 - np.clip(lat + db, -np.pi / 2, np.pi / 2), lon + dl
+        x, y, z = np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)
+        x, y, z = (np.ascontiguousarray(a) for a in (x, y, z))
+        out = np.empty(n, dtype=np.int64)
+        hc.hc_vec2pix_near(nside, n, _p(x), _p(y), _p(z), lon, _p(out))
+        bad += int((out != hp.vec2pix(x, y, z)).sum())
+    assert bad == 0
