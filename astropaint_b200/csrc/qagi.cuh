@@ -66,8 +66,11 @@ static const double gk15h_wgk[8] = AP_GK15_WGK;
 #endif
 
 template <class F>
-AP_NOINLINE AP_HD_NOINLINE void qk15i(const F& f, double boun, double a, double b, double& result,
+AP_NOINLINE AP_HD_NOINLINE void qk15i(const F& f_ref, double boun, double a, double b, double& result,
                                       double& abserr, double& resabs, double& resasc) {
+  // the rule is out of line, so the integrand object arrives by address (the caller's local memory):
+  // take a register copy once instead of reloading its fields on every evaluation
+  const F f = f_ref;
   double fv1[7], fv2[7];
   double centr = AP_MUL(0.5, AP_ADD(a, b));
   double hlgth = AP_MUL(0.5, AP_SUB(b, a));
@@ -86,7 +89,9 @@ AP_NOINLINE AP_HD_NOINLINE void qk15i(const F& f, double boun, double a, double 
     double absc = AP_MUL(hlgth, AP_GK(xgk)[j]);
     double absc1 = AP_SUB(centr, absc);
     double absc2 = AP_ADD(centr, absc);
-    double i1 = 1.0 / absc1, i2 = 1.0 / absc2;
+    // 1/(c - a) and 1/(c + a) from one reciprocal of (c - a)(c + a)
+    double ip = 1.0 / AP_MUL(absc1, absc2);
+    double i1 = AP_MUL(absc2, ip), i2 = AP_MUL(absc1, ip);
     double f1 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, absc1), i1)));
     double f2 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, absc2), i2)));
     f1 = AP_MUL(AP_MUL(f1, i1), i1);
