@@ -157,8 +157,11 @@ extern "C" int ap_scatter_add_f32(int64_t n, const int64_t* d_pix, const double*
 // K3: fused painter
 // ------------------------------------------------------------------------------------------
 constexpr int kPaintThreads = 256;
-constexpr int kMaxHalosPerBlock = 128;
-constexpr int kHintMax = 1024;
+constexpr int kMaxHalosPerBlock = 112;
+constexpr int kHintMax = 256;     // warp-group hints cover chunks up to 8 Ki pixels
+constexpr int kPixMapMax = 4096;  // pixel -> ring-item byte map for the first 4 Ki pixels of a chunk
+constexpr int kStageHalos = 28;   // spline coefficients staged in shared memory per chunk (P_TABLE)
+constexpr int kStageMaxNodes = 15;
 constexpr int P_TABLE = 100;   // tabulated template (spline of per-halo nodes)
 constexpr int P_STATS = 101;   // no painting: per-halo pixel count and R range (K1)
 
@@ -201,7 +204,7 @@ struct RingItemVec {  // extra per-ring data of R_vec templates
 template <int P>
 struct PaintShared {
   static constexpr bool VEC = (P == P_NFW_BG);
-  static constexpr int NCTX = (P == P_TABLE) ? 3 : ((P == P_STATS) ? 1 : kCtx);
+  static constexpr int NCTX = (P == P_TABLE) ? 4 : ((P == P_STATS) ? 1 : kCtx);
   HaloHdr hdr[kMaxHalosPerBlock];
   double cen_cos[kMaxHalosPerBlock], cen_phi[kMaxHalosPerBlock], cen_sin[kMaxHalosPerBlock],
       cen_Da[kMaxHalosPerBlock];
@@ -213,6 +216,8 @@ struct PaintShared {
   int32_t pix_off[kPaintThreads + 1];
   int32_t warp_sum[kPaintThreads / 32];
   int32_t hint[kHintMax];  // hint[g] = ring item holding pixel 32 g of the current chunk
+  uint8_t pixmap[P == P_STATS ? 1 : kPixMapMax];  // ring item of each of the first 4 Ki pixels
+  double stage[P == P_TABLE ? kStageHalos * (kStageMaxNodes - 1) * 4 : 1];
   // P_STATS accumulators
   unsigned long long cnt[P == P_STATS ? kMaxHalosPerBlock : 1];
   unsigned long long hmin[P == P_STATS ? kMaxHalosPerBlock : 1], hmax[P == P_STATS ? kMaxHalosPerBlock : 1];
@@ -263,7 +268,8 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       const double* x = tab.nodes + h * tab.n_samples;
       sm.ctx[tid][0] = tab.scale ? tab.scale[h] : 1.0;
       sm.ctx[tid][1] = x[0];
-      sm.ctx[tid][2] = (double)(tab.n_samples - 1) / (x[tab.n_samples - 1] - x[0]);
+      sm.ctx[tid][3] = (x[tab.n_samples - 1] - x[0]) / (double)(tab.n_samples - 1);
+      sm.ctx[tid][2] = 1.0 / sm.ctx[tid][3];
     } else {
       double p[kMaxParams];
 #pragma unroll
@@ -287,6 +293,30 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
   unsigned long long painted = 0;
 
   for (int32_t base = 0; base < T; base += kPaintThreads) {
+    // P_TABLE: the spline coefficients of the halos this chunk touches are one contiguous run in HBM;
+    // start streaming the first kStageHalos of them now (coalesced), park them in shared memory after
+    // phase 1 so that phase 2 never waits on a dependent global load
+    constexpr int kStageRegs = (P == P_TABLE) ? (kStageHalos * (kStageMaxNodes - 1) * 4 + kPaintThreads - 1) / kPaintThreads : 1;
+    double stage_reg[kStageRegs];
+    int stage_lo = 0, stage_n = 0;
+    const bool do_stage = (P == P_TABLE) && tab.n_samples <= kStageMaxNodes;
+    if (do_stage) {
+      int lo = 0, hi = G;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (sm.ring_off[mid] <= base) lo = mid; else hi = mid;
+      }
+      stage_lo = lo;
+      const int nc = (tab.n_samples - 1) * 4;
+      stage_n = min(kStageHalos, G - lo) * nc;
+      const double* src = tab.coef + (h0 + lo) * (int64_t)nc;
+#pragma unroll
+      for (int q = 0; q < kStageRegs; ++q) {
+        int e = tid + q * kPaintThreads;
+        stage_reg[q] = (e < stage_n) ? __ldg(src + e) : 0.0;
+      }
+    }
+
     // phase 1: one ring item per thread
     int32_t it = base + tid;
     int32_t len = 0;
@@ -343,6 +373,15 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       if (tid == kPaintThreads - 1) sm.pix_off[kPaintThreads] = end;
       // every multiple of 32 inside [start, end) starts a warp-sized pixel group in this ring item
       for (int32_t m = (start + 31) & ~31; m < end && (m >> 5) < kHintMax; m += 32) sm.hint[m >> 5] = tid;
+      const int32_t mend = min(end, (int32_t)kPixMapMax);
+      for (int32_t m = start; m < mend; ++m) sm.pixmap[m] = (uint8_t)tid;
+      if (do_stage) {
+#pragma unroll
+        for (int q = 0; q < kStageRegs; ++q) {
+          int e = tid + q * kPaintThreads;
+          if (e < stage_n) sm.stage[e] = stage_reg[q];
+        }
+      }
     }
     __syncthreads();
     const int32_t total = sm.pix_off[kPaintThreads];
@@ -352,7 +391,9 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
     // (table loads, series) overlap, then both REDs are issued
     auto eval = [&](int32_t k, int64_t& pix) -> double {
       int lo;
-      if ((k >> 5) < kHintMax) {
+      if (k < kPixMapMax) {
+        lo = sm.pixmap[k];
+      } else if ((k >> 5) < kHintMax) {
         lo = sm.hint[k >> 5];
         while (sm.pix_off[lo + 1] <= k) ++lo;
       } else {  // chunk with more than 32 Ki pixels (sky-sized discs): plain binary search
@@ -389,9 +430,20 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
           } else {
             i = spline_interval(ns, x, R);
           }
-          const double t = R - __ldg(x + i);
-          const double2* c2 = reinterpret_cast<const double2*>(tab.coef + (h * (int64_t)(ns - 1) + i) * 4);
-          const double2 c01 = __ldg(c2), c23 = __ldg(c2 + 1);
+          double t;
+          double2 c01, c23;
+          const int sh = hl - stage_lo;
+          if (do_stage && tab.uniform && sh < kStageHalos) {
+            t = R - (sm.ctx[hl][1] + (double)i * sm.ctx[hl][3]);  // node i of np.linspace to 1 ulp
+            const double2* c2 = reinterpret_cast<const double2*>(sm.stage + (sh * (ns - 1) + i) * 4);
+            c01 = c2[0];
+            c23 = c2[1];
+          } else {
+            t = R - __ldg(x + i);
+            const double2* c2 = reinterpret_cast<const double2*>(tab.coef + (h * (int64_t)(ns - 1) + i) * 4);
+            c01 = __ldg(c2);
+            c23 = __ldg(c2 + 1);
+          }
           val = (c01.x + t * (c01.y + t * (c23.x + t * c23.y))) * sm.ctx[hl][0];
         } else {
           val = profile_eval_R<P>(sm.ctx[hl], R);
