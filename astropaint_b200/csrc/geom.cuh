@@ -51,9 +51,14 @@ AP_HD RingGeom ring_geom(const Hpx& h, int64_t iz, const RingSpan& s, const Halo
   //   sin^2((theta_p+theta_c)/2) = (1 - z_p z_c + s_p s_c)/2
   // (the reference goes through theta_p = acos(z_p), pix2ang; identical to ~1e-12 relative)
   double dz = s.z - c.cos_t;
+#if defined(__CUDA_ARCH__)
+  g.A = (dz * dz) * __drcp_rn(2.0 * ((1.0 - s.z * c.cos_t) + g.sth * c.sin_t));
+  g.phi_step = kTwoPi * __drcp_rn((double)s.nr);
+#else
   g.A = (dz * dz) / (2.0 * ((1.0 - s.z * c.cos_t) + g.sth * c.sin_t));
-  g.B = g.sth * c.sin_t;
   g.phi_step = kTwoPi / (double)s.nr;
+#endif
+  g.B = g.sth * c.sin_t;
   g.phi0 = ((double)s.ip_lo + (s.shifted ? 0.5 : 0.0)) * g.phi_step;
   double d = g.phi0 - c.phi;
   g.d0 = d - kTwoPi * rint(d * kInvTwoPi);

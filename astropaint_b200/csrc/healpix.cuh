@@ -36,26 +36,29 @@ AP_HD int64_t ring_above(const Hpx& h, double z) {
 }
 
 AP_HD double ring2z(const Hpx& h, int64_t ring) {
-  if (ring < h.nside) return AP_SUB(1.0, AP_MUL((double)(ring * ring), h.fact2));
-  if (ring <= 3 * h.nside) return AP_MUL((double)(2 * h.nside - ring), h.fact1);
-  ring = 4 * h.nside - ring;
-  return AP_SUB(AP_MUL((double)(ring * ring), h.fact2), 1.0);
+  // (double)(ring * ring) is exact either way; squaring in fp64 keeps the integer pipe out of it
+  const int32_t r = (int32_t)ring, ns = (int32_t)h.nside;
+  if (r < ns) return AP_SUB(1.0, AP_MUL(AP_MUL((double)r, (double)r), h.fact2));
+  if (r <= 3 * ns) return AP_MUL((double)(2 * ns - r), h.fact1);
+  const double q = (double)(4 * ns - r);
+  return AP_SUB(AP_MUL(AP_MUL(q, q), h.fact2), 1.0);
 }
 
 AP_HD void ring_info(const Hpx& h, int64_t ring, int64_t& startpix, int64_t& ringpix, bool& shifted) {
-  if (ring < h.nside) {
+  const int32_t r = (int32_t)ring, ns = (int32_t)h.nside;  // ring numbers fit 32 bits (nside <= 2^18)
+  if (r < ns) {
     shifted = true;
-    ringpix = 4 * ring;
-    startpix = 2 * ring * (ring - 1);
-  } else if (ring < 3 * h.nside) {
-    shifted = ((ring - h.nside) & 1) == 0;
-    ringpix = 4 * h.nside;
-    startpix = h.ncap + (ring - h.nside) * 4 * h.nside;
+    ringpix = 4 * r;
+    startpix = (int64_t)(2 * r) * (r - 1);
+  } else if (r < 3 * ns) {
+    shifted = ((r - ns) & 1) == 0;
+    ringpix = 4 * ns;
+    startpix = h.ncap + (int64_t)(r - ns) * (4 * ns);
   } else {
     shifted = true;
-    int64_t nr = 4 * h.nside - ring;
+    const int32_t nr = 4 * ns - r;
     ringpix = 4 * nr;
-    startpix = h.npix - 2 * nr * (nr + 1);
+    startpix = h.npix - (int64_t)(2 * nr) * (nr + 1);
   }
 }
 
@@ -131,16 +134,17 @@ AP_HD RingSpan ring_span(const Hpx& h, const DiscHeader& d, int64_t iz) {
   double dphi = atan2(sqrt(ysq), x);
   if (!(dphi > 0)) return s;
   double shift = s.shifted ? 0.5 : 0.0;
-  double f = AP_MUL((double)nr, kInvTwoPi);
-  int64_t ip_lo = (int64_t)floor(AP_SUB(AP_MUL(f, AP_SUB(d.phi, dphi)), shift)) + 1;
-  int64_t ip_hi = (int64_t)floor(AP_SUB(AP_MUL(f, AP_ADD(d.phi, dphi)), shift));
+  double f = AP_MUL((double)s.nr, kInvTwoPi);
+  // |floor(...)| <= 2 nr < 2^21: the conversions stay in 32 bits
+  int32_t ip_lo = (int32_t)floor(AP_SUB(AP_MUL(f, AP_SUB(d.phi, dphi)), shift)) + 1;
+  int32_t ip_hi = (int32_t)floor(AP_SUB(AP_MUL(f, AP_ADD(d.phi, dphi)), shift));
   if (ip_lo > ip_hi) return s;
-  if (ip_hi >= nr) {
-    ip_lo -= nr;
-    ip_hi -= nr;
+  if (ip_hi >= s.nr) {
+    ip_lo -= s.nr;
+    ip_hi -= s.nr;
   }
-  s.ip_lo = (int32_t)ip_lo;
-  s.len = (int32_t)(ip_hi - ip_lo + 1);
+  s.ip_lo = ip_lo;
+  s.len = ip_hi - ip_lo + 1;
   return s;
 }
 
