@@ -36,7 +36,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.mark.parametrize("nside", [1, 2, 8, 64, 512, 8192])
+@pytest.mark.parametrize("nside", [1, 2, 3, 8, 12, 64, 100, 512, 8192])
 def test_disc_pixel_sets_bit_exact(hc, nside):
     hp = H.HealpixRing(nside)
     rng = np.random.default_rng(100 + nside)
@@ -81,7 +81,7 @@ def test_R_and_R_vec_match_healpy_formulas(hc):
             assert abs(rmax.value - Rref.max()) <= 1e-10 * Rref.max()
 
 
-@pytest.mark.parametrize("nside", [1, 4, 64, 8192])
+@pytest.mark.parametrize("nside", [1, 3, 4, 12, 64, 100, 8192])
 def test_vec2pix_bit_exact(hc, nside):
     hp = H.HealpixRing(nside)
     rng = np.random.default_rng(nside)

@@ -12,7 +12,7 @@ from oracle import healpix_np as H, reference_loop as ref, profiles_np as oprof
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.npz")
 
 
-@pytest.mark.parametrize("nside", [1, 2, 4, 16, 64])
+@pytest.mark.parametrize("nside", [1, 2, 3, 4, 12, 16, 64, 100])
 def test_pix_vec_ang_round_trips(nside):
     hp = H.HealpixRing(nside)
     pix = np.arange(hp.npix)
@@ -33,7 +33,7 @@ def test_pix_vec_ang_round_trips(nside):
     assert np.all(np.diff(zs) < 0)
 
 
-@pytest.mark.parametrize("nside", [1, 4, 16, 64])
+@pytest.mark.parametrize("nside", [1, 3, 4, 12, 16, 64])
 def test_query_disc_is_brute_force_disc(nside):
     """{p : angdist(p, c) <= r} over ALL pixels, 250 random discs incl. poles / whole sky / empty."""
     hp = H.HealpixRing(nside)
