@@ -15,7 +15,7 @@ warnings.filterwarnings("ignore", message="The given NumPy array is not writable
 
 from . import _capi
 from ._capi import ApHalos, c_ptr, c_i32, ptr, check
-from .lib import transform
+from .lib import transform  # noqa: F401  (reference expressions cited in DeviceHalos)
 
 GEOMETRY_COLUMNS = ("x", "y", "z", "theta", "phi", "D_a")
 
@@ -59,13 +59,23 @@ class DeviceHalos:
         self._rows = rows
         self._pinned = pinned or {}
         self.cols = {}
-        n_all = len(data)
-        self.index = np.arange(n_all) if rows is None else np.asarray(rows)
-        self.n = len(self.index)
-        radius = R_times * transform.arcmin2rad(self._host_col("R_ang_200c"))
-        self.cols["__radius__"] = to_device(radius, device)
+        self._n_all = len(data)
+        self.n = self._n_all if rows is None else len(rows)
+        # disc radius = R_times * arcmin2rad(R_ang_200c) = R_times * ((R_ang / 60) * (pi / 180))
+        # (paint_bucket.py:1226-1227, lib/transform.py:148-150).  Formed on the device from the uploaded
+        # column with the same three IEEE operations numpy performs (ap_disc_radius; torch's own
+        # `x / 60` multiplies by a reciprocal and rounds differently), so it rounds identically
+        # (tests/test_gpu_parity.py::test_device_radius_is_numpy_radius) and costs no host pass.
+        r_ang = self.col("R_ang_200c")
+        radius = torch.empty_like(r_ang)
+        check(_capi.lib().ap_disc_radius(r_ang.numel(), ptr(r_ang), float(R_times), ptr(radius), stream_ptr()))
+        self.cols["__radius__"] = radius
         for k in GEOMETRY_COLUMNS:
             self.col(k)
+
+    @property
+    def index(self):
+        return np.arange(self._n_all) if self._rows is None else np.asarray(self._rows)
 
     def _take(self, v):
         """rows of a host column: a view for all rows / a contiguous block, a gather otherwise"""
@@ -112,7 +122,7 @@ class DeviceHalos:
         sub._data = self._data
         sub._pinned = {}
         sub._rows = self.index[idx]
-        sub.index = sub._rows
+        sub._n_all = self._n_all
         sub.n = len(idx)
         ti = torch.as_tensor(np.asarray(idx), device=self.device, dtype=torch.int64)
         sub.cols = {k: v.index_select(0, ti) for k, v in self.cols.items()}

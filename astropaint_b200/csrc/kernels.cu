@@ -71,6 +71,28 @@ static int check_nside(int64_t nside) {
 }
 
 // ------------------------------------------------------------------------------------------
+// disc radius: R_times * np.deg2rad(R_ang_200c / 60), operation for operation
+// (Canvas.Disc.gen_pixel_index, paint_bucket.py:1226-1227; transform.arcmin2rad, lib/transform.py:148-150)
+// ------------------------------------------------------------------------------------------
+__global__ void disc_radius_kernel(int64_t n, const double* __restrict__ r_ang_arcmin, double r_times,
+                                   double* __restrict__ radius) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double deg = __ddiv_rn(r_ang_arcmin[i], 60.0);               // angle / 60
+  const double rad = __dmul_rn(deg, 3.14159265358979323846 / 180.0);  // np.deg2rad: x * (pi / 180)
+  radius[i] = __dmul_rn(r_times, rad);
+}
+
+extern "C" int ap_disc_radius(int64_t n, const double* d_R_ang_200c, double R_times, double* d_radius, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n == 0) return 0;
+  if (!d_R_ang_200c || !d_radius) return fail("disc_radius: NULL pointer");
+  disc_radius_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, d_R_ang_200c, R_times, d_radius);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // K1b: flat pixel list (+R, +R_vec); one warp per halo
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) disc_pixels_kernel(Hpx hpx, HalosDev H, const int64_t* pix_off, int64_t* pix,

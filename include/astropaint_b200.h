@@ -46,6 +46,11 @@ typedef struct ap_halos {
 const char* ap_last_error(void);
 int ap_version(void);
 
+/* d_radius[i] = R_times * np.deg2rad(d_R_ang_200c[i] / 60): the query_disc radius of
+ * Canvas.Disc.gen_pixel_index (paint_bucket.py:1226-1227, lib/transform.py:148-150), rounded exactly
+ * as numpy rounds it (IEEE divide, multiply, multiply; no reciprocal, no FMA).                 */
+int ap_disc_radius(int64_t n, const double* d_R_ang_200c, double R_times, double* d_radius, void* stream);
+
 /* hp.query_disc per halo (Canvas.Disc.gen_pixel_index, paint_bucket.py:1215-1229), counts only.
  * d_n_pix[n] (required), d_n_rings[n] (optional).  If d_rmin/d_rmax are non-NULL they receive
  * min/max of R = D_a * angdist over each halo's pixels (gen_cent2pix_mpc, :1266-1273), i.e.

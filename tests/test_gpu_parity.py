@@ -542,3 +542,18 @@ def test_fp32_accumulate_battaglia_and_python_paths():
     want = np.zeros(12 * 1024 * 1024)
     ref.spray(want, cat.data, 1024, tmpl, R_times=5)
     assert np.abs(canvas.pixels - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_device_radius_is_numpy_radius(cats):
+    """the disc radius is formed on the device; it must round exactly like the reference's numpy
+    expression R_times * np.deg2rad(R_ang_200c / 60) (paint_bucket.py:1226-1227)"""
+    import torch
+    from astropaint_b200 import _engine as eng
+    from astropaint_b200 import synthetic
+    import astropaint_b200 as ap
+    big = ap.Catalog(synthetic.websky_like(200000, seed=9))
+    for cat in list(cats.values()) + [big]:
+        for R_times in (1, 5, 2.5):
+            halos = eng.DeviceHalos(cat.data, R_times, torch.device("cuda", 0))
+            want = R_times * np.deg2rad(cat.data.R_ang_200c.values / 60)
+            assert np.array_equal(halos.cols["__radius__"].cpu().numpy(), want)
