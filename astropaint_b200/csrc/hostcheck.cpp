@@ -38,6 +38,23 @@ int64_t hc_query_disc(int64_t nside, double x, double y, double z, double radius
   return n;
 }
 
+// per-halo pixel count and sum of pixel ids for n halos (near-tie scans against the device)
+void hc_query_disc_stats(int64_t nside, int64_t n, const double* x, const double* y, const double* z,
+                         const double* radius, int64_t* count, int64_t* pixsum) {
+  Hpx h = make_hpx(nside);
+  for (int64_t i = 0; i < n; ++i) {
+    DiscHeader d = disc_header(h, x[i], y[i], z[i], radius[i]);
+    int64_t c = 0, s = 0;
+    for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+      RingSpan sp = ring_span(h, d, iz);
+      for (int32_t j = 0; j < sp.len; ++j) s += span_pixel_sorted(sp, j);
+      c += sp.len;
+    }
+    count[i] = c;
+    pixsum[i] = s;
+  }
+}
+
 // R (and R_vec) of every disc pixel, in ascending pixel order; also the span-based R range
 int64_t hc_disc_R(int64_t nside, double x, double y, double z, double radius, double theta, double phi, double D_a,
                   double* R, double* Rvec, int64_t cap, double* rmin, double* rmax) {

@@ -14,7 +14,10 @@
 
 namespace ap {
 
-constexpr int kQagiLimit = 50;       // scipy.integrate.quad default `limit`
+#ifndef AP_QAGI_LIMIT
+#define AP_QAGI_LIMIT 50
+#endif
+constexpr int kQagiLimit = AP_QAGI_LIMIT;  // scipy.integrate.quad default `limit` = 50
 constexpr double kEpmach = 2.220446049250313e-16;   // d1mach(4)
 constexpr double kUflow = 2.2250738585072014e-308;  // d1mach(1)
 constexpr double kOflow = 1.7976931348623157e+308;  // d1mach(2)

@@ -557,3 +557,34 @@ def test_device_radius_is_numpy_radius(cats):
             halos = eng.DeviceHalos(cat.data, R_times, torch.device("cuda", 0))
             want = R_times * np.deg2rad(cat.data.R_ang_200c.values / 60)
             assert np.array_equal(halos.cols["__radius__"].cpu().numpy(), want)
+
+
+def test_disc_query_cuda_vs_glibc_at_scale():
+    """5e5 Websky-shaped discs at nside 8192 (4e7 halo-pixels, 1.1e7 ring boundaries): per-halo pixel
+    count and sum of pixel ids from the device (CUDA libm) equal those of the same header compiled for
+    the host (glibc) — the near-tie scan of DESIGN.md §5."""
+    import ctypes as C
+    import os
+    import torch
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic, _engine as eng
+    N, nside = 500000, 8192
+    L = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "astropaint_b200", "_native",
+                            "libap_hostcheck.so"))
+    L.hc_query_disc_stats.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 6
+    cat = ap.Catalog(synthetic.websky_like(N, seed=21))
+    dev = torch.device("cuda", 0)
+    halos = eng.DeviceHalos(cat.data, 5, dev)
+    n_pix, _, _, _ = eng.disc_count(halos, nside)
+    off, pix, _, _ = eng.disc_pixels(halos, nside, n_pix)
+    seg = torch.repeat_interleave(torch.arange(N, device=dev), n_pix)
+    sum_d = torch.zeros(N, dtype=torch.int64, device=dev).index_add_(0, seg, pix).cpu().numpy()
+    cnt_d = n_pix.cpu().numpy()
+    d = cat.data
+    x, y, z = (np.ascontiguousarray(d[k].values) for k in "xyz")
+    rad = np.ascontiguousarray(5 * np.deg2rad(d.R_ang_200c.values / 60))
+    cnt_h, sum_h = np.zeros(N, dtype=np.int64), np.zeros(N, dtype=np.int64)
+    L.hc_query_disc_stats(nside, N, x.ctypes.data, y.ctypes.data, z.ctypes.data, rad.ctypes.data, cnt_h.ctypes.data,
+                          sum_h.ctypes.data)
+    assert np.array_equal(cnt_d, cnt_h) and np.array_equal(sum_d, sum_h)
+    assert cnt_d.sum() > 3e7
