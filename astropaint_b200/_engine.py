@@ -197,6 +197,25 @@ def table_nodes(halos, n_pix, rmin, rmax, n_samples, method):
     return nodes, n_nodes
 
 
+LOS_KINDS = {"b16_tau": 0, "b16_ne": 1, "b16_rho_gas": 2, "nfw_rho": 3}
+
+
+def los_nodes(kind, halos, args, nodes, n_nodes):
+    """QUADPACK projection of the 3-D profile `kind` at every (halo, node); args = its per-halo arguments."""
+    values = torch.empty_like(nodes)
+    a = list(args) + [None] * (3 - len(args))
+    check(_capi.lib().ap_los_nodes(LOS_KINDS[kind], halos.n, ptr(a[0]), ptr(a[1]), ptr(a[2]), nodes.shape[1], ptr(nodes),
+                                   ptr(n_nodes), ptr(values), stream_ptr()))
+    return values
+
+
+def paint_los_small(kind, halos, nside, args, scale, n_pix, n_samples, d_map, d_count=None):
+    s = halos.struct()
+    a = list(args) + [None] * (3 - len(args))
+    check(_fn("ap_paint_los_small", d_map)(LOS_KINDS[kind], nside, C.byref(s), ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(scale),
+                                           ptr(n_pix), n_samples, ptr(d_map), ptr(d_count), stream_ptr()))
+
+
 def b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes):
     values = torch.empty_like(nodes)
     check(_capi.lib().ap_b16_tau_nodes(halos.n, ptr(R200), ptr(M200), ptr(zred), nodes.shape[1], ptr(nodes),

@@ -8,7 +8,7 @@ table path when they are wrapped in `@interpolate`.
 # ids of include/astropaint_b200.h :: enum ap_profile
 AP_CONSTANT, AP_LINEAR, AP_SOLID_SPHERE, AP_GAUSSIAN = 0, 1, 2, 3
 AP_NFW_RHO2D, AP_NFW_TAU2D, AP_NFW_KSZ, AP_NFW_DEFLECTION, AP_NFW_BG = 4, 5, 6, 7, 8
-AP_B16_TAU2D = 9
+AP_B16_TAU2D, AP_B16_RHOGAS2D, AP_NFW_RHO2D_LOS = 9, 10, 11
 
 
 def device_profile(profile_id, args, kwonly=None):

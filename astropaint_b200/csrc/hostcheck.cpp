@@ -110,6 +110,22 @@ void hc_qagi_b16(double R, double R_200c, double M_200c, double redshift, double
   *ier = q.ier;
 }
 
+// generic LOS projection with QUADPACK diagnostics (kind = LosKind)
+int hc_los(int kind, double R, double p0, double p1, double p2, double* result, int* neval) {
+  double ctx[kCtx];
+  QagiResult q;
+  switch (kind) {
+    case LOS_B16_TAU: los_setup<LOS_B16_TAU>(p0, p1, p2, ctx); los_eval<LOS_B16_TAU>(ctx, R, &q); break;
+    case LOS_B16_NE: los_setup<LOS_B16_NE>(p0, p1, p2, ctx); los_eval<LOS_B16_NE>(ctx, R, &q); break;
+    case LOS_B16_RHO_GAS: los_setup<LOS_B16_RHO_GAS>(p0, p1, p2, ctx); los_eval<LOS_B16_RHO_GAS>(ctx, R, &q); break;
+    case LOS_NFW_RHO: los_setup<LOS_NFW_RHO>(p0, p1, p2, ctx); los_eval<LOS_NFW_RHO>(ctx, R, &q); break;
+    default: return 1;
+  }
+  *result = q.result;
+  *neval = q.neval;
+  return 0;
+}
+
 double hc_b16_tau_3D(double r, double R_200c, double M_200c, double redshift) {
   double ctx[kCtx];
   b16_setup(R_200c, M_200c, redshift, ctx);
@@ -138,6 +154,8 @@ int hc_profile_R(int profile, const double* p, int64_t n, const double* R, doubl
     case P_NFW_KSZ: eval_R<P_NFW_KSZ>(p, n, R, out); return 0;
     case P_NFW_DEFLECTION: eval_R<P_NFW_DEFLECTION>(p, n, R, out); return 0;
     case P_B16_TAU2D: eval_R<P_B16_TAU2D>(p, n, R, out); return 0;
+    case P_B16_RHOGAS2D: eval_R<P_B16_RHOGAS2D>(p, n, R, out); return 0;
+    case P_NFW_RHO2D_LOS: eval_R<P_NFW_RHO2D_LOS>(p, n, R, out); return 0;
   }
   return 1;
 }

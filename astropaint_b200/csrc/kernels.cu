@@ -585,6 +585,8 @@ static int paint_profile_impl(int profile, int64_t nside, const ap_halos* halos,
     case P_NFW_DEFLECTION: return launch_paint<P_NFW_DEFLECTION>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
     case P_NFW_BG: return launch_paint<P_NFW_BG>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
     case P_B16_TAU2D: return launch_paint<P_B16_TAU2D>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_B16_RHOGAS2D: return launch_paint<P_B16_RHOGAS2D>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
+    case P_NFW_RHO2D_LOS: return launch_paint<P_NFW_RHO2D_LOS>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
   }
   return fail("unknown profile id");
 }
@@ -672,12 +674,15 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
 
 // 7 blocks of 128 threads per SM (72 registers): measured 3% faster than the unconstrained 96-register
 // build; the kernel is fp64-pipe bound (~55-70% of the DFMA issue rate), not occupancy bound
+// 7 blocks of 128 threads per SM (72 registers): measured 3% faster than the unconstrained 96-register
+// build; the kernel is fp64-pipe bound (~55-70% of the DFMA issue rate), not occupancy bound
 #ifndef AP_QAGI_MINBLOCKS
 #define AP_QAGI_MINBLOCKS 7
 #endif
-__global__ void __launch_bounds__(128, AP_QAGI_MINBLOCKS) b16_tau_nodes_kernel(int64_t n, const double* R200, const double* M200,
-                                                            const double* zred, int32_t ns, const double* nodes,
-                                                            const int32_t* n_nodes, double* values) {
+template <int KIND>
+__global__ void __launch_bounds__(128, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64_t n, const double* p0, const double* p1,
+                                                                           const double* p2, int32_t ns, const double* nodes,
+                                                                           const int32_t* n_nodes, double* values) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * ns) return;
   int64_t h = t / ns;
@@ -686,22 +691,36 @@ __global__ void __launch_bounds__(128, AP_QAGI_MINBLOCKS) b16_tau_nodes_kernel(i
     return;
   }
   double ctx[kCtx];
-  b16_setup(R200[h], M200[h], zred[h], ctx);
-  values[t] = b16_tau_2D(ctx, nodes[t]);
+  los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+  values[t] = los_eval<KIND>(ctx, nodes[t]);
+}
+
+extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const double* d_p1, const double* d_p2,
+                            int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes, double* d_values,
+                            void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
+  if (n == 0) return 0;
+  if (!d_p0 || !d_p1 || (kind != LOS_NFW_RHO && !d_p2) || !d_nodes || !d_n_nodes || !d_values)
+    return fail("los_nodes: NULL pointer");
+  int threads = 128;
+  int64_t total = n * n_samples;
+  unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case LOS_B16_TAU: los_nodes_kernel<LOS_B16_TAU><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
+    case LOS_B16_NE: los_nodes_kernel<LOS_B16_NE><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
+    case LOS_B16_RHO_GAS: los_nodes_kernel<LOS_B16_RHO_GAS><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
+    case LOS_NFW_RHO: los_nodes_kernel<LOS_NFW_RHO><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
+  }
+  AP_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double* d_M_200c, const double* d_redshift,
                                 int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes, double* d_values,
                                 void* stream) {
-  if (n < 0) return fail("n < 0");
-  if (n == 0) return 0;
-  if (!d_R_200c || !d_M_200c || !d_redshift || !d_nodes || !d_n_nodes || !d_values) return fail("b16_tau_nodes: NULL pointer");
-  int threads = 128;
-  int64_t total = n * n_samples;
-  b16_tau_nodes_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-      n, d_R_200c, d_M_200c, d_redshift, n_samples, d_nodes, d_n_nodes, d_values);
-  AP_LAUNCH_CHECK();
-  return 0;
+  return ap_los_nodes(LOS_B16_TAU, n, d_R_200c, d_M_200c, d_redshift, n_samples, d_nodes, d_n_nodes, d_values, stream);
 }
 
 // diagnostic: tau_2D(R) with QUADPACK's own error estimate and evaluation count
@@ -845,8 +864,8 @@ extern "C" int ap_spline_build_uniform(int64_t n, int32_t n_samples, const doubl
 }
 
 // bypass: halos with 0 < n_pix < n_samples; one warp per halo, lane k owns pixel k
-template <class MapT>
-__global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev H, const double* R200, const double* M200,
+template <int KIND, class MapT>
+__global__ void __launch_bounds__(128) paint_los_small_kernel(Hpx hpx, HalosDev H, const double* R200, const double* M200,
                                                               const double* zred, const double* scale, const int64_t* n_pix,
                                                               int32_t ns, MapT* map, unsigned long long* n_painted) {
   int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -867,8 +886,8 @@ __global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev 
       int32_t ip = s.ip_lo + js;
       double R = c.D_a * pixel_sep(g, js);
       double ctx[kCtx];
-      b16_setup(R200[h], M200[h], zred[h], ctx);
-      double val = b16_tau_2D(ctx, R) * (scale ? scale[h] : 1.0);
+      los_setup<KIND>(R200[h], M200[h], zred ? zred[h] : 0.0, ctx);
+      double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
       int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
       atomicAdd(&map[pix], (MapT)val);
       break;
@@ -878,39 +897,69 @@ __global__ void __launch_bounds__(128) paint_b16_small_kernel(Hpx hpx, HalosDev 
   if (n_painted && lane == 0) atomicAdd(n_painted, (unsigned long long)np);
 }
 
-static int paint_b16_small_impl(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
-                                const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
-                                int32_t n_samples, void* d_map, bool f32, unsigned long long* d_n_painted, void* stream) {
+template <int KIND>
+static void launch_los_small(bool f32, unsigned blocks, int threads, cudaStream_t st, Hpx hpx, HalosDev H, const double* p0,
+                             const double* p1, const double* p2, const double* scale, const int64_t* n_pix, int32_t ns,
+                             void* map, unsigned long long* n_painted) {
+  if (f32)
+    paint_los_small_kernel<KIND, float><<<blocks, threads, 0, st>>>(hpx, H, p0, p1, p2, scale, n_pix, ns, (float*)map, n_painted);
+  else
+    paint_los_small_kernel<KIND, double><<<blocks, threads, 0, st>>>(hpx, H, p0, p1, p2, scale, n_pix, ns, (double*)map, n_painted);
+}
+
+static int paint_los_small_impl(int kind, int64_t nside, const ap_halos* halos, const double* d_R_200c,
+                                const double* d_M_200c, const double* d_redshift, const double* d_scale,
+                                const int64_t* d_n_pix, int32_t n_samples, void* d_map, bool f32,
+                                unsigned long long* d_n_painted, void* stream) {
+  if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
   if (check_nside(nside)) return 1;
   if (check_halos(halos, true)) return 1;
   if (n_samples < 2 || n_samples > 32) return fail("n_samples must be in [2, 32]");
   if (halos->n == 0) return 0;
-  if (!d_R_200c || !d_M_200c || !d_redshift || !d_n_pix || !d_map) return fail("paint_b16_small: NULL pointer");
+  if (!d_R_200c || !d_M_200c || (kind != LOS_NFW_RHO && !d_redshift) || !d_n_pix || !d_map)
+    return fail("paint_los_small: NULL pointer");
   int threads = 128;
   int64_t blocks = (halos->n * 32 + threads - 1) / threads;
-  if (f32)
-    paint_b16_small_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        make_hpx(nside), to_dev(halos), d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, (float*)d_map,
-        d_n_painted);
-  else
-    paint_b16_small_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        make_hpx(nside), to_dev(halos), d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, (double*)d_map,
-        d_n_painted);
+  {
+    Hpx hpx = make_hpx(nside);
+    HalosDev H = to_dev(halos);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned nb = (unsigned)blocks;
+    switch (kind) {
+      case LOS_B16_TAU: launch_los_small<LOS_B16_TAU>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
+      case LOS_B16_NE: launch_los_small<LOS_B16_NE>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
+      case LOS_B16_RHO_GAS: launch_los_small<LOS_B16_RHO_GAS>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
+      case LOS_NFW_RHO: launch_los_small<LOS_NFW_RHO>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
+    }
+  }
   AP_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int ap_paint_los_small(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
+                                  const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
+                                  double* d_map, unsigned long long* d_n_painted, void* stream) {
+  return paint_los_small_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_pix, n_samples, d_map, false, d_n_painted,
+                              stream);
+}
+extern "C" int ap_paint_los_small_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0,
+                                      const double* d_p1, const double* d_p2, const double* d_scale,
+                                      const int64_t* d_n_pix, int32_t n_samples, float* d_map,
+                                      unsigned long long* d_n_painted, void* stream) {
+  return paint_los_small_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_pix, n_samples, d_map, true, d_n_painted,
+                              stream);
 }
 extern "C" int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
                                   const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
                                   int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream) {
-  return paint_b16_small_impl(nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, false,
-                              d_n_painted, stream);
+  return paint_los_small_impl(LOS_B16_TAU, nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples,
+                              d_map, false, d_n_painted, stream);
 }
 extern "C" int ap_paint_b16_small_f32(int64_t nside, const ap_halos* halos, const double* d_R_200c,
                                       const double* d_M_200c, const double* d_redshift, const double* d_scale,
                                       const int64_t* d_n_pix, int32_t n_samples, float* d_map,
                                       unsigned long long* d_n_painted, void* stream) {
-  return paint_b16_small_impl(nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, true,
-                              d_n_painted, stream);
+  return paint_los_small_impl(LOS_B16_TAU, nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples,
+                              d_map, true, d_n_painted, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -25,7 +25,17 @@ enum ProfileId : int {
   P_NFW_DEFLECTION = 7, // NFW.deflection_angle(R, c_200c, R_200c, M_200c)
   P_NFW_BG = 8,         // NFW.BG(R_vec, c_200c, R_200c, M_200c, theta, phi, v_th, v_ph, *, T_cmb)
   P_B16_TAU2D = 9,      // Battaglia16.tau_2D(R, R_200c, M_200c, redshift)  (QUADPACK per pixel)
-  P_COUNT_ = 10
+  P_B16_RHOGAS2D = 10,  // Battaglia16.rho_gas_2D(R, R_200c, M_200c, redshift)  (QUADPACK per pixel)
+  P_NFW_RHO2D_LOS = 11, // NFW.rho_2D(R, rho_s, R_s) = LOS_integrate(rho_3D)  (QUADPACK per pixel)
+  P_COUNT_ = 12
+};
+
+// 3-D profiles that @LOS_integrate projects on device (ap_los_nodes / ap_paint_los_small)
+enum LosKind : int {
+  LOS_B16_TAU = 0,      // Battaglia16.tau_3D(r, R_200c, M_200c, redshift)
+  LOS_B16_NE = 1,       // Battaglia16.ne_3D
+  LOS_B16_RHO_GAS = 2,  // Battaglia16.rho_gas_3D
+  LOS_NFW_RHO = 3       // NFW.rho_3D(r, rho_s, r_s)
 };
 
 constexpr int kMaxParams = 8;
@@ -43,6 +53,8 @@ AP_HD int profile_n_params(int id) {
     case P_NFW_DEFLECTION: return 3;
     case P_NFW_BG: return 8;
     case P_B16_TAU2D: return 3;
+    case P_B16_RHOGAS2D: return 3;
+    case P_NFW_RHO2D_LOS: return 2;
     default: return -1;
   }
 }
@@ -138,6 +150,60 @@ AP_HD void b16_setup(double R_200c, double M_200c, double z, double* ctx) {
   ctx[3] = rho0 * critical_density(z) * (cst::Ob0 / cst::Om0) / factor * cst::sigma_T;
 }
 
+// NFW.rho_3D(r) * 2r / sqrt(r^2 - R^2) = 8 rho_s r_s^3 / ((r + r_s)^2 sqrt(r^2 - R^2))   (NFW.py:38-58, 83-93)
+struct NfwRhoIntegrand {
+  double K8, rs, RR;
+  AP_HD double operator()(double r) const {
+    double q = AP_ADD(r, rs);
+    double w = AP_SUB(AP_MUL(r, r), RR);
+#if defined(__CUDA_ARCH__)
+    return AP_MUL(K8 * __drcp_rn(AP_MUL(q, q)), rsqrt(w));
+#else
+    return K8 / AP_MUL(q, q) / sqrt(w);
+#endif
+  }
+};
+
+template <int KIND>
+AP_HD void los_setup(double p0, double p1, double p2, double* ctx) {
+  if (KIND == LOS_NFW_RHO) {
+    ctx[0] = 8.0 * p0 * p1 * p1 * p1;
+    ctx[1] = p1;
+    return;
+  }
+  b16_setup(p0, p1, p2, ctx);  // ctx[3] = sigma_T * n_e normalisation
+  if (KIND != LOS_B16_TAU) {
+    ctx[3] /= cst::sigma_T;  // n_e
+    if (KIND == LOS_B16_RHO_GAS) {
+      const double me = 9.10938291e-31, mH = 1.67262178e-27, mHe = 4.0 * mH, xH = 0.76;
+      const double nH_ne = 2.0 * xH / (xH + 1.0), nHe_ne = (1.0 - xH) / (2.0 * (1.0 + xH));
+      ctx[3] *= (me + nH_ne * mH + nHe_ne * mHe) / 1.989e30 * cst::h;  // back to rho_gas
+    }
+  }
+}
+
+template <int KIND>
+AP_HD double los_eval(const double* ctx, double R, QagiResult* info = nullptr) {
+  QagiResult q;
+  if (KIND == LOS_NFW_RHO) {
+    NfwRhoIntegrand f;
+    f.K8 = ctx[0];
+    f.rs = ctx[1];
+    f.RR = AP_MUL(R, R);
+    q = qagi_upper(f, R, 0.0, 1.0e-2);
+  } else {
+    B16Integrand f;
+    f.inv_R200xc = ctx[0];
+    f.alpha = ctx[1];
+    f.expo = ctx[2];
+    f.K2 = 2.0 * ctx[3];
+    f.RR = AP_MUL(R, R);
+    q = qagi_upper(f, R, 0.0, 1.0e-2);  // utils.py:448
+  }
+  if (info) *info = q;
+  return q.result;
+}
+
 AP_HD double b16_tau_2D(const double* ctx, double R, QagiResult* info = nullptr) {
   B16Integrand f;
   f.inv_R200xc = ctx[0];
@@ -193,6 +259,10 @@ AP_HD void profile_setup(const double* p, double* ctx) {
     }
   } else if (P == P_B16_TAU2D) {
     b16_setup(p[0], p[1], p[2], ctx);
+  } else if (P == P_B16_RHOGAS2D) {
+    los_setup<LOS_B16_RHO_GAS>(p[0], p[1], p[2], ctx);
+  } else if (P == P_NFW_RHO2D_LOS) {
+    los_setup<LOS_NFW_RHO>(p[0], p[1], 0.0, ctx);
   }
 }
 
@@ -219,6 +289,8 @@ AP_HD double profile_eval_R(const double* ctx, double R) {
   }
   if (P == P_NFW_DEFLECTION) return nfw_deflection(ctx, R);
   if (P == P_B16_TAU2D) return b16_tau_2D(ctx, R);
+  if (P == P_B16_RHOGAS2D) return los_eval<LOS_B16_RHO_GAS>(ctx, R);
+  if (P == P_NFW_RHO2D_LOS) return los_eval<LOS_NFW_RHO>(ctx, R);
   return 0.0;
 }
 

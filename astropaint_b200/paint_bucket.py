@@ -707,10 +707,10 @@ class Painter:
         ns = info["n_samples"]
         n_pix, _, rmin, rmax = eng.disc_count(halos, nside, want_range=True)
         nodes, n_nodes = eng.table_nodes(halos, n_pix, rmin, rmax, ns, info["sampling_method"])
-        assert info["kind"] == "b16_tau"
-        R200, M200, zred = (col(a) for a in info["args"])
-        R200, M200, zred = (t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in (R200, M200, zred))
-        values = eng.b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes)
+        assert info["kind"] in eng.LOS_KINDS
+        args = [col(a) for a in info["args"]]
+        args = [t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in args]
+        values = eng.los_nodes(info["kind"], halos, args, nodes, n_nodes)
         coef = eng.spline_build(nodes, values, n_nodes, uniform=(info["sampling_method"] == "linspace"))
         scale = None
         if info["scale"] is not None:
@@ -722,7 +722,7 @@ class Painter:
             scale = scale.contiguous()
         eng.paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count,
                         uniform=(info["sampling_method"] == "linspace"))
-        eng.paint_b16_small(halos, nside, R200, M200, zred, scale, n_pix, ns, d_map, d_count)
+        eng.paint_los_small(info["kind"], halos, nside, args, scale, n_pix, ns, d_map, d_count)
 
     def _paint_python_table(self, info, halos, nside, rows, R_mode, host_cols, d_map, d_count):
         """A Python template wrapped in @interpolate: nodes, spline and painting on device; the

@@ -7,7 +7,7 @@ import numpy as np
 
 from ..lib.cosmology import cosmo, sigma_T, m_p  # noqa: F401
 from ..lib.utils import interpolate, LOS_integrate
-from .._registry import device_profile, device_table, AP_B16_TAU2D
+from .._registry import device_profile, device_table, AP_B16_TAU2D, AP_B16_RHOGAS2D
 
 f_b = cosmo.Ob0 / cosmo.Om0
 c = 299792.  # km/s
@@ -67,11 +67,13 @@ def rho_gas_2D_interp(R, R_200c, M_200c, redshift):
     return rho_gas_3D(R, R_200c, M_200c, redshift)
 
 
+@device_profile(AP_B16_RHOGAS2D, ["R_200c", "M_200c", "redshift"])
 @LOS_integrate
 def rho_gas_2D(R, R_200c, M_200c, redshift):
     return rho_gas_3D(R, R_200c, M_200c, redshift)
 
 
+@device_table("b16_ne", ["R_200c", "M_200c", "redshift"], n_samples=20)
 @interpolate
 @LOS_integrate
 def ne_2D(R, R_200c, M_200c, redshift):

@@ -9,8 +9,8 @@ import numpy as np
 from ..lib.cosmology import cosmo, sigma_T, m_p
 from ..lib.utils import interpolate, LOS_integrate
 from ..lib import transform
-from .._registry import (device_profile, AP_NFW_RHO2D, AP_NFW_TAU2D, AP_NFW_KSZ,
-                         AP_NFW_DEFLECTION, AP_NFW_BG)
+from .._registry import (device_profile, device_table, AP_NFW_RHO2D, AP_NFW_TAU2D, AP_NFW_KSZ,
+                         AP_NFW_DEFLECTION, AP_NFW_BG, AP_NFW_RHO2D_LOS)
 
 f_b = cosmo.Ob0 / cosmo.Om0
 c = 299792.  # km/s
@@ -46,12 +46,14 @@ def rho_2D_bartlemann(R, rho_s, R_s):
     return 8 * rho_s * R_s * f
 
 
+@device_profile(AP_NFW_RHO2D_LOS, ["rho_s", "R_s"])
 @LOS_integrate
 def rho_2D(R, rho_s, R_s):
     """3-D NFW profile integrated along the line of sight."""
     return rho_3D(R, rho_s, R_s)
 
 
+@device_table("nfw_rho", ["rho_s", "R_s"], n_samples=20, sampling_method="logspace")
 @interpolate(n_samples=20, sampling_method="logspace")
 @LOS_integrate
 def rho_2D_interp(R, rho_s, R_s):

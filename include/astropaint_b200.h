@@ -30,7 +30,17 @@ enum ap_profile {
   AP_NFW_KSZ = 6,        /* profiles/NFW.py:172-178       kSZ_T(R, rho_s, R_s, v_r, T_cmb) */
   AP_NFW_DEFLECTION = 7, /* profiles/NFW.py:111-150       deflection_angle(R, c_200c, R_200c, M_200c) */
   AP_NFW_BG = 8,         /* profiles/NFW.py:181-193       BG(R_vec, c_200c, R_200c, M_200c, theta, phi, v_th, v_ph, T_cmb) */
-  AP_B16_TAU2D = 9       /* profiles/Battaglia16.py:221-239 tau_2D(R, R_200c, M_200c, redshift) */
+  AP_B16_TAU2D = 9,      /* profiles/Battaglia16.py:221-239 tau_2D(R, R_200c, M_200c, redshift) */
+  AP_B16_RHOGAS2D = 10,  /* profiles/Battaglia16.py:181-198 rho_gas_2D(R, R_200c, M_200c, redshift) */
+  AP_NFW_RHO2D_LOS = 11  /* profiles/NFW.py:83-93         rho_2D(R, rho_s, R_s) = LOS_integrate(rho_3D) */
+};
+
+/* 3-D profiles projected by @LOS_integrate on device (one QUADPACK qagie per line of sight) */
+enum ap_los_kind {
+  AP_LOS_B16_TAU = 0,      /* Battaglia16.tau_3D(r, R_200c, M_200c, redshift)   :132-155 */
+  AP_LOS_B16_NE = 1,       /* Battaglia16.ne_3D                                  :97-129  */
+  AP_LOS_B16_RHO_GAS = 2,  /* Battaglia16.rho_gas_3D                             :65-94   */
+  AP_LOS_NFW_RHO = 3       /* NFW.rho_3D(r, rho_s, r_s)                          NFW.py:38-58 */
 };
 
 /* Per-halo geometry inputs shared by all entry points (catalog columns, paint_bucket.py:308-364):
@@ -91,6 +101,12 @@ int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double* d_M_200c, 
                      int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes,
                      double* d_values, void* stream);
 
+/* The same for any ap_los_kind: d_p0, d_p1, d_p2 are the 3-D profile's per-halo arguments in reference
+ * order (R_200c, M_200c, redshift | rho_s, r_s, NULL).  Serves Battaglia16.ne_2D (interpolate(n=20) of
+ * LOS_integrate(ne_3D), :201-218) and NFW.rho_2D_interp (n=20, logspace; NFW.py:96-108).            */
+int ap_los_nodes(int kind, int64_t n, const double* d_p0, const double* d_p1, const double* d_p2, int32_t n_samples,
+                 const double* d_nodes, const int32_t* d_n_nodes, double* d_values, void* stream);
+
 /* Diagnostic: Battaglia16.tau_2D at arbitrary (R, halo) pairs with QUADPACK's abserr and neval
  * (scipy.integrate.quad full_output; lib/utils.py:448).  d_abserr / d_neval may be NULL.       */
 int ap_b16_tau_eval(int64_t n, const double* d_R, const double* d_R_200c, const double* d_M_200c,
@@ -121,6 +137,10 @@ int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_2
                        const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
                        int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream);
 
+int ap_paint_los_small(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
+                       const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
+                       double* d_map, unsigned long long* d_n_painted, void* stream);
+
 /* Canvas.cutouts / stack_cutouts (paint_bucket.py:1601-1743, 1745-1941): healpy
  * CartesianProj(lonra, latra, xsize, ysize).projmap(map, rot=(lon, lat), vec2pix) per halo.
  * d_lon_deg/d_lat_deg[n_sel] are the catalog lon/lat (degrees) of the selected halos.
@@ -142,6 +162,9 @@ int ap_paint_profile_f32(int profile, int64_t nside, const ap_halos* halos, cons
 int ap_paint_table_f32(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
                        const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes, const double* d_scale,
                        float* d_map, unsigned long long* d_n_painted, void* stream);
+int ap_paint_los_small_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
+                           const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
+                           float* d_map, unsigned long long* d_n_painted, void* stream);
 int ap_paint_b16_small_f32(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
                            const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
                            int32_t n_samples, float* d_map, unsigned long long* d_n_painted, void* stream);

@@ -252,3 +252,28 @@ def b16_kSZ_T(R, R_200c, M_200c, v_r, redshift, *, T_cmb=T_cmb):
     """Battaglia16.py:265-271"""
     tau = b16_tau_2D_interp(R, R_200c, M_200c, redshift)
     return -tau * v_r / c * T_cmb * (1 + redshift)
+
+
+def nfw_rho_3D(r, rho_s, r_s):
+    """NFW.py:38-58"""
+    return 4 * rho_s * r_s ** 3 / r / (r + r_s) ** 2
+
+
+def nfw_rho_2D(R, rho_s, R_s):
+    """NFW.py:83-93 = LOS_integrate(rho_3D)"""
+    return los_integrate(nfw_rho_3D, R, rho_s, R_s)
+
+
+def nfw_rho_2D_interp(R, rho_s, R_s):
+    """NFW.py:96-108 = interpolate(n_samples=20, sampling_method="logspace")(LOS_integrate(rho_3D))"""
+    return interpolate(nfw_rho_2D, R, rho_s, R_s, n_samples=20, sampling_method="logspace")
+
+
+def b16_rho_gas_2D(R, R_200c, M_200c, redshift):
+    """Battaglia16.py:181-198"""
+    return los_integrate(b16_rho_gas_3D, R, R_200c, M_200c, redshift)
+
+
+def b16_ne_2D(R, R_200c, M_200c, redshift):
+    """Battaglia16.py:201-218 = interpolate(LOS_integrate(ne_3D)) with the decorator defaults (20, linspace)"""
+    return interpolate(lambda RR, *a: los_integrate(b16_ne_3D, RR, *a), R, R_200c, M_200c, redshift, n_samples=20)

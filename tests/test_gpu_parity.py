@@ -588,3 +588,28 @@ def test_disc_query_cuda_vs_glibc_at_scale():
                           sum_h.ctypes.data)
     assert np.array_equal(cnt_d, cnt_h) and np.array_equal(sum_d, sum_h)
     assert cnt_d.sum() > 3e7
+
+
+@pytest.mark.parametrize("kind,nside,n,m_min", [("nfw_rho_2D", 2048, 30, 1e14), ("nfw_rho_2D_interp", 2048, 80, 1e14),
+                                               ("nfw_rho_2D_interp", 8192, 40, 3e14),
+                                               ("b16_rho_gas_2D", 2048, 30, 1e14), ("b16_ne_2D", 2048, 80, 1e14),
+                                               ("b16_ne_2D", 8192, 40, 3e14)])
+def test_los_projected_templates_on_device(kind, nside, n, m_min):
+    """the remaining @LOS_integrate / @interpolate built-ins (NFW.rho_2D, rho_2D_interp; Battaglia16
+    rho_gas_2D, ne_2D): device QUADPACK for every 3-D profile, log-spaced tables included"""
+    import warnings
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    from astropaint_b200.profiles import NFW, Battaglia16
+    _, o, _ = _oracle()
+    t, ot, path = {"nfw_rho_2D": (NFW.rho_2D, o.nfw_rho_2D, "device_profile"),
+                   "nfw_rho_2D_interp": (NFW.rho_2D_interp, o.nfw_rho_2D_interp, "device_table"),
+                   "b16_rho_gas_2D": (Battaglia16.rho_gas_2D, o.b16_rho_gas_2D, "device_profile"),
+                   "b16_ne_2D": (Battaglia16.ne_2D, o.b16_ne_2D, "device_table")}[kind]
+    cat = ap.Catalog(synthetic.websky_like(n, seed=13, m_min=m_min))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, want, p = _spray_both(cat, nside, 5, t, ot)
+    assert p.last_spray["path"] == path
+    assert np.abs(want).max() > 0
+    map_close(got, want, 1e-6)

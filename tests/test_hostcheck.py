@@ -199,3 +199,32 @@ def test_vec2pix_near_azimuth_equals_vec2pix(hc, nside):
         hc.hc_vec2pix_near(nside, n, _p(x), _p(y), _p(z), lon, _p(out))
         bad += int((out != hp.vec2pix(x, y, z)).sum())
     assert bad == 0
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_los_kinds_equal_scipy(hc, kind):
+    """every 3-D profile the device projects: value and neval against scipy.integrate.quad"""
+    from scipy import integrate
+    import warnings
+    hc.hc_los.argtypes = [C.c_int, d, d, d, d, C.POINTER(d), C.POINTER(C.c_int)]
+    f3 = [oprof.b16_tau_3D, oprof.b16_ne_3D, oprof.b16_rho_gas_3D, oprof.nfw_rho_3D][kind]
+    rng = np.random.default_rng(kind)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(40):
+            M = 10 ** rng.uniform(13, 15.5)
+            z = rng.uniform(0, 4)
+            R200 = float(ref.M_200c_to_R_200c(M, z))
+            if kind == 3:
+                c200 = float(ref.M_200c_to_c_200c(M, z))
+                args = (float(ref.M_200c_to_rho_s(M, z, R200, c200)), R200 / c200)
+            else:
+                args = (R200, M, z)
+            for R in R200 * rng.uniform(0.001, 5, 6):
+                f = lambda r: f3(r, *args) * 2. * r / np.sqrt(r ** 2 - R ** 2)  # noqa: E731
+                v, e, info = integrate.quad(f, R, np.inf, epsabs=0., epsrel=1e-2, full_output=1)[:3]
+                res, ne = d(), C.c_int()
+                a3 = list(args) + [0.0] * (3 - len(args))
+                assert hc.hc_los(kind, R, *a3, C.byref(res), C.byref(ne)) == 0
+                assert ne.value == info["neval"]
+                assert abs(res.value - v) <= 1e-10 * abs(v)
