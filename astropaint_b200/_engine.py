@@ -115,6 +115,22 @@ class DeviceHalos:
         s.d_theta, s.d_phi, s.d_D_a = p("theta"), p("phi"), p("D_a")
         return s
 
+    def gathered(self, perm):
+        """The same halos in the order `perm` (int64 device tensor): one gather per resident column."""
+        out = DeviceHalos.__new__(DeviceHalos)
+        out.device, out._data, out._pinned, out._rows = self.device, self._data, {}, None
+        out._n_all, out.n = self.n, self.n
+        out.cols = {k: v.index_select(0, perm) for k, v in self.cols.items()}
+        return out
+
+    def view(self, lo, hi):
+        """Halos [lo, hi) of this object without copying (column views)."""
+        out = DeviceHalos.__new__(DeviceHalos)
+        out.device, out._data, out._pinned, out._rows = self.device, self._data, {}, None
+        out._n_all, out.n = hi - lo, hi - lo
+        out.cols = {k: v[lo:hi] for k, v in self.cols.items()}
+        return out
+
     def subset(self, idx):
         """New DeviceHalos holding rows `idx` (positions within this object)."""
         sub = DeviceHalos.__new__(DeviceHalos)
@@ -127,6 +143,24 @@ class DeviceHalos:
         ti = torch.as_tensor(np.asarray(idx), device=self.device, dtype=torch.int64)
         sub.cols = {k: v.index_select(0, ti) for k, v in self.cols.items()}
         return sub
+
+
+def ring_start_pixel(nside, z):
+    """First pixel of the first ring a disc whose upper edge is at z = cos(theta - radius) can touch,
+    less one ring of safety margin (healpix ring_above + 1, get_ring_info_small startpix)."""
+    az = abs(z)
+    if az <= 2.0 / 3.0:
+        ring = int(nside * (2.0 - 1.5 * z))
+    else:
+        ir = int(nside * np.sqrt(3.0 * (1.0 - az)))
+        ring = ir if z > 0 else 4 * nside - ir - 1
+    ring = max(ring + 1 - 1, 1)  # ring_above + 1 is the first candidate ring; keep one ring of margin
+    if ring < nside:
+        return 2 * ring * (ring - 1)
+    if ring < 3 * nside:
+        return 2 * nside * (nside - 1) + (ring - nside) * 4 * nside
+    nr = 4 * nside - ring
+    return 12 * nside * nside - 2 * nr * (nr + 1)
 
 
 # ---------------------------------------------------------------------------------------------

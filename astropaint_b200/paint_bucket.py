@@ -259,6 +259,7 @@ class Canvas:
         self.template_name = None
         self.stack = None
         self._host_buf = None
+        self._prefetch = None
         self.clean()
         self.instantiate_discs()
 
@@ -299,15 +300,31 @@ class Canvas:
             import torch
             if self._host_buf is None:  # page-locked, reused across clean(): one DMA per read-back
                 self._host_buf = torch.empty(self.npix, dtype=self._dmap.dtype, pin_memory=True)
-            self._host_buf.copy_(self._dmap)
+                self._prefetch = None
+            if self._prefetch is not None:
+                # the spray already streamed the finished ring bands to the host on a copy stream
+                # (Painter._paint_device_table); fetch whatever is left
+                stream, upto = self._prefetch
+                stream.synchronize()
+                if upto < self.npix:
+                    self._host_buf[upto:].copy_(self._dmap[upto:])
+                self._prefetch = None
+            else:
+                self._host_buf.copy_(self._dmap)
             self._pixels = self._host_buf.numpy()
             self._dmap_spare = self._dmap
             self._dmap = None
         self._state = "host"
         return self._pixels
 
+    def _cancel_prefetch(self):
+        if self._prefetch is not None:
+            self._prefetch[0].synchronize()
+            self._prefetch = None
+
     @pixels.setter
     def pixels(self, val):
+        self._cancel_prefetch()
         self._pixels = val
         self._dmap = None
         self._state = "host"
@@ -325,6 +342,8 @@ class Canvas:
         import torch
         dev = eng.require_cuda()
         tdt = torch.float32 if self.accumulate == "fp32" else torch.float64
+        if self._state != "device":
+            self._cancel_prefetch()
         if self._state == "zero":
             if self._dmap_spare is not None and self._dmap_spare.device == dev:
                 self._dmap = self._dmap_spare.zero_()
@@ -375,6 +394,7 @@ class Canvas:
 
     def clean(self):
         """Set all pixels to zero (paint_bucket.py:1307-1323)."""
+        self._cancel_prefetch()
         self._pixels = None
         # keep the HBM allocation for the next spray instead of returning 8*npix bytes to the allocator
         self._dmap_spare = getattr(self, "_dmap", None) if getattr(self, "_dmap", None) is not None \
@@ -628,6 +648,7 @@ class Painter:
         arguments to 500-point grids as the reference does.
         """
         _say("Painting the canvas...")
+        canvas._cancel_prefetch()
         canvas.template_name = self.template.__name__
         assert distance_units.lower() in ["mpc", "mpcs", "megaparsecs", "megaparsec"], \
             "For now the distance unit has to be megaparsecs."
@@ -681,8 +702,13 @@ class Painter:
             eng.paint_profile(halos, nside, info["id"], params, d_map, d_count)
             path = "device_profile"
         elif getattr(tmpl, "_ap_device_table", None) is not None and self.R_arg_indx == 0:
-            self._paint_device_table(tmpl._ap_device_table, halos, nside, col, template_kwargs, d_map, d_count)
-            path = "device_table"
+            prefetch = None
+            if (canvas._host_buf is not None and canvas._state == "device" and d_map is canvas._dmap
+                    and halos.n >= self.PREFETCH_MIN_HALOS and canvas._host_buf.dtype == d_map.dtype):
+                prefetch = canvas  # the host copy of the map has been asked for before: stream it back
+            self._paint_device_table(tmpl._ap_device_table, halos, nside, col, template_kwargs, d_map, d_count,
+                                     prefetch)
+            path = "device_table" if prefetch is None else "device_table+prefetch"
         elif self._interp_info() is not None:
             self._paint_python_table(self._interp_info(), halos, nside, rows, R_mode, host_cols, d_map, d_count)
             path = "python_table"
@@ -701,17 +727,25 @@ class Painter:
             return None
         return info
 
-    def _paint_device_table(self, info, halos, nside, col, template_kwargs, d_map, d_count):
-        """Battaglia16.tau_2D_interp / kSZ_T entirely on device (see csrc/kernels.cu, K4)."""
+    #: catalogs at least this large stream finished ring bands of the map to the host while the remaining
+    #: halos are still being integrated (only once the host copy has been read before)
+    PREFETCH_MIN_HALOS = 200000
+    PREFETCH_CHUNKS = 8
+
+    def _paint_device_table(self, info, halos, nside, col, template_kwargs, d_map, d_count, prefetch=None):
+        """@interpolate(@LOS_integrate(profile_3D)) entirely on device (csrc/kernels.cu, K1/K4/K3).
+
+        With `prefetch` (the Canvas whose pinned host buffer should receive the map) the halos are
+        ordered by the first HEALPix ring their disc can touch and processed in PREFETCH_CHUNKS chunks:
+        once chunk k is painted no later chunk writes above the first ring of chunk k+1, so that band is
+        copied device->host on a second stream while chunk k+1 is still in its QUADPACK phase.
+        """
         import torch
         ns = info["n_samples"]
-        n_pix, _, rmin, rmax = eng.disc_count(halos, nside, want_range=True)
-        nodes, n_nodes = eng.table_nodes(halos, n_pix, rmin, rmax, ns, info["sampling_method"])
+        uniform = info["sampling_method"] == "linspace"
         assert info["kind"] in eng.LOS_KINDS
         args = [col(a) for a in info["args"]]
         args = [t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in args]
-        values = eng.los_nodes(info["kind"], halos, args, nodes, n_nodes)
-        coef = eng.spline_build(nodes, values, n_nodes, uniform=(info["sampling_method"] == "linspace"))
         scale = None
         if info["scale"] is not None:
             sc = info["scale"]
@@ -720,9 +754,42 @@ class Painter:
             scale = sc["fn"](cols, kw)
             scale = scale if scale.numel() == halos.n else scale.expand(halos.n)
             scale = scale.contiguous()
-        eng.paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count,
-                        uniform=(info["sampling_method"] == "linspace"))
-        eng.paint_los_small(info["kind"], halos, nside, args, scale, n_pix, ns, d_map, d_count)
+
+        def run(h, a, sc_):
+            n_pix, _, rmin, rmax = eng.disc_count(h, nside, want_range=True)
+            nodes, n_nodes = eng.table_nodes(h, n_pix, rmin, rmax, ns, info["sampling_method"])
+            values = eng.los_nodes(info["kind"], h, a, nodes, n_nodes)
+            coef = eng.spline_build(nodes, values, n_nodes, uniform=uniform)
+            eng.paint_table(h, nside, nodes, coef, n_nodes, sc_, d_map, d_count, uniform=uniform)
+            eng.paint_los_small(info["kind"], h, nside, a, sc_, n_pix, ns, d_map, d_count)
+
+        if prefetch is None:
+            run(halos, args, scale)
+            return
+        canvas, K, n = prefetch, self.PREFETCH_CHUNKS, halos.n
+        zmax = torch.cos(torch.clamp(halos.col("theta") - halos.cols["__radius__"], min=0.0))
+        perm = torch.argsort(zmax, descending=True)
+        hs = halos.gathered(perm)
+        args = [a.index_select(0, perm) for a in args]
+        scale = scale.index_select(0, perm) if scale is not None else None
+        bounds = [(k * n) // K for k in range(K + 1)]
+        z_first = zmax.index_select(0, perm[torch.as_tensor(bounds[:-1], device=perm.device)]).cpu().numpy()
+        p_first = [eng.ring_start_pixel(nside, float(z)) for z in z_first] + [canvas.npix]
+        copy_stream = torch.cuda.Stream(device=d_map.device)
+        done = 0
+        for k in range(K):
+            lo, hi = bounds[k], bounds[k + 1]
+            if hi > lo:
+                run(hs.view(lo, hi), [a[lo:hi] for a in args], scale[lo:hi] if scale is not None else None)
+            upto = max(done, min(p_first[k + 1], canvas.npix))
+            if upto > done:
+                ev = torch.cuda.Event()
+                ev.record()
+                copy_stream.wait_event(ev)
+                with torch.cuda.stream(copy_stream):
+                    canvas._host_buf[done:upto].copy_(d_map[done:upto], non_blocking=True)
+                done = upto
+        canvas._prefetch = (copy_stream, done)
 
     def _paint_python_table(self, info, halos, nside, rows, R_mode, host_cols, d_map, d_count):
         """A Python template wrapped in @interpolate: nodes, spline and painting on device; the

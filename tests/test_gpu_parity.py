@@ -613,3 +613,32 @@ def test_los_projected_templates_on_device(kind, nside, n, m_min):
     assert p.last_spray["path"] == path
     assert np.abs(want).max() > 0
     map_close(got, want, 1e-6)
+
+
+def test_prefetch_pipeline_matches_plain_spray(monkeypatch):
+    """ring-band ordered chunks with device->host streaming of finished bands == the plain path"""
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    from astropaint_b200.profiles import Battaglia16
+    cat = ap.Catalog(synthetic.websky_like(4000, seed=17, m_min=5e13))
+    canvas = ap.Canvas(cat, 2048, R_times=5)
+    p = ap.Painter(Battaglia16.kSZ_T)
+    p.spray(canvas)
+    assert p.last_spray["path"] == "device_table"
+    plain = canvas.pixels.copy()              # first read allocates the pinned host buffer
+    n_plain = int(p.last_spray["d_count"].item())
+    monkeypatch.setattr(ap.Painter, "PREFETCH_MIN_HALOS", 0)
+    canvas.clean()
+    p.spray(canvas)
+    assert p.last_spray["path"] == "device_table+prefetch"
+    assert int(p.last_spray["d_count"].item()) == n_plain
+    got = canvas.pixels
+    map_close(got, plain, 1e-12)
+    # additive second spray on the (host-authoritative) canvas, again through the prefetch path
+    p.spray(canvas)
+    map_close(canvas.pixels, 2 * plain, 1e-12)
+    # a spray that is never read back must not leave a dangling copy
+    canvas.clean()
+    p.spray(canvas)
+    canvas.clean()
+    assert (canvas.pixels == 0).all()
