@@ -145,22 +145,100 @@ class DeviceHalos:
         return sub
 
 
-def ring_start_pixel(nside, z):
-    """First pixel of the first ring a disc whose upper edge is at z = cos(theta - radius) can touch,
-    less one ring of safety margin (healpix ring_above + 1, get_ring_info_small startpix)."""
-    az = abs(z)
-    if az <= 2.0 / 3.0:
-        ring = int(nside * (2.0 - 1.5 * z))
-    else:
-        ir = int(nside * np.sqrt(3.0 * (1.0 - az)))
-        ring = ir if z > 0 else 4 * nside - ir - 1
-    ring = max(ring + 1 - 1, 1)  # ring_above + 1 is the first candidate ring; keep one ring of margin
+def _ring_start(nside, ring):
+    """first pixel of `ring` (healpix get_ring_info_small)"""
     if ring < nside:
         return 2 * ring * (ring - 1)
     if ring < 3 * nside:
         return 2 * nside * (nside - 1) + (ring - nside) * 4 * nside
     nr = 4 * nside - ring
     return 12 * nside * nside - 2 * nr * (nr + 1)
+
+
+def band_layout(nside, n_bands):
+    """Equal-area ring bands of the map: ring_bounds[k] is the first ring of band k (z = 1 - 2k/K),
+    pix_bounds[k] its first pixel; pix_bounds[K] = npix."""
+    rings, pix = [1], [0]
+    for k in range(1, n_bands):
+        z = 1.0 - 2.0 * k / n_bands
+        az = abs(z)
+        if az <= 2.0 / 3.0:
+            r = int(nside * (2.0 - 1.5 * z))
+        else:
+            ir = int(nside * np.sqrt(3.0 * (1.0 - az)))
+            r = ir if z > 0 else 4 * nside - ir - 1
+        r = min(max(r, rings[-1]), 4 * nside - 1)
+        rings.append(r)
+        pix.append(_ring_start(nside, r))
+    rings.append(4 * nside)
+    pix.append(12 * nside * nside)
+    return rings, pix
+
+
+def top_ring(halos, nside):
+    """Per halo (device, int64): a ring at or above the first ring its disc can touch — healpix
+    ring_above(cos(theta - radius)), i.e. one ring of margin against the kernels' own irmin."""
+    z = torch.cos(torch.clamp(halos.col("theta") - halos.cols["__radius__"], min=0.0))
+    az = z.abs()
+    r_eq = torch.floor(nside * (2.0 - 1.5 * z))
+    ir = torch.floor(nside * torch.sqrt(torch.clamp(3.0 * (1.0 - az), min=0.0)))
+    r_cap = torch.where(z > 0, ir, 4 * nside - ir - 1)
+    return torch.clamp(torch.where(az <= 2.0 / 3.0, r_eq, r_cap), min=1).to(torch.int64)
+
+
+def table_spray(halos, nside, kind, args, scale, n_samples, method, d_map, d_count=None, n_bands=1, band_done=None,
+                timers=None):
+    """@interpolate(@LOS_integrate(profile_3D)) for all halos: K1 stats -> nodes -> QUADPACK -> spline ->
+    K3 paint -> bypass.  With n_bands > 1 the halos are grouped by the equal-area ring band holding the
+    first ring their disc can touch and processed band by band; after band k no later halo writes above
+    band k+1, so `band_done(k, pix_lo, pix_hi)` may ship those pixels (device->host copy, all-reduce)
+    on another stream while band k+1 is still in its QUADPACK phase."""
+    uniform = method == "linspace"
+
+    def tick(name):
+        if timers is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timers.append((name, ev))
+
+    def run(h, a, sc):
+        tick("disc_count")
+        n_pix, _, rmin, rmax = disc_count(h, nside, want_range=True)
+        tick("table_nodes")
+        nodes, n_nodes = table_nodes(h, n_pix, rmin, rmax, n_samples, method)
+        tick("los_nodes")
+        values = los_nodes(kind, h, a, nodes, n_nodes)
+        tick("spline_build")
+        coef = spline_build(nodes, values, n_nodes, uniform=uniform)
+        tick("paint_table")
+        paint_table(h, nside, nodes, coef, n_nodes, sc, d_map, d_count, uniform=uniform)
+        tick("paint_los_small")
+        paint_los_small(kind, h, nside, a, sc, n_pix, n_samples, d_map, d_count)
+        tick("end")
+
+    if n_bands <= 1:
+        run(halos, args, scale)
+        if band_done is not None:
+            band_done(0, 0, d_map.numel())
+        return
+    tick("band_sort")
+    rings, pix = band_layout(nside, n_bands)
+    tr = top_ring(halos, nside)
+    band = torch.bucketize(tr, torch.as_tensor(rings[1:-1], device=tr.device, dtype=torch.int64), right=True)
+    order = torch.argsort(band, stable=True)
+    counts = torch.bincount(band, minlength=n_bands).cpu().numpy()
+    hs = halos.gathered(order)
+    args = [a.index_select(0, order) for a in args]
+    scale = scale.index_select(0, order) if scale is not None else None
+    tick("end")
+    lo = 0
+    for k in range(n_bands):
+        hi = lo + int(counts[k])
+        if hi > lo:
+            run(hs.view(lo, hi), [a[lo:hi] for a in args], scale[lo:hi] if scale is not None else None)
+        if band_done is not None:
+            band_done(k, pix[k], pix[k + 1])
+        lo = hi
 
 
 # ---------------------------------------------------------------------------------------------

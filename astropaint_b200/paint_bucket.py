@@ -672,7 +672,7 @@ class Painter:
         _say("Your artwork is finished. Check it out with Canvas.show_map()")
 
     # ------------------------ one rank's share ------------------------
-    def _paint_rows(self, canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned=None):
+    def _paint_rows(self, canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned=None, band_done=None):
         """Paint catalog rows `rows` (None = all) into the device map d_map; returns stats dict."""
         import torch
         dev = d_map.device
@@ -706,15 +706,19 @@ class Painter:
             if (canvas._host_buf is not None and canvas._state == "device" and d_map is canvas._dmap
                     and halos.n >= self.PREFETCH_MIN_HALOS and canvas._host_buf.dtype == d_map.dtype):
                 prefetch = canvas  # the host copy of the map has been asked for before: stream it back
+            banded = band_done if halos.n >= self.PREFETCH_MIN_HALOS else None
             self._paint_device_table(tmpl._ap_device_table, halos, nside, col, template_kwargs, d_map, d_count,
-                                     prefetch)
-            path = "device_table" if prefetch is None else "device_table+prefetch"
+                                     prefetch, banded)
+            path = "device_table" + ("+prefetch" if prefetch is not None else "") + ("+bands" if banded else "")
+            band_done = None if banded else band_done
         elif self._interp_info() is not None:
             self._paint_python_table(self._interp_info(), halos, nside, rows, R_mode, host_cols, d_map, d_count)
             path = "python_table"
         else:
             hc = host_cols if rows is None else {k: v[rows] for k, v in host_cols.items()}
             eng.spray_flat(halos, nside, tmpl, R_mode, hc, d_map, d_count)
+        if band_done is not None:      # paths that do not work band by band: the whole map at once
+            band_done(0, 0, d_map.numel())
         return {"path": path, "n_halos": halos.n, "d_count": d_count}
 
     def _interp_info(self):
@@ -732,17 +736,15 @@ class Painter:
     PREFETCH_MIN_HALOS = 200000
     PREFETCH_CHUNKS = 8
 
-    def _paint_device_table(self, info, halos, nside, col, template_kwargs, d_map, d_count, prefetch=None):
-        """@interpolate(@LOS_integrate(profile_3D)) entirely on device (csrc/kernels.cu, K1/K4/K3).
+    def _paint_device_table(self, info, halos, nside, col, template_kwargs, d_map, d_count, prefetch=None,
+                            band_done=None):
+        """@interpolate(@LOS_integrate(profile_3D)) entirely on device (eng.table_spray: K1/K4/K3).
 
-        With `prefetch` (the Canvas whose pinned host buffer should receive the map) the halos are
-        ordered by the first HEALPix ring their disc can touch and processed in PREFETCH_CHUNKS chunks:
-        once chunk k is painted no later chunk writes above the first ring of chunk k+1, so that band is
-        copied device->host on a second stream while chunk k+1 is still in its QUADPACK phase.
+        With `prefetch` (the Canvas whose pinned host buffer should receive the map) or `band_done` (the
+        multi-GPU reduce) the halos are processed ring band by ring band (eng.table_spray) and every
+        finished band is shipped on a second stream while the next band is in its QUADPACK phase.
         """
         import torch
-        ns = info["n_samples"]
-        uniform = info["sampling_method"] == "linspace"
         assert info["kind"] in eng.LOS_KINDS
         args = [col(a) for a in info["args"]]
         args = [t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in args]
@@ -754,42 +756,24 @@ class Painter:
             scale = sc["fn"](cols, kw)
             scale = scale if scale.numel() == halos.n else scale.expand(halos.n)
             scale = scale.contiguous()
+        n_bands = 1
+        if prefetch is not None:
+            canvas = prefetch
+            copy_stream = torch.cuda.Stream(device=d_map.device)
 
-        def run(h, a, sc_):
-            n_pix, _, rmin, rmax = eng.disc_count(h, nside, want_range=True)
-            nodes, n_nodes = eng.table_nodes(h, n_pix, rmin, rmax, ns, info["sampling_method"])
-            values = eng.los_nodes(info["kind"], h, a, nodes, n_nodes)
-            coef = eng.spline_build(nodes, values, n_nodes, uniform=uniform)
-            eng.paint_table(h, nside, nodes, coef, n_nodes, sc_, d_map, d_count, uniform=uniform)
-            eng.paint_los_small(info["kind"], h, nside, a, sc_, n_pix, ns, d_map, d_count)
-
-        if prefetch is None:
-            run(halos, args, scale)
-            return
-        canvas, K, n = prefetch, self.PREFETCH_CHUNKS, halos.n
-        zmax = torch.cos(torch.clamp(halos.col("theta") - halos.cols["__radius__"], min=0.0))
-        perm = torch.argsort(zmax, descending=True)
-        hs = halos.gathered(perm)
-        args = [a.index_select(0, perm) for a in args]
-        scale = scale.index_select(0, perm) if scale is not None else None
-        bounds = [(k * n) // K for k in range(K + 1)]
-        z_first = zmax.index_select(0, perm[torch.as_tensor(bounds[:-1], device=perm.device)]).cpu().numpy()
-        p_first = [eng.ring_start_pixel(nside, float(z)) for z in z_first] + [canvas.npix]
-        copy_stream = torch.cuda.Stream(device=d_map.device)
-        done = 0
-        for k in range(K):
-            lo, hi = bounds[k], bounds[k + 1]
-            if hi > lo:
-                run(hs.view(lo, hi), [a[lo:hi] for a in args], scale[lo:hi] if scale is not None else None)
-            upto = max(done, min(p_first[k + 1], canvas.npix))
-            if upto > done:
+            def band_done(k, p_lo, p_hi):  # noqa: F811
                 ev = torch.cuda.Event()
                 ev.record()
                 copy_stream.wait_event(ev)
                 with torch.cuda.stream(copy_stream):
-                    canvas._host_buf[done:upto].copy_(d_map[done:upto], non_blocking=True)
-                done = upto
-        canvas._prefetch = (copy_stream, done)
+                    canvas._host_buf[p_lo:p_hi].copy_(d_map[p_lo:p_hi], non_blocking=True)
+            n_bands = self.PREFETCH_CHUNKS
+        elif band_done is not None:
+            n_bands = self.PREFETCH_CHUNKS
+        eng.table_spray(halos, nside, info["kind"], args, scale, info["n_samples"], info["sampling_method"], d_map,
+                        d_count, n_bands=n_bands, band_done=band_done)
+        if prefetch is not None:
+            prefetch._prefetch = (copy_stream, prefetch.npix)
 
     def _paint_python_table(self, info, halos, nside, rows, R_mode, host_cols, d_map, d_count):
         """A Python template wrapped in @interpolate: nodes, spline and painting on device; the
