@@ -1,12 +1,14 @@
 // astropaint_b200 — sm_100a kernels and the C ABI (include/astropaint_b200.h).
 //
-// Kernel map (DESIGN.md has the roofline of each):
-//   disc_count_kernel    K1  per-halo ring walk: pixel count, ring count, R range
-//   disc_pixels_kernel   K1b flat (halo, pixel) list (+R, +R_vec) for parity and Python templates
-//   paint_kernel<P>      K3  fused disc query -> pixel geometry -> template -> fp64 RED scatter
-//   table_nodes / b16_tau_nodes / spline_build   K4  @interpolate tables on device
-//   paint_b16_small      the len(R) < n_samples bypass of @interpolate
-//   cutout_kernel / stack_kernel   K5  CartesianProj cutouts and their stack
+// Kernel map (DESIGN.md section 3 has the roofline of each):
+//   disc_radius_kernel            R_times * arcmin2rad(R_ang_200c) with numpy's rounding
+//   paint_kernel<P, MapT>         K3  fused disc query -> pixel geometry -> template -> RED scatter
+//     P = built-in profile id | P_TABLE (per-halo spline) | P_STATS (K1: pixel count + R range)
+//   disc_pixels_kernel            K1b flat (halo, pixel) list (+R, +R_vec): parity, Python templates
+//   scatter_add_kernel            np.add.at for the flat list
+//   table_nodes_kernel, los_nodes_kernel<KIND>, spline_build(_uniform)_kernel   K4 @interpolate tables
+//   paint_los_small_kernel<KIND>  the len(R) < n_samples bypass of @interpolate
+//   cutout_kernel<STACK>          K5  CartesianProj cutouts and their stack
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -29,12 +31,6 @@ static int fail(const std::string& m) {
   g_err = m;
   return 1;
 }
-#define AP_CUDA(call)                                                                   \
-  do {                                                                                  \
-    cudaError_t e_ = (call);                                                            \
-    if (e_ != cudaSuccess)                                                              \
-      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
-  } while (0)
 #define AP_LAUNCH_CHECK()                                                               \
   do {                                                                                  \
     cudaError_t e_ = cudaGetLastError();                                                \
