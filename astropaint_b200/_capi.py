@@ -39,6 +39,10 @@ SIGNATURES = {
                                      c_ptr, c_ptr, c_ptr]),
     "ap_paint_los_small_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
                                          c_ptr, c_ptr, c_ptr]),
+    "ap_paint_los_items": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
+                                     c_ptr, c_ptr]),
+    "ap_paint_los_items_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                                         c_ptr, c_ptr, c_ptr]),
     "ap_b16_tau_eval": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spline_build": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spline_build_uniform": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -322,10 +322,23 @@ def los_nodes(kind, halos, args, nodes, n_nodes):
 
 
 def paint_los_small(kind, halos, nside, args, scale, n_pix, n_samples, d_map, d_count=None):
+    """The `len(R) < n_samples` bypass: halos with 1 .. n_samples-1 pixels get the projected profile at every
+    pixel.  The (halo, pixel ordinal) work items are compacted first (one small device->host read of their
+    number) so that no warp is launched for halos that do not need it and every lane integrates."""
+    small = (n_pix > 0) & (n_pix < n_samples)
+    idx = torch.nonzero(small).squeeze(1)
+    if idx.numel() == 0:
+        return
+    cnt = n_pix.index_select(0, idx)
+    item_halo = torch.repeat_interleave(idx, cnt)
+    start = torch.cumsum(cnt, 0) - cnt
+    item_ord = (torch.arange(item_halo.numel(), device=item_halo.device) - torch.repeat_interleave(start, cnt)).to(torch.int32)
     s = halos.struct()
     a = list(args) + [None] * (3 - len(args))
-    check(_fn("ap_paint_los_small", d_map)(LOS_KINDS[kind], nside, C.byref(s), ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(scale),
-                                           ptr(n_pix), n_samples, ptr(d_map), ptr(d_count), stream_ptr()))
+    check(_fn("ap_paint_los_items", d_map)(LOS_KINDS[kind], nside, C.byref(s), ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(scale),
+                                           item_halo.numel(), ptr(item_halo), ptr(item_ord), ptr(d_map), stream_ptr()))
+    if d_count is not None:
+        d_count += item_halo.numel()
 
 
 def b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes):

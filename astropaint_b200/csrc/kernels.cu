@@ -893,6 +893,83 @@ __global__ void __launch_bounds__(128) paint_los_small_kernel(Hpx hpx, HalosDev 
   if (n_painted && lane == 0) atomicAdd(n_painted, (unsigned long long)np);
 }
 
+// Compacted bypass: one thread per (halo, pixel ordinal) work item, every lane of a warp busy with its
+// own quadrature (the warp-per-halo kernel above leaves 18-31 lanes idle and still launches a warp for
+// every halo that does not need it).
+template <int KIND, class MapT>
+__global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev H, const double* p0, const double* p1,
+                                                              const double* p2, const double* scale, int64_t n_items,
+                                                              const int64_t* item_halo, const int32_t* item_ord,
+                                                              MapT* map) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_items) return;
+  const int64_t h = item_halo[t];
+  const int32_t want = item_ord[t];
+  DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+  HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
+  int32_t run = 0;
+  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+    RingSpan s = ring_span(hpx, d, iz);
+    if (s.len <= 0) continue;
+    if (want < run + s.len) {
+      RingGeom g = ring_geom(hpx, iz, s, c);
+      int32_t js = want - run;
+      int32_t ip = s.ip_lo + js;
+      double R = c.D_a * pixel_sep(g, js);
+      double ctx[kCtx];
+      los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+      double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
+      atomicAdd(&map[s.startpix + (ip < 0 ? ip + s.nr : ip)], (MapT)val);
+      return;
+    }
+    run += s.len;
+  }
+}
+
+template <int KIND>
+static void launch_los_items(bool f32, unsigned blocks, cudaStream_t st, Hpx hpx, HalosDev H, const double* p0,
+                             const double* p1, const double* p2, const double* scale, int64_t n_items,
+                             const int64_t* item_halo, const int32_t* item_ord, void* map) {
+  if (f32)
+    paint_los_items_kernel<KIND, float><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, (float*)map);
+  else
+    paint_los_items_kernel<KIND, double><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, (double*)map);
+}
+
+static int paint_los_items_impl(int kind, int64_t nside, const ap_halos* halos, const double* p0, const double* p1,
+                                const double* p2, const double* scale, int64_t n_items, const int64_t* item_halo,
+                                const int32_t* item_ord, void* d_map, bool f32, void* stream) {
+  if (check_nside(nside)) return 1;
+  if (check_halos(halos, true)) return 1;
+  if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
+  if (n_items < 0) return fail("n_items < 0");
+  if (n_items == 0 || halos->n == 0) return 0;
+  if (!p0 || !p1 || (kind != LOS_NFW_RHO && !p2) || !item_halo || !item_ord || !d_map)
+    return fail("paint_los_items: NULL pointer");
+  unsigned blocks = (unsigned)((n_items + 127) / 128);
+  Hpx hpx = make_hpx(nside);
+  HalosDev H = to_dev(halos);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case LOS_B16_TAU: launch_los_items<LOS_B16_TAU>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
+    case LOS_B16_NE: launch_los_items<LOS_B16_NE>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
+    case LOS_B16_RHO_GAS: launch_los_items<LOS_B16_RHO_GAS>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
+    case LOS_NFW_RHO: launch_los_items<LOS_NFW_RHO>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
+  }
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ap_paint_los_items(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
+                                  const double* d_p2, const double* d_scale, int64_t n_items, const int64_t* d_item_halo,
+                                  const int32_t* d_item_ord, double* d_map, void* stream) {
+  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, n_items, d_item_halo, d_item_ord, d_map, false, stream);
+}
+extern "C" int ap_paint_los_items_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0,
+                                      const double* d_p1, const double* d_p2, const double* d_scale, int64_t n_items,
+                                      const int64_t* d_item_halo, const int32_t* d_item_ord, float* d_map, void* stream) {
+  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, n_items, d_item_halo, d_item_ord, d_map, true, stream);
+}
+
 template <int KIND>
 static void launch_los_small(bool f32, unsigned blocks, int threads, cudaStream_t st, Hpx hpx, HalosDev H, const double* p0,
                              const double* p1, const double* p2, const double* scale, const int64_t* n_pix, int32_t ns,

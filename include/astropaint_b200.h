@@ -141,6 +141,13 @@ int ap_paint_los_small(int kind, int64_t nside, const ap_halos* halos, const dou
                        const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
                        double* d_map, unsigned long long* d_n_painted, void* stream);
 
+/* The same bypass from a compacted work list: item t paints the d_item_ord[t]-th pixel (ring by ring, 0 <= ord <
+ * n_pix) of halo d_item_halo[t].  Every lane of a warp runs its own quadrature; the
+ * caller builds the list from ap_disc_count's d_n_pix (astropaint_b200/_engine.py::paint_los_small). */
+int ap_paint_los_items(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
+                       const double* d_p2, const double* d_scale, int64_t n_items, const int64_t* d_item_halo,
+                       const int32_t* d_item_ord, double* d_map, void* stream);
+
 /* Canvas.cutouts / stack_cutouts (paint_bucket.py:1601-1743, 1745-1941): healpy
  * CartesianProj(lonra, latra, xsize, ysize).projmap(map, rot=(lon, lat), vec2pix) per halo.
  * d_lon_deg/d_lat_deg[n_sel] are the catalog lon/lat (degrees) of the selected halos.
@@ -165,6 +172,9 @@ int ap_paint_table_f32(int64_t nside, const ap_halos* halos, int32_t n_samples, 
 int ap_paint_los_small_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
                            const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
                            float* d_map, unsigned long long* d_n_painted, void* stream);
+int ap_paint_los_items_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
+                           const double* d_p2, const double* d_scale, int64_t n_items, const int64_t* d_item_halo,
+                           const int32_t* d_item_ord, float* d_map, void* stream);
 int ap_paint_b16_small_f32(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
                            const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
                            int32_t n_samples, float* d_map, unsigned long long* d_n_painted, void* stream);

@@ -170,3 +170,37 @@ def test_shard_rows_is_array_split():
         assert np.array_equal(np.concatenate(parts), np.arange(n))
         want = np.array_split(np.arange(n), w)
         assert all(np.array_equal(a, b) for a, b in zip(parts, want))
+
+
+def test_ring_band_layout_is_safe_for_streaming():
+    """The banded pipeline ships band k once the halos of bands <= k are painted.  That is only correct
+    if no halo assigned to band b touches a pixel below pix_bounds[b]: check it against the oracle's
+    pixel sets (CPU tensors stand in for the device columns)."""
+    import torch
+    from astropaint_b200 import _engine as eng
+    from oracle import healpix_np as H
+
+    class FakeHalos:
+        def __init__(self, theta, radius):
+            self.cols = {"theta": torch.from_numpy(theta), "__radius__": torch.from_numpy(radius)}
+
+        def col(self, k):
+            return self.cols[k]
+
+    rng = np.random.default_rng(0)
+    for nside, K in [(16, 8), (64, 8), (256, 5), (64, 1)]:
+        hp = H.HealpixRing(nside)
+        rings, pix = eng.band_layout(nside, K)
+        assert rings[0] == 1 and pix[0] == 0 and pix[-1] == hp.npix and all(np.diff(pix) >= 0)
+        n = 400
+        theta = np.arccos(rng.uniform(-1, 1, n))
+        theta[:20] = [0.0, np.pi, 1e-9, np.pi - 1e-9] * 5
+        phi = rng.uniform(0, 2 * np.pi, n)
+        radius = rng.choice([1.0, 0.1, 3.0], n) * rng.uniform(0, 4.0 / nside, n) + (rng.uniform(0, 1, n) < 0.02) * 1.0
+        tr = eng.top_ring(FakeHalos(theta, radius), nside).numpy()
+        band = np.searchsorted(np.asarray(rings[1:-1]), tr, side="right")
+        for i in range(n):
+            v = (np.sin(theta[i]) * np.cos(phi[i]), np.sin(theta[i]) * np.sin(phi[i]), np.cos(theta[i]))
+            q = hp.query_disc(v, radius[i])
+            if len(q):
+                assert q.min() >= pix[band[i]], (nside, K, i, q.min(), pix[band[i]], band[i])
