@@ -106,20 +106,20 @@ def run_reference(args):
     if rank != 0:
         return
     cores = min(os.cpu_count() or 1, 64)
-    n = max(args.cpu_halos, 24 * cores)
-    # every step is the same bounded sample (the reference's cost is a per-halo sum, so the rate
-    # does not depend on which halos are sampled)
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(max(cores, n // 8), cores)
+    # a bounded sample of the workload per step: ~100 halos per core (about 4 s of QUADPACK-dominated CPU
+    # work per step); the reference's cost is a per-halo sum, so the rate does not depend on which halos
+    n = max(args.cpu_halos, 100 * cores)
+    for _ in range(args.warmup):
+        cpu_sample(n, cores)
     times, pairs = [], 0
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, args.steps)
     for _ in range(steps):
         pairs, dt = cpu_sample(n, cores)
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = pairs / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"first {n} halos of the workload catalog per step ({pairs} halo-pixels), oracle "
