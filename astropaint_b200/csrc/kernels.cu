@@ -37,6 +37,25 @@ static int fail(const std::string& m) {
     if (e_ != cudaSuccess) return fail(std::string("launch: ") + cudaGetErrorString(e_)); \
   } while (0)
 
+// Optional bounds instrumentation (-DAP_DEBUG_BOUNDS, tools/debug_bounds.sh): compute-sanitizer is not
+// available on the B200 pool, so a debug build counts every out-of-range index instead of making the
+// access; ap_debug_bounds_errors() must read 0 after the GPU test-suite.
+__device__ unsigned long long g_bounds_errors = 0ull;
+#ifdef AP_DEBUG_BOUNDS
+#define AP_BOUNDS_OK(cond) ((cond) ? true : (atomicAdd(&g_bounds_errors, 1ull), false))
+#else
+#define AP_BOUNDS_OK(cond) true
+#endif
+extern "C" long long ap_debug_bounds_errors(void) {
+#ifdef AP_DEBUG_BOUNDS
+  unsigned long long v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_bounds_errors, sizeof(v)) != cudaSuccess) return -2;
+  return (long long)v;
+#else
+  return -1;  // not an instrumented build
+#endif
+}
+
 extern "C" const char* ap_last_error(void) { return g_err.c_str(); }
 extern "C" int ap_version(void) { return 100; }
 
@@ -109,6 +128,7 @@ __global__ void __launch_bounds__(256) disc_pixels_kernel(Hpx hpx, HalosDev H, c
     for (int32_t j = lane; j < s.len; j += 32) {
       int64_t p = span_pixel_sorted(s, j);
       int64_t o = run + j;
+      if (!AP_BOUNDS_OK(p >= 0 && p < hpx.npix && o < pix_off[h + 1])) continue;
       pix[o] = p;
       if (want) {
         int32_t js = span_j_of_ip(s, (int32_t)(p - s.startpix));
@@ -147,7 +167,7 @@ template <class MapT>
 __global__ void scatter_add_kernel(int64_t n, const int64_t* pix, const double* val, MapT* map) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) atomicAdd(&map[pix[i]], (MapT)val[i]);
+  for (; i < n; i += stride) atomicAdd(&map[pix[i]], (MapT)val[i]);  // indices come from ap_disc_pixels
 }
 
 static int scatter_add_impl(int64_t n, const int64_t* d_pix, const double* d_val, void* d_map, bool f32, void* stream) {
@@ -411,6 +431,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       int lo;
       if (k < kPixMapMax) {
         lo = sm.pixmap[k];
+        if (!AP_BOUNDS_OK(k >= sm.pix_off[lo] && k < sm.pix_off[lo + 1])) lo = 0;
       } else if ((k >> 5) < kHintMax) {
         lo = sm.hint[k >> 5];
         while (sm.pix_off[lo + 1] <= k) ++lo;
@@ -451,7 +472,8 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
           double t;
           double2 c01, c23;
           const int sh = hl - stage_lo;
-          if (do_stage && tab.uniform && sh < kStageHalos) {
+          if (do_stage && tab.uniform && sh < kStageHalos &&
+              AP_BOUNDS_OK(sh >= 0 && (sh * (ns - 1) + i) * 4 + 3 < stage_n && i >= 0 && i <= ns - 2)) {
             t = R - (sm.ctx[hl][1] + (double)i * sm.ctx[hl][3]);  // node i of np.linspace to 1 ulp
             const double2* c2 = reinterpret_cast<const double2*>(sm.stage + (sh * (ns - 1) + i) * 4);
             c01 = c2[0];
@@ -476,8 +498,8 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       const bool two = (k + kPaintThreads < total);
       double v0 = eval(k, p0);
       double v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
-      atomicAdd(&map[p0], (MapT)v0);
-      if (two) atomicAdd(&map[p1], (MapT)v1);
+      if (AP_BOUNDS_OK(p0 >= 0 && p0 < hpx.npix)) atomicAdd(&map[p0], (MapT)v0);
+      if (two && AP_BOUNDS_OK(p1 >= 0 && p1 < hpx.npix)) atomicAdd(&map[p1], (MapT)v1);
     }
     __syncthreads();
   }
@@ -919,7 +941,8 @@ __global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev 
       double ctx[kCtx];
       los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
       double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
-      atomicAdd(&map[s.startpix + (ip < 0 ? ip + s.nr : ip)], (MapT)val);
+      if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && s.startpix + (ip < 0 ? ip + s.nr : ip) < hpx.npix))
+        atomicAdd(&map[s.startpix + (ip < 0 ? ip + s.nr : ip)], (MapT)val);
       return;
     }
     run += s.len;
@@ -1100,6 +1123,7 @@ __global__ void __launch_bounds__(kStackThreads) cutout_kernel(Hpx hpx, const do
     double sy = m[3] * vx + m[4] * vy + m[5] * vz;
     double sz = m[6] * vx + m[7] * vy + m[8] * vz;
     int64_t pix = vec2pix_ring_near(hpx, sx, sy, sz, phic[i], cphi[i], sphi[i]);
+    if (!AP_BOUNDS_OK(pix >= 0 && pix < hpx.npix)) continue;
     double v = __ldg(&map[pix]);
     if (STACK)
       acc += wgt[i] * v;

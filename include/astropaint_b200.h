@@ -55,6 +55,9 @@ typedef struct ap_halos {
 
 const char* ap_last_error(void);
 int ap_version(void);
+/* Number of out-of-range indices seen by a -DAP_DEBUG_BOUNDS build (tools/debug_bounds.sh); -1 for a
+ * normal build.                                                                               */
+long long ap_debug_bounds_errors(void);
 
 /* d_radius[i] = R_times * np.deg2rad(d_R_ang_200c[i] / 60): the query_disc radius of
  * Canvas.Disc.gen_pixel_index (paint_bucket.py:1226-1227, lib/transform.py:148-150), rounded exactly

@@ -61,3 +61,13 @@ def map_close(got, want, rtol=1e-6):
     rel = np.abs(g[big] - w[big]) / np.abs(w[big])
     assert rel.max() <= rtol, f"per-pixel relative error {rel.max()} > {rtol}"
     return err
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """With a -DAP_DEBUG_BOUNDS library (tools/debug_bounds.sh) the run fails if any index was out of range."""
+    if os.environ.get("AP_REPORT_BOUNDS"):
+        from astropaint_b200 import _capi
+        n = _capi.lib().ap_debug_bounds_errors()
+        print(f"\n[ap] out-of-range indices counted by the instrumented build: {n}")
+        if n != 0:
+            session.exitstatus = 1
