@@ -228,3 +228,32 @@ def test_los_kinds_equal_scipy(hc, kind):
                 assert hc.hc_los(kind, R, *a3, C.byref(res), C.byref(ne)) == 0
                 assert ne.value == info["neval"]
                 assert abs(res.value - v) <= 1e-10 * abs(v)
+
+
+@pytest.mark.parametrize("nside", [1, 4, 64, 1024])
+def test_disc_edge_cases_bit_exact(hc, nside):
+    """degenerate and adversarial discs: zero / tiny / >= pi radius, centres on the poles, on phi = 0 and
+    pi, on the equator, exactly on pixel centres and on ring boundaries"""
+    hp = H.HealpixRing(nside)
+    buf = np.empty(hp.npix, dtype=np.int64)
+    centres = [(0, 0, 1), (0, 0, -1), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (1, 1e-300, 0), (-1, -1e-300, 0),
+               (1e-9, 0, 1), (0, -1e-9, -1), (3, 4, 0), (1, 1, 1), (-2, 5, -0.001)]
+    pix = np.unique(np.linspace(0, hp.npix - 1, 25).astype(np.int64))
+    x, y, z = hp.pix2vec(pix)                                    # exact pixel centres
+    centres += list(zip(x, y, z))
+    for r in range(1, 4 * nside, max(1, nside // 3)):            # points exactly on ring latitudes
+        zz = hp.ring2z(r)
+        s = np.sqrt(max(0.0, 1 - zz * zz))
+        centres.append((s * np.cos(0.3), s * np.sin(0.3), zz))
+    pixsize = np.sqrt(4 * np.pi / hp.npix)
+    radii = [0.0, 1e-300, 1e-12, 0.5 * pixsize, pixsize, 2.5 * pixsize, 0.1, 1.0, np.pi / 2, np.pi - 1e-12, np.pi,
+             np.nextafter(np.pi, 4), 4.0, 100.0]
+    n_cases = 0
+    for c in centres:
+        for r in radii:
+            want = hp.query_disc(c, r)
+            n = hc.hc_query_disc(nside, float(c[0]), float(c[1]), float(c[2]), float(r), _p(buf), len(buf))
+            assert n == len(want), (nside, c, r, n, len(want))
+            assert np.array_equal(buf[:n], want), (nside, c, r)
+            n_cases += 1
+    assert n_cases > 300
