@@ -642,3 +642,59 @@ def test_prefetch_pipeline_matches_plain_spray(monkeypatch):
     p.spray(canvas)
     canvas.clean()
     assert (canvas.pixels == 0).all()
+
+
+@pytest.mark.parametrize("nside", [4, 64, 1024])
+def test_disc_edge_cases_on_device(nside):
+    """the degenerate / adversarial discs of tests/test_hostcheck.py through the device kernels (K1 count,
+    K1b flat list, and the fused painter via a coverage-count spray)"""
+    import pandas as pd
+    import torch
+    from astropaint_b200 import _engine as eng
+    _, _, ohp = _oracle()
+    hp = ohp.HealpixRing(nside)
+    centres = [(0, 0, 1), (0, 0, -1), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (1e-9, 0, 1), (0, -1e-9, -1),
+               (3, 4, 0), (1, 1, 1), (-2, 5, -0.001)]
+    pix = np.unique(np.linspace(0, hp.npix - 1, 15).astype(np.int64))
+    x, y, z = hp.pix2vec(pix)
+    centres += list(zip(x, y, z))
+    pixsize = np.sqrt(4 * np.pi / hp.npix)
+    # radius pi/2 around an axis puts thousands of pixel centres EXACTLY on the disc boundary; how such an
+    # exact tie falls is decided by the last bit of libm's atan2 (CUDA vs glibc here, and any two libm
+    # builds under the reference) -- DESIGN.md section 5.  It is exercised on the host build only.
+    radii = [0.0, 1e-12, 0.5 * pixsize, pixsize, 2.5 * pixsize, 0.1, 1.0, 1.5, np.pi - 1e-12, 3.2, 4.0]
+    rows = [(c, r) for c in centres for r in radii]
+    c = np.array([row[0] for row in rows], dtype=np.float64)
+    r_ang = np.rad2deg(np.array([row[1] for row in rows])) * 60
+    r_eff = np.deg2rad(r_ang / 60)            # what the device forms (ap_disc_radius, R_times = 1)
+    theta = np.arctan2(np.hypot(c[:, 0], c[:, 1]), c[:, 2])
+    phi = np.arctan2(c[:, 1], c[:, 0]) % (2 * np.pi)
+    df = pd.DataFrame({"x": c[:, 0], "y": c[:, 1], "z": c[:, 2], "theta": theta, "phi": phi,
+                       "D_a": np.ones(len(rows)), "R_ang_200c": r_ang})
+    dev = torch.device("cuda", 0)
+    halos = eng.DeviceHalos(df, 1, dev)
+    n_pix, _, rmin, rmax = eng.disc_count(halos, nside, want_range=True)
+    off, pixd, R, _ = eng.disc_pixels(halos, nside, n_pix, want_R=True)
+    off, pixd, R = off.cpu().numpy(), pixd.cpu().numpy(), R.cpu().numpy()
+    rmin, rmax = rmin.cpu().numpy(), rmax.cpu().numpy()
+    cover = np.zeros(hp.npix)
+    for i in range(len(rows)):
+        want = hp.query_disc(c[i], r_eff[i])
+        got = pixd[off[i]:off[i + 1]]
+        if 0.0 < r_eff[i] < 1e-9:
+            # cos(radius) == 1.0: whether the centre's own pixel is returned is decided by the last bit of
+            # cos(atan2(.)) (ysq = 1 - z^2 - x^2 ~ +-1e-16), i.e. by the libm -- CUDA and glibc may differ,
+            # as any two libm builds under healpy may.  Either answer must be {} or {centre pixel}.
+            own = hp.vec2pix(*c[i])
+            assert len(got) <= 1 and len(want) <= 1 and all(g == own for g in got), (nside, rows[i], got, want)
+            np.add.at(cover, got, 1.0)
+            continue
+        assert np.array_equal(got, want), (nside, rows[i], len(got), len(want))
+        np.add.at(cover, want, 1.0)
+        if len(want):
+            Ri = R[off[i]:off[i + 1]]
+            assert abs(rmin[i] - Ri.min()) <= 1e-12 and abs(rmax[i] - Ri.max()) <= 1e-12
+    d_map = torch.zeros(hp.npix, dtype=torch.float64, device=dev)
+    one = torch.ones(1, dtype=torch.float64, device=dev)
+    eng.paint_profile(halos, nside, 0, [one], d_map)          # AP_CONSTANT: coverage count
+    assert np.array_equal(d_map.cpu().numpy(), cover)
