@@ -130,8 +130,8 @@ double hc_b16_tau_3D(double r, double R_200c, double M_200c, double redshift) {
   double ctx[kCtx];
   b16_setup(R_200c, M_200c, redshift, ctx);
   B16Integrand f;
-  f.inv_R200xc = ctx[0]; f.alpha = ctx[1]; f.expo = ctx[2]; f.K2 = 2.0 * ctx[3]; f.RR = 0.0;
-  return f(r) / 2.0;  // with R = 0 the LOS weight 2r/sqrt(r^2) is 2
+  f.inv_R200xc = ctx[0]; f.alpha = ctx[1]; f.expo = ctx[2]; f.RR = 0.0;
+  return f(r) * ctx[3];  // with R = 0 the LOS weight r/sqrt(r^2) is 1; ctx[3] = the profile's normalisation
 }
 
 double hc_critical_density(double z) { return critical_density(z); }

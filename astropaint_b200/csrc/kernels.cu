@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
   constexpr bool VEC = (P == P_NFW_BG);
   constexpr bool STATS = (P == P_STATS);
   __shared__ PaintShared<P> sm;
+  if (P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) fm_smem_init();
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int64_t h0 = (int64_t)blockIdx.x * halos_per_block;
@@ -690,17 +691,17 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
   return 0;
 }
 
-// 7 blocks of 128 threads per SM (72 registers): measured 3% faster than the unconstrained 96-register
-// build; the kernel is fp64-pipe bound (~55-70% of the DFMA issue rate), not occupancy bound
-// 7 blocks of 128 threads per SM (72 registers): measured 3% faster than the unconstrained 96-register
-// build; the kernel is fp64-pipe bound (~55-70% of the DFMA issue rate), not occupancy bound
+// 6 blocks of 128 threads per SM (80 registers): measured 176.1 / 173.5 / 180.9 / 182.9 ms
+// per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers); the kernel is fp64-pipe bound
+// (66% of the DFMA issue rate, profiles/), not occupancy bound
 #ifndef AP_QAGI_MINBLOCKS
-#define AP_QAGI_MINBLOCKS 7
+#define AP_QAGI_MINBLOCKS 6
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(128, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64_t n, const double* p0, const double* p1,
                                                                            const double* p2, int32_t ns, const double* nodes,
                                                                            const int32_t* n_nodes, double* values) {
+  fm_smem_init();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * ns) return;
   int64_t h = t / ns;
@@ -745,6 +746,7 @@ extern "C" int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double*
 __global__ void __launch_bounds__(128) b16_tau_eval_kernel(int64_t n, const double* R, const double* R200,
                                                            const double* M200, const double* zred, double* result,
                                                            double* abserr, int32_t* neval) {
+  fm_smem_init();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   double ctx[kCtx];
@@ -886,6 +888,7 @@ template <int KIND, class MapT>
 __global__ void __launch_bounds__(128) paint_los_small_kernel(Hpx hpx, HalosDev H, const double* R200, const double* M200,
                                                               const double* zred, const double* scale, const int64_t* n_pix,
                                                               int32_t ns, MapT* map, unsigned long long* n_painted) {
+  fm_smem_init();
   int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (h >= H.n) return;
@@ -923,6 +926,7 @@ __global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev 
                                                               const double* p2, const double* scale, int64_t n_items,
                                                               const int64_t* item_halo, const int32_t* item_ord,
                                                               MapT* map) {
+  fm_smem_init();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_items) return;
   const int64_t h = item_halo[t];

@@ -11,6 +11,7 @@
 // scipy.integrate.quad (value, abserr, neval) on the CPU.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace ap {
 
@@ -32,7 +33,10 @@ struct QagiResult {
 // Code-size note (measured, profiles/): fully inlining the rule at its three call sites with the 15
 // integrand evaluations unrolled produced a 270 KB kernel that thrashed the instruction cache.
 // The rule is therefore ONE out-of-line device function with a rolled pair loop, and its
-// node/weight tables live in __constant__ memory (uniform broadcast loads).  An earlier version
+// node/weight tables live in __constant__ memory (uniform broadcast loads).  (Round 1, later: giving
+// dqagie a single call site of the rule -- first evaluation as iteration 1 of the bisection loop -- and
+// inlining it there measured 183.5 ms against 168.0 ms per 1e7 halos for this out-of-line form; a
+// shared-memory home for fv1/fv2 and bank-conflict-free replicated log/exp tables measured +-1%.)  An earlier version
 // kept the tables as function-local arrays: after inlining, nvcc 12.9 (-O3, sm_100a) overlapped
 // their local-memory slots with the caller's epsilon table and the device results diverged from
 // the host build — tests/test_gpu_parity.py::test_device_quadpack_matches_scipy guards this.
@@ -79,8 +83,8 @@ AP_NOINLINE AP_HD_NOINLINE void qk15i(const F& f_ref, double boun, double a, dou
   double hlgth = AP_MUL(0.5, AP_SUB(b, a));
   // x = boun + (1 - t) / t and the Jacobian 1 / t^2 share one reciprocal (QUADPACK divides three
   // times; the results differ by <= 1 ulp)
-  double ic = 1.0 / centr;
-  double fval1 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, centr), ic)));
+  double ic = fm_rcp(centr);
+  double fval1 = f(fm_fma(AP_SUB(1.0, centr), ic, boun));
   double fc = AP_MUL(AP_MUL(fval1, ic), ic);
   double resg = AP_MUL(AP_GK(wg)[7], fc);
   double resk = AP_MUL(AP_GK(wgk)[7], fc);
@@ -93,10 +97,10 @@ AP_NOINLINE AP_HD_NOINLINE void qk15i(const F& f_ref, double boun, double a, dou
     double absc1 = AP_SUB(centr, absc);
     double absc2 = AP_ADD(centr, absc);
     // 1/(c - a) and 1/(c + a) from one reciprocal of (c - a)(c + a)
-    double ip = 1.0 / AP_MUL(absc1, absc2);
+    double ip = fm_rcp(AP_MUL(absc1, absc2));
     double i1 = AP_MUL(absc2, ip), i2 = AP_MUL(absc1, ip);
-    double f1 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, absc1), i1)));
-    double f2 = f(AP_ADD(boun, AP_MUL(AP_SUB(1.0, absc2), i2)));
+    double f1 = f(fm_fma(AP_SUB(1.0, absc1), i1, boun));
+    double f2 = f(fm_fma(AP_SUB(1.0, absc2), i2, boun));
     f1 = AP_MUL(AP_MUL(f1, i1), i1);
     f2 = AP_MUL(AP_MUL(f2, i2), i2);
     fv1[j] = f1;

@@ -172,7 +172,11 @@ def test_device_quadpack_matches_scipy():
             f = lambda r: o.b16_tau_3D(r, R200[i], M[i], z[i]) * 2. * r / np.sqrt(r ** 2 - R[i] ** 2)  # noqa: E731
             v, e, info = integrate.quad(f, R[i], np.inf, epsabs=0., epsrel=1.e-2, full_output=1)[:3]
             assert nev[i] == info["neval"], (i, R[i] / R200[i], nev[i], info["neval"])
-            assert abs(res[i] - v) <= 1e-10 * abs(v)
+            # same decisions (neval) but not the same bits: the integrand is formed as exp/log instead of pow
+            # and the epsilon algorithm (dqelg: 1/(1/d1 + 1/d2 - 1/d3) of near-equal differences) amplifies
+            # last-bit differences to ~1e-9 on a few quadratures (3e7 device quadratures, two builds whose
+            # integrands differ by one rounding: max relative difference 1.4e-8) -- bar: 1e-7, map bar 1e-6
+            assert abs(res[i] - v) <= 1e-7 * abs(v)
             assert abs(err[i] - e) <= 1e-3 * abs(e) + 1e-300   # error estimates are differences of near-equal sums
 
 
@@ -662,7 +666,9 @@ def test_disc_edge_cases_on_device(nside):
     # radius pi/2 around an axis puts thousands of pixel centres EXACTLY on the disc boundary; how such an
     # exact tie falls is decided by the last bit of libm's atan2 (CUDA vs glibc here, and any two libm
     # builds under the reference) -- DESIGN.md section 5.  It is exercised on the host build only.
-    radii = [0.0, 1e-12, 0.5 * pixsize, pixsize, 2.5 * pixsize, 0.1, 1.0, 1.5, np.pi - 1e-12, 3.2, 4.0]
+    # (np.pi - 1e-12 is likewise host-only: around a pixel centre it mirrors the centre's ring onto a ring
+    # centre, ring_above() sits on an exact tie and one ulp of cos() moves a whole ring in or out)
+    radii = [0.0, 1e-12, 0.5 * pixsize, pixsize, 2.5 * pixsize, 0.1, 1.0, 1.5, 3.0, 3.2, 4.0]
     rows = [(c, r) for c in centres for r in radii]
     c = np.array([row[0] for row in rows], dtype=np.float64)
     r_ang = np.rad2deg(np.array([row[1] for row in rows])) * 60
