@@ -216,6 +216,8 @@ def table_spray(halos, nside, kind, args, scale, n_samples, method, d_map, d_cou
         paint_los_small(kind, h, nside, a, sc, n_pix, n_samples, d_map, d_count)
         tick("end")
 
+    if _capi.lib().ap_disc_mode(-1) > 0:
+        n_bands = 1     # inclusive discs reach above top_ring()'s estimate: no band streaming (rare path)
     if n_bands <= 1:
         run(halos, args, scale)
         if band_done is not None:
@@ -244,6 +246,23 @@ def table_spray(halos, nside, kind, args, scale, n_samples, method, d_map, d_cou
 # ---------------------------------------------------------------------------------------------
 # kernel wrappers
 # ---------------------------------------------------------------------------------------------
+class disc_mode:
+    """`with disc_mode(canvas.inclusive):` -- every disc query issued by this thread inside the block is
+    healpy's query_disc(inclusive=True) (oversampling factor 4, healpy's default; Canvas(..., inclusive=True),
+    paint_bucket.py:782, :1228) instead of the exclusive one.  Thread-local in the C library (ap_disc_mode)."""
+
+    def __init__(self, inclusive, fact=4):
+        self.fact = int(fact) if inclusive else 0
+
+    def __enter__(self):
+        self.prev = _capi.lib().ap_disc_mode(self.fact)
+        return self
+
+    def __exit__(self, *exc):
+        _capi.lib().ap_disc_mode(self.prev)
+        return False
+
+
 def disc_count(halos, nside, inclusive=False, want_range=False, want_rings=False):
     L = _capi.lib()
     dev = halos.device

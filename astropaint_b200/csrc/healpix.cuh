@@ -16,6 +16,10 @@ namespace ap {
 struct Hpx {
   int64_t nside, npix, ncap;
   double fact1, fact2;
+  // inclusive disc queries (healpy query_disc(inclusive=True, fact=incl_fct)): 0 = exclusive query.
+  // rad_small / rad_big = max_pixrad() at incl_fct * nside and at nside, formed on the host (hpx_set_inclusive)
+  int32_t incl_fct;
+  double rad_small, rad_big;
 };
 
 AP_HD Hpx make_hpx(int64_t nside) {
@@ -25,7 +29,41 @@ AP_HD Hpx make_hpx(int64_t nside) {
   h.ncap = 2 * nside * (nside - 1);
   h.fact2 = 4.0 / (double)h.npix;
   h.fact1 = (double)(nside << 1) * h.fact2;
+  h.incl_fct = 0;
+  h.rad_small = h.rad_big = 0.0;
   return h;
+}
+
+// T_Healpix_Base::max_pixrad(): v_angle(set_z_phi(2/3, pi/(4 nside)), set_z_phi(1 - (1 - 1/nside)^2/3, 0))
+AP_HD double max_pixrad(int64_t nside) {
+  double za = 2.0 / 3.0, pa = kPi / (double)(4 * nside);
+  double sa = sqrt(AP_MUL(AP_SUB(1.0, za), AP_ADD(1.0, za)));
+  double ax = AP_MUL(sa, cos(pa)), ay = AP_MUL(sa, sin(pa)), az = za;
+  double t1 = AP_SUB(1.0, 1.0 / (double)nside);
+  t1 = AP_MUL(t1, t1);
+  double zb = AP_SUB(1.0, t1 / 3.0);
+  double sb = sqrt(AP_MUL(AP_SUB(1.0, zb), AP_ADD(1.0, zb)));
+  double bx = AP_MUL(sb, 1.0), by = AP_MUL(sb, 0.0), bz = zb;  // cos(0), sin(0)
+  double cx = AP_SUB(AP_MUL(ay, bz), AP_MUL(az, by));
+  double cy = AP_SUB(AP_MUL(az, bx), AP_MUL(ax, bz));
+  double cz = AP_SUB(AP_MUL(ax, by), AP_MUL(ay, bx));
+  double cl = sqrt(AP_ADD(AP_ADD(AP_MUL(cx, cx), AP_MUL(cy, cy)), AP_MUL(cz, cz)));
+  double dot = AP_ADD(AP_ADD(AP_MUL(ax, bx), AP_MUL(ay, by)), AP_MUL(az, bz));
+  return atan2(cl, dot);
+}
+
+// query_disc_internal's radii for fact > 0 (healpix_base.cc): host only (called by the C ABI entry points)
+inline void hpx_set_inclusive(Hpx& h, int fct) {
+  h.incl_fct = fct;
+  if (fct <= 0) {
+    h.incl_fct = 0;
+    h.rad_small = h.rad_big = 0.0;
+  } else if (fct == 1) {
+    h.rad_small = h.rad_big = max_pixrad(h.nside);
+  } else {
+    h.rad_small = max_pixrad(h.nside * fct);
+    h.rad_big = max_pixrad(h.nside);
+  }
 }
 
 AP_HD int64_t ring_above(const Hpx& h, double z) {
@@ -66,7 +104,8 @@ AP_HD void ring_info(const Hpx& h, int64_t ring, int64_t& startpix, int64_t& rin
 // ir_first..ir_last; ring iz is a FULL ring (pole cap inside the disc) when iz < irmin or
 // iz > irmax, otherwise its span comes from ring_span().
 struct DiscHeader {
-  double phi, z0, xa, cosr;
+  double phi, z0, xa, cosr;  // cosr = cos(rbig): the span boundaries
+  double cosrs;              // cos(rsmall): check_pixel_ring's threshold (inclusive queries only)
   int64_t irmin, irmax, ir_first, ir_last;
 };
 
@@ -77,7 +116,14 @@ AP_HD DiscHeader disc_header(const Hpx& h, double x, double y, double z, double 
   double phi = atan2(y, x);
   if (phi < 0.0) phi = AP_ADD(phi, kTwoPi);
   d.phi = phi;
-  if (radius >= kPi) {  // whole sky
+  const int fct = h.incl_fct;
+  double rsmall = radius, rbig = radius;
+  if (fct) {  // inclusive: radius enlarged by the pixel radius at fct * nside (ring range, trimming) and nside (spans)
+    rsmall = AP_ADD(radius, h.rad_small);
+    rbig = AP_ADD(radius, h.rad_big);
+  }
+  d.cosrs = 0.0;
+  if (rsmall >= kPi) {  // whole sky
     d.z0 = d.xa = d.cosr = 0.0;
     d.ir_first = 1;
     d.ir_last = 4 * h.nside - 1;
@@ -85,17 +131,26 @@ AP_HD DiscHeader disc_header(const Hpx& h, double x, double y, double z, double 
     d.irmax = 4 * h.nside;
     return d;
   }
-  d.cosr = cos(radius);
+  if (fct) {
+    rbig = fmin(kPi, rbig);
+    d.cosrs = cos(rsmall);
+  }
+  d.cosr = cos(rbig);
   d.z0 = cos(theta);
   d.xa = 1.0 / sqrt(AP_MUL(AP_SUB(1.0, d.z0), AP_ADD(1.0, d.z0)));
-  double rlat1 = AP_SUB(theta, radius);
+  double rlat1 = AP_SUB(theta, rsmall);
   double zmax = cos(rlat1);
   d.irmin = ring_above(h, zmax) + 1;
   d.ir_first = d.irmin;
   if (rlat1 <= 0 && d.irmin > 1) d.ir_first = 1;  // north pole in the disc
-  double rlat2 = AP_ADD(theta, radius);
+  if (fct > 1 && rlat1 > 0) {
+    d.irmin = d.irmin > 2 ? d.irmin - 1 : 1;
+    d.ir_first = d.irmin;
+  }
+  double rlat2 = AP_ADD(theta, rsmall);
   double zmin = cos(rlat2);
   d.irmax = ring_above(h, zmin);
+  if (fct > 1 && rlat2 < kPi) d.irmax = d.irmax + 1 < 4 * h.nside - 1 ? d.irmax + 1 : 4 * h.nside - 1;
   d.ir_last = d.irmax;
   if (rlat2 >= kPi && d.irmax + 1 < 4 * h.nside) d.ir_last = 4 * h.nside - 1;  // south pole
   return d;
@@ -115,6 +170,11 @@ struct RingSpan {
   double z;
 };
 
+AP_HD bool check_pixel_ring(const Hpx& b1, const Hpx& b2, int64_t pix, int64_t nr, int64_t ipix1, int fct, double cz,
+                            double cphi, double cosrp2, int64_t cpix);
+AP_HD int64_t loc2pix_ring(const Hpx& h, double nz, double tt, double sth, bool have_sth = true);
+AP_HD double tt_of_phi(double phi);
+
 AP_HD RingSpan ring_span(const Hpx& h, const DiscHeader& d, int64_t iz) {
   RingSpan s;
   int64_t nr;
@@ -130,14 +190,27 @@ AP_HD RingSpan ring_span(const Hpx& h, const DiscHeader& d, int64_t iz) {
   double z = s.z;
   double x = AP_MUL(AP_SUB(d.cosr, AP_MUL(z, d.z0)), d.xa);
   double ysq = AP_SUB(AP_SUB(1.0, AP_MUL(z, z)), AP_MUL(x, x));
-  if (ysq <= 0) return s;
-  double dphi = atan2(sqrt(ysq), x);
+  double dphi;
+  if (ysq <= 0) {  // no intersection: ring completely inside or outside the (enlarged) disc
+    if (h.incl_fct <= 1) return s;
+    dphi = kPi - 1e-15;
+  } else {
+    dphi = atan2(sqrt(ysq), x);
+  }
   if (!(dphi > 0)) return s;
   double shift = s.shifted ? 0.5 : 0.0;
   double f = AP_MUL((double)s.nr, kInvTwoPi);
   // |floor(...)| <= 2 nr < 2^21: the conversions stay in 32 bits
   int32_t ip_lo = (int32_t)floor(AP_SUB(AP_MUL(f, AP_SUB(d.phi, dphi)), shift)) + 1;
   int32_t ip_hi = (int32_t)floor(AP_SUB(AP_MUL(f, AP_ADD(d.phi, dphi)), shift));
+  if (h.incl_fct > 1) {  // trim both ends while the end pixel provably does not overlap the disc
+    const Hpx b2 = make_hpx(h.nside * h.incl_fct);
+    const int64_t cpix = loc2pix_ring(h, d.z0, tt_of_phi(d.phi), 0.0, false);  // zphi2pix(z0, phi)
+    while (ip_lo <= ip_hi && check_pixel_ring(h, b2, ip_lo, s.nr, s.startpix, h.incl_fct, d.z0, d.phi, d.cosrs, cpix))
+      ++ip_lo;
+    while (ip_hi > ip_lo && check_pixel_ring(h, b2, ip_hi, s.nr, s.startpix, h.incl_fct, d.z0, d.phi, d.cosrs, cpix))
+      --ip_hi;
+  }
   if (ip_lo > ip_hi) return s;
   if (ip_hi >= s.nr) {
     ip_lo -= s.nr;
@@ -186,7 +259,7 @@ AP_HD double ring_sth(const Hpx& h, int64_t iz, double z) {
 }
 
 // loc2pix (RING) from nz = z/|v|, tt = fmodulo(phi / (pi/2), 4) and, for |nz| >= 0.99, sth = sin(theta).
-AP_HD int64_t loc2pix_ring(const Hpx& h, double nz, double tt, double sth) {
+AP_HD int64_t loc2pix_ring(const Hpx& h, double nz, double tt, double sth, bool have_sth) {
   double za = fabs(nz);
   int64_t ns = h.nside;
   if (za <= kTwoThird) {
@@ -205,7 +278,7 @@ AP_HD int64_t loc2pix_ring(const Hpx& h, double nz, double tt, double sth) {
   }
   double tp = AP_SUB(tt, (double)(int64_t)tt);
   double tmp;
-  if (za < 0.99) {
+  if (za < 0.99 || !have_sth) {
     tmp = AP_MUL((double)ns, sqrt(AP_MUL(3.0, AP_SUB(1.0, za))));
   } else {
     tmp = AP_MUL((double)ns, sth) / sqrt(AP_ADD(1.0, za) / 3.0);
@@ -274,6 +347,130 @@ AP_HD int64_t vec2pix_ring_near(const Hpx& h, double x, double y, double z, doub
   double nz = AP_MUL(z, xl);
   double sth = (fabs(nz) < 0.99) ? 0.0 : AP_MUL(sqrt(AP_ADD(AP_MUL(x, x), AP_MUL(y, y))), xl);
   return loc2pix_ring(h, nz, tt_of_phi(phi), sth);
+}
+
+
+// ---- inclusive query helpers (healpix_base.cc: ring2xyf, xyf2ring, pix2loc, check_pixel_ring) ----
+AP_HD int64_t hp_isqrt(int64_t v) {
+  int64_t r = (int64_t)sqrt((double)v + 0.5);
+  if (r * r > v) --r;
+  if ((r + 1) * (r + 1) <= v) ++r;
+  return r;
+}
+
+AP_HD int hp_special_div(int64_t a, int64_t b) {  // a / b for 0 <= a < 4b
+  int t = (a >= (b << 1)) ? 1 : 0;
+  a -= t * (b << 1);
+  return (t << 1) + ((a >= b) ? 1 : 0);
+}
+
+AP_HD void ring2xyf(const Hpx& h, int64_t pix, int64_t& ix, int64_t& iy, int& face) {
+  const int jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+  const int64_t ns = h.nside, nl2 = 2 * ns;
+  int64_t iring, iphi, kshift, nr;
+  if (pix < h.ncap) {
+    iring = (1 + hp_isqrt(1 + 2 * pix)) >> 1;
+    iphi = (pix + 1) - 2 * iring * (iring - 1);
+    kshift = 0;
+    nr = iring;
+    face = hp_special_div(iphi - 1, nr);
+  } else if (pix < h.npix - h.ncap) {
+    int64_t ip = pix - h.ncap;
+    int64_t tmp = ip / (4 * ns);
+    iring = tmp + ns;
+    iphi = ip - tmp * 4 * ns + 1;
+    kshift = (iring + ns) & 1;
+    nr = ns;
+    int64_t ire = tmp + 1, irm = nl2 + 1 - tmp;
+    int64_t ifm = (iphi - (ire >> 1) + ns - 1) / ns, ifp = (iphi - (irm >> 1) + ns - 1) / ns;
+    face = (ifp == ifm) ? (int)(ifp | 4) : ((ifp < ifm) ? (int)ifp : (int)(ifm + 8));
+  } else {
+    int64_t ip = h.npix - pix;
+    iring = (1 + hp_isqrt(2 * ip - 1)) >> 1;
+    iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1));
+    kshift = 0;
+    nr = iring;
+    iring = 2 * nl2 - iring;
+    face = hp_special_div(iphi - 1, nr) + 8;
+  }
+  int64_t irt = iring - ((2 + (face >> 2)) * ns) + 1;
+  int64_t ipt = 2 * iphi - jpll[face] * nr - kshift - 1;
+  if (ipt >= nl2) ipt -= 8 * ns;
+  ix = (ipt - irt) >> 1;
+  iy = (-ipt - irt) >> 1;
+}
+
+AP_HD int64_t xyf2ring(const Hpx& h, int64_t ix, int64_t iy, int face) {
+  const int jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+  const int jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+  const int64_t nl4 = 4 * h.nside;
+  int64_t jr = jrll[face] * h.nside - ix - iy - 1;
+  int64_t n_before, nr;
+  bool shifted;
+  ring_info(h, jr, n_before, nr, shifted);
+  nr >>= 2;
+  int64_t kshift = shifted ? 0 : 1;
+  int64_t jp = (jpll[face] * nr + ix - iy + 1 + kshift) / 2;
+  if (jp < 1) jp += nl4;
+  return n_before + jp - 1;
+}
+
+// pix2loc (RING): z and phi of a pixel centre
+AP_HD void pix2zphi_ring(const Hpx& h, int64_t pix, double& z, double& phi) {
+  const int64_t ns = h.nside;
+  if (pix < h.ncap) {
+    int64_t iring = (1 + hp_isqrt(1 + 2 * pix)) >> 1;
+    int64_t iphi = (pix + 1) - 2 * iring * (iring - 1);
+    double tmp = AP_MUL((double)(iring * iring), h.fact2);
+    z = AP_SUB(1.0, tmp);
+    phi = AP_MUL(AP_SUB((double)iphi, 0.5), kHalfPi) / (double)iring;
+  } else if (pix < h.npix - h.ncap) {
+    int64_t nl4 = 4 * ns;
+    int64_t ip = pix - h.ncap;
+    int64_t tmp = ip / nl4;
+    int64_t iring = tmp + ns, iphi = ip - nl4 * tmp + 1;
+    double fodd = ((iring + ns) & 1) ? 1.0 : 0.5;
+    z = AP_MUL((double)(2 * ns - iring), h.fact1);
+    phi = AP_MUL(AP_MUL(AP_MUL(AP_SUB((double)iphi, fodd), kPi), 0.75), h.fact1);
+  } else {
+    int64_t ip = h.npix - pix;
+    int64_t iring = (1 + hp_isqrt(2 * ip - 1)) >> 1;
+    int64_t iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1));
+    double tmp = AP_MUL((double)(iring * iring), h.fact2);
+    z = AP_SUB(tmp, 1.0);
+    phi = AP_MUL(AP_SUB((double)iphi, 0.5), kHalfPi) / (double)iring;
+  }
+}
+
+AP_HD double cosdist_zphi(double z1, double phi1, double z2, double phi2) {
+  return AP_ADD(AP_MUL(z1, z2), AP_MUL(cos(AP_SUB(phi1, phi2)),
+                                       sqrt(AP_MUL(AP_SUB(1.0, AP_MUL(z1, z1)), AP_SUB(1.0, AP_MUL(z2, z2))))));
+}
+
+// true = none of the 4 (fct - 1) boundary sub-pixel centres (resolution b2 = fct * nside) of ring pixel
+// `pix` lies within the enlarged radius: the pixel does not overlap the disc and may be trimmed
+AP_HD bool check_pixel_ring(const Hpx& b1, const Hpx& b2, int64_t pix, int64_t nr, int64_t ipix1, int fct, double cz,
+                            double cphi, double cosrp2, int64_t cpix) {
+  if (pix >= nr) pix -= nr;
+  if (pix < 0) pix += nr;
+  pix += ipix1;
+  if (pix == cpix) return false;  // disc centre in the pixel => overlap
+  int64_t px, py;
+  int pf;
+  ring2xyf(b1, pix, px, py, pf);
+  const int64_t ox = fct * px, oy = fct * py;
+  double pz, pphi;
+  for (int i = 0; i < fct - 1; ++i) {  // go along the 4 edges
+    pix2zphi_ring(b2, xyf2ring(b2, ox + i, oy, pf), pz, pphi);
+    if (cosdist_zphi(pz, pphi, cz, cphi) > cosrp2) return false;
+    pix2zphi_ring(b2, xyf2ring(b2, ox + fct - 1, oy + i, pf), pz, pphi);
+    if (cosdist_zphi(pz, pphi, cz, cphi) > cosrp2) return false;
+    pix2zphi_ring(b2, xyf2ring(b2, ox + fct - 1 - i, oy + fct - 1, pf), pz, pphi);
+    if (cosdist_zphi(pz, pphi, cz, cphi) > cosrp2) return false;
+    pix2zphi_ring(b2, xyf2ring(b2, ox, oy + fct - 1 - i, pf), pz, pphi);
+    if (cosdist_zphi(pz, pphi, cz, cphi) > cosrp2) return false;
+  }
+  return true;
 }
 
 }  // namespace ap

@@ -38,6 +38,25 @@ int64_t hc_query_disc(int64_t nside, double x, double y, double z, double radius
   return n;
 }
 
+// healpy.query_disc(inclusive=True, fact=fact)
+int64_t hc_query_disc_inclusive(int64_t nside, double x, double y, double z, double radius, int fact, int64_t* out,
+                                int64_t cap) {
+  Hpx h = make_hpx(nside);
+  hpx_set_inclusive(h, fact);
+  DiscHeader d = disc_header(h, x, y, z, radius);
+  int64_t n = 0;
+  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+    RingSpan s = ring_span(h, d, iz);
+    for (int32_t j = 0; j < s.len; ++j) {
+      if (out && n < cap) out[n] = span_pixel_sorted(s, j);
+      ++n;
+    }
+  }
+  return n;
+}
+
+double hc_max_pixrad(int64_t nside) { return max_pixrad(nside); }
+
 // per-halo pixel count and sum of pixel ids for n halos (near-tie scans against the device)
 void hc_query_disc_stats(int64_t nside, int64_t n, const double* x, const double* y, const double* z,
                          const double* radius, int64_t* count, int64_t* pixsum) {

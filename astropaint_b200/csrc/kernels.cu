@@ -31,6 +31,20 @@ static int fail(const std::string& m) {
   g_err = m;
   return 1;
 }
+// Disc-query mode of the calling thread: 0 = hp.query_disc(inclusive=False) (Canvas default,
+// paint_bucket.py:782), f > 0 = inclusive=True with oversampling factor f (healpy's default f is 4).
+// Every entry point that runs a disc query (count, pixels, paint, LOS bypass) honours it.
+static thread_local int g_incl_fact = 0;
+extern "C" int ap_disc_mode(int inclusive_fact) {
+  int prev = g_incl_fact;
+  if (inclusive_fact >= 0) g_incl_fact = inclusive_fact;  // negative: query only
+  return prev;
+}
+static Hpx disc_hpx(int64_t nside) {
+  Hpx h = make_hpx(nside);
+  hpx_set_inclusive(h, g_incl_fact);
+  return h;
+}
 #define AP_LAUNCH_CHECK()                                                               \
   do {                                                                                  \
     cudaError_t e_ = cudaGetLastError();                                                \
@@ -154,7 +168,7 @@ extern "C" int ap_disc_pixels(int64_t nside, const ap_halos* halos, const int64_
   if (!d_pix_off || !d_pix) return fail("d_pix_off / d_pix NULL");
   int threads = 256;
   int64_t blocks = (halos->n * 32 + threads - 1) / threads;
-  disc_pixels_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(make_hpx(nside), to_dev(halos), d_pix_off,
+  disc_pixels_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(disc_hpx(nside), to_dev(halos), d_pix_off,
                                                                              d_pix, d_R, d_R_vec);
   AP_LAUNCH_CHECK();
   return 0;
@@ -226,7 +240,7 @@ struct StatsArgs {
 };
 
 struct HaloHdr {  // DiscHeader with 32-bit ring numbers (nside <= 2^18)
-  double phi, z0, xa, cosr;
+  double phi, z0, xa, cosr, cosrs;
   int32_t irmin, irmax, ir_first, ir_last;
 };
 
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       d.ir_last = 0;
     }
     HaloHdr hh;
-    hh.phi = d.phi; hh.z0 = d.z0; hh.xa = d.xa; hh.cosr = d.cosr;
+    hh.phi = d.phi; hh.z0 = d.z0; hh.xa = d.xa; hh.cosr = d.cosr; hh.cosrs = d.cosrs;
     hh.irmin = (int32_t)d.irmin; hh.irmax = (int32_t)d.irmax;
     hh.ir_first = (int32_t)d.ir_first; hh.ir_last = (int32_t)d.ir_last;
     sm.hdr[tid] = hh;
@@ -367,7 +381,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       }
       const HaloHdr& hh = sm.hdr[lo];
       DiscHeader d;
-      d.phi = hh.phi; d.z0 = hh.z0; d.xa = hh.xa; d.cosr = hh.cosr;
+      d.phi = hh.phi; d.z0 = hh.z0; d.xa = hh.xa; d.cosr = hh.cosr; d.cosrs = hh.cosrs;
       d.irmin = hh.irmin; d.irmax = hh.irmax; d.ir_first = hh.ir_first; d.ir_last = hh.ir_last;
       int64_t iz = d.ir_first + (it - sm.ring_off[lo]);
       RingSpan s = ring_span(hpx, d, iz);
@@ -545,10 +559,10 @@ static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& p
   if (stats) st = *stats;
   if (f32 && P != P_STATS)
     paint_kernel<P, float><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(
-        make_hpx(nside), to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+        disc_hpx(nside), to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
   else
     paint_kernel<P, double><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(
-        make_hpx(nside), to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+        disc_hpx(nside), to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
   AP_LAUNCH_CHECK();
   return 0;
 }
@@ -559,7 +573,12 @@ extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive
   if (check_nside(nside)) return 1;
   bool want_r = d_rmin || d_rmax;
   if (check_halos(halos, want_r)) return 1;
-  if (inclusive) return fail("inclusive=True disc query is not implemented");
+  // `inclusive` != 0 asks for healpy's inclusive query for THIS call (factor 4 unless ap_disc_mode set one)
+  struct ModeGuard {
+    int prev;
+    explicit ModeGuard(int inc) : prev(g_incl_fact) { if (inc && g_incl_fact == 0) g_incl_fact = 4; }
+    ~ModeGuard() { g_incl_fact = prev; }
+  } guard(inclusive);
   if (want_r && (!d_rmin || !d_rmax)) return fail("d_rmin and d_rmax must both be given");
   if (!d_n_pix) return fail("d_n_pix == NULL");
   if (halos->n == 0) return 0;
@@ -974,7 +993,7 @@ static int paint_los_items_impl(int kind, int64_t nside, const ap_halos* halos, 
   if (!p0 || !p1 || (kind != LOS_NFW_RHO && !p2) || !item_halo || !item_ord || !d_map)
     return fail("paint_los_items: NULL pointer");
   unsigned blocks = (unsigned)((n_items + 127) / 128);
-  Hpx hpx = make_hpx(nside);
+  Hpx hpx = disc_hpx(nside);
   HalosDev H = to_dev(halos);
   cudaStream_t st = (cudaStream_t)stream;
   switch (kind) {
@@ -1021,7 +1040,7 @@ static int paint_los_small_impl(int kind, int64_t nside, const ap_halos* halos, 
   int threads = 128;
   int64_t blocks = (halos->n * 32 + threads - 1) / threads;
   {
-    Hpx hpx = make_hpx(nside);
+    Hpx hpx = disc_hpx(nside);
     HalosDev H = to_dev(halos);
     cudaStream_t st = (cudaStream_t)stream;
     unsigned nb = (unsigned)blocks;

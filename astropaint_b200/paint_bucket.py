@@ -436,8 +436,9 @@ class Canvas:
             for b in range(0, len(idx), self.BATCH):
                 rows = idx[b:b + self.BATCH]
                 halos = eng.DeviceHalos(self.catalog.data, self.R_times, dev, rows=rows)
-                n_pix, _, _, _ = eng.disc_count(halos, self.nside, self.inclusive)
-                off, pix, R, Rv = eng.disc_pixels(halos, self.nside, n_pix, want_R=want_R, want_vec=want_vec)
+                with eng.disc_mode(self.inclusive):
+                    n_pix, _, _, _ = eng.disc_count(halos, self.nside)
+                    off, pix, R, Rv = eng.disc_pixels(halos, self.nside, n_pix, want_R=want_R, want_vec=want_vec)
                 off = off.cpu().numpy()
                 pix = pix.cpu().numpy()
                 R = R.cpu().numpy() if R is not None else None
@@ -673,14 +674,17 @@ class Painter:
 
     # ------------------------ one rank's share ------------------------
     def _paint_rows(self, canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned=None, band_done=None):
-        """Paint catalog rows `rows` (None = all) into the device map d_map; returns stats dict."""
+        """Paint catalog rows `rows` (None = all) into the device map d_map; returns stats dict.
+        Canvas(inclusive=True) switches every disc query of the spray to healpy's inclusive one."""
+        with eng.disc_mode(canvas.inclusive):
+            return self._paint_rows_impl(canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned, band_done)
+
+    def _paint_rows_impl(self, canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned=None, band_done=None):
         import torch
         dev = d_map.device
         data = canvas.catalog.data
         halos = eng.DeviceHalos(data, canvas.R_times, dev, rows=rows, pinned=pinned)
         nside = canvas.nside
-        if canvas.inclusive:
-            raise NotImplementedError("inclusive=True disc queries are not implemented on device yet")
         d_count = torch.zeros(1, dtype=torch.int64, device=dev)
         tmpl = self.template
 

@@ -59,6 +59,13 @@ int ap_version(void);
  * normal build.                                                                               */
 long long ap_debug_bounds_errors(void);
 
+/* Disc-query mode of the calling thread, honoured by every entry point below that runs a disc query
+ * (count, pixels, paint, LOS bypass): 0 = hp.query_disc(..., inclusive=False), the Canvas default
+ * (paint_bucket.py:782, :1228); f > 0 = inclusive=True with healpy's oversampling factor f (healpy's own
+ * default is 4, which is what Canvas(inclusive=True) gets).  Returns the previous mode; a negative
+ * argument only queries.                                                                        */
+int ap_disc_mode(int inclusive_fact);
+
 /* d_radius[i] = R_times * np.deg2rad(d_R_ang_200c[i] / 60): the query_disc radius of
  * Canvas.Disc.gen_pixel_index (paint_bucket.py:1226-1227, lib/transform.py:148-150), rounded exactly
  * as numpy rounds it (IEEE divide, multiply, multiply; no reciprocal, no FMA).                 */
@@ -67,7 +74,8 @@ int ap_disc_radius(int64_t n, const double* d_R_ang_200c, double R_times, double
 /* hp.query_disc per halo (Canvas.Disc.gen_pixel_index, paint_bucket.py:1215-1229), counts only.
  * d_n_pix[n] (required), d_n_rings[n] (optional).  If d_rmin/d_rmax are non-NULL they receive
  * min/max of R = D_a * angdist over each halo's pixels (gen_cent2pix_mpc, :1266-1273), i.e.
- * R.min()/R.max() of utils.sample_array (lib/utils.py:411-412); +inf/-inf for empty discs.   */
+ * R.min()/R.max() of utils.sample_array (lib/utils.py:411-412); +inf/-inf for empty discs.
+ * inclusive != 0: healpy's inclusive query (factor 4) for this call even if ap_disc_mode is 0. */
 int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
                   int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream);
 

@@ -136,10 +136,209 @@ class HealpixRing:
             append(sp, self.npix)
         return ranges
 
-    def query_disc(self, vec, radius, inclusive=False):
+    # -- healpix_base.cc: max_pixrad -------------------------------------------------
+    def max_pixrad(self):
+        """Largest angular distance between a pixel centre and its corners: v_angle between
+        set_z_phi(2/3, pi/(4 nside)) and set_z_phi(1 - (1 - 1/nside)^2 / 3, 0)."""
+        def zphi(z, phi):  # vec3::set_z_phi
+            st = math.sqrt((1.0 - z) * (1.0 + z))
+            return st * math.cos(phi), st * math.sin(phi), z
+        ax, ay, az = zphi(2.0 / 3.0, math.pi / (4 * self.nside))
+        t1 = 1.0 - 1.0 / self.nside
+        t1 *= t1
+        bx, by, bz = zphi(1.0 - t1 / 3.0, 0.0)
+        # v_angle = atan2(|a x b|, a . b), plain left-to-right double arithmetic as in vec3.h
+        cx, cy, cz = ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx
+        return math.atan2(math.sqrt(cx * cx + cy * cy + cz * cz), ax * bx + ay * by + az * bz)
+
+    # -- healpix_base.cc: ring2xyf / xyf2ring ---------------------------------------
+    _JRLL = (2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4)
+    _JPLL = (1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7)
+
+    @staticmethod
+    def _special_div(a, b):
+        t = 1 if a >= (b << 1) else 0
+        a -= t * (b << 1)
+        return (t << 1) + (1 if a >= b else 0)
+
+    def ring2xyf(self, pix):
+        ns, npix, ncap = self.nside, self.npix, self.ncap
+        nl2 = 2 * ns
+        if pix < ncap:
+            iring = (1 + int(_isqrt(1 + 2 * pix))) >> 1
+            iphi = (pix + 1) - 2 * iring * (iring - 1)
+            kshift = 0
+            nr = iring
+            face = self._special_div(iphi - 1, nr)
+        elif pix < npix - ncap:
+            ip = pix - ncap
+            tmp = ip // (4 * ns)
+            iring = tmp + ns
+            iphi = ip - tmp * 4 * ns + 1
+            kshift = (iring + ns) & 1
+            nr = ns
+            ire = tmp + 1
+            irm = nl2 + 1 - tmp
+            ifm = (iphi - (ire >> 1) + ns - 1) // ns
+            ifp = (iphi - (irm >> 1) + ns - 1) // ns
+            face = (ifp | 4) if ifp == ifm else (ifp if ifp < ifm else ifm + 8)
+        else:
+            ip = npix - pix
+            iring = (1 + int(_isqrt(2 * ip - 1))) >> 1
+            iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1))
+            kshift = 0
+            nr = iring
+            iring = 2 * nl2 - iring
+            face = self._special_div(iphi - 1, nr) + 8
+        irt = iring - ((2 + (face >> 2)) * ns) + 1
+        ipt = 2 * iphi - self._JPLL[face] * nr - kshift - 1
+        if ipt >= nl2:
+            ipt -= 8 * ns
+        return (ipt - irt) >> 1, (-ipt - irt) >> 1, face
+
+    def xyf2ring(self, ix, iy, face):
+        ns = self.nside
+        nl4 = 4 * ns
+        jr = self._JRLL[face] * ns - ix - iy - 1
+        n_before, nr, shifted = self.ring_info(jr)
+        nr >>= 2
+        kshift = 0 if shifted else 1
+        jp = (self._JPLL[face] * nr + ix - iy + 1 + kshift) // 2
+        assert jp <= 4 * nr
+        if jp < 1:
+            jp += nl4
+        return n_before + jp - 1
+
+    def pix2zphi(self, pix):
+        z, phi, _, _ = self.pix2loc(pix)
+        return float(z[0]), float(phi[0])
+
+    def zphi2pix(self, z, phi):
+        return int(self.loc2pix(np.array([z]), np.array([phi]), np.array([0.0]), False)[0])
+
+    # -- healpix_base.cc: check_pixel_ring (anonymous namespace) --------------------
+    def _check_pixel_ring(self, b2, pix, nr, ipix1, fct, cz, cphi, cosrp2, cpix):
+        """True when NO boundary sub-pixel centre of `pix` (at resolution b2 = fct * nside) lies within
+        the enlarged radius, i.e. the pixel can be trimmed from the end of the span."""
+        if pix >= nr:
+            pix -= nr
+        if pix < 0:
+            pix += nr
+        pix += ipix1
+        if pix == cpix:
+            return False  # disc centre in the pixel => overlap
+        px, py, pf = self.ring2xyf(pix)
+
+        def cosdist(ix, iy):
+            pz, pphi = b2.pix2zphi(b2.xyf2ring(ix, iy, pf))
+            return pz * cz + math.cos(pphi - cphi) * math.sqrt((1.0 - pz * pz) * (1.0 - cz * cz))
+
+        ox, oy = fct * px, fct * py
+        for i in range(fct - 1):  # go along the 4 edges
+            if cosdist(ox + i, oy) > cosrp2:
+                return False
+            if cosdist(ox + fct - 1, oy + i) > cosrp2:
+                return False
+            if cosdist(ox + fct - 1 - i, oy + fct - 1) > cosrp2:
+                return False
+            if cosdist(ox, oy + fct - 1 - i) > cosrp2:
+                return False
+        return True
+
+    # -- healpix_base.cc: query_disc_internal, RING, fact > 0 (query_disc_inclusive) -
+    def query_disc_inclusive_ranges(self, vec, radius, fact=4):
+        """healpy.query_disc(..., inclusive=True, fact=4): every pixel OVERLAPPING the disc, possibly a
+        few more.  Same ring walk as the exclusive query with (a) the radius enlarged by the pixel radius
+        at nside (span boundaries) and at fact*nside (ring range, trimming test), (b) one more ring on
+        each side, (c) whole rings when the enlarged disc swallows the ring, and (d) each span trimmed
+        from both ends while check_pixel_ring proves the end pixel does not overlap."""
+        fct = int(fact)
+        assert fct >= 1
+        x, y, zc = (float(v) for v in vec)
+        theta = math.atan2(math.sqrt(x * x + y * y), zc)
+        phi = math.atan2(y, x)
+        if phi < 0.0:
+            phi += TWOPI
+        ranges = []
+
+        def append(a, b):
+            if b <= a:
+                return
+            if ranges and a <= ranges[-1][1]:
+                if b > ranges[-1][1]:
+                    ranges[-1][1] = b
+            else:
+                ranges.append([a, b])
+
+        b2 = None
+        if fct > 1:
+            b2 = HealpixRing(fct * self.nside)
+            rsmall = radius + b2.max_pixrad()
+            rbig = radius + self.max_pixrad()
+        else:
+            rsmall = rbig = radius + self.max_pixrad()
+        if rsmall >= math.pi:
+            return [[0, self.npix]]
+        rbig = min(math.pi, rbig)
+        cosrsmall = math.cos(rsmall)
+        cosrbig = math.cos(rbig)
+        z0 = math.cos(theta)
+        den = math.sqrt((1.0 - z0) * (1.0 + z0))
+        xa = 1.0 / den if den != 0.0 else math.inf
+        cpix = self.zphi2pix(z0, phi)
+        rlat1 = theta - rsmall
+        zmax = math.cos(rlat1)
+        irmin = self.ring_above(zmax) + 1
+        if rlat1 <= 0 and irmin > 1:  # north pole in the disc
+            sp, rp, _ = self.ring_info(irmin - 1)
+            append(0, sp + rp)
+        if fct > 1 and rlat1 > 0:
+            irmin = max(1, irmin - 1)
+        rlat2 = theta + rsmall
+        zmin = math.cos(rlat2)
+        irmax = self.ring_above(zmin)
+        if fct > 1 and rlat2 < math.pi:
+            irmax = min(4 * self.nside - 1, irmax + 1)
+        for iz in range(irmin, irmax + 1):
+            z = self.ring2z(iz)
+            xx = (cosrbig - z * z0) * xa
+            ysq = 1.0 - z * z - xx * xx
+            if ysq != ysq:
+                dphi = math.nan
+            elif ysq <= 0:  # no intersection, ring completely inside or outside
+                dphi = 0.0 if fct == 1 else math.pi - 1e-15
+            else:
+                dphi = math.atan2(math.sqrt(ysq), xx)
+            if dphi > 0:
+                ipix1, nr, shifted = self.ring_info(iz)
+                shift = 0.5 if shifted else 0.0
+                ipix2 = ipix1 + nr - 1
+                ip_lo = int(math.floor(nr * INV_TWOPI * (phi - dphi) - shift)) + 1
+                ip_hi = int(math.floor(nr * INV_TWOPI * (phi + dphi) - shift))
+                if fct > 1:
+                    while ip_lo <= ip_hi and self._check_pixel_ring(b2, ip_lo, nr, ipix1, fct, z0, phi, cosrsmall, cpix):
+                        ip_lo += 1
+                    while ip_hi > ip_lo and self._check_pixel_ring(b2, ip_hi, nr, ipix1, fct, z0, phi, cosrsmall, cpix):
+                        ip_hi -= 1
+                if ip_lo <= ip_hi:
+                    if ip_hi >= nr:
+                        ip_lo -= nr
+                        ip_hi -= nr
+                    if ip_lo < 0:
+                        append(ipix1, ipix1 + ip_hi + 1)
+                        append(ipix1 + ip_lo + nr, ipix2 + 1)
+                    else:
+                        append(ipix1 + ip_lo, ipix1 + ip_hi + 1)
+        if rlat2 >= math.pi and irmax + 1 < 4 * self.nside:  # south pole in the disc
+            sp, rp, _ = self.ring_info(irmax + 1)
+            append(sp, self.npix)
+        return ranges
+
+    def query_disc(self, vec, radius, inclusive=False, fact=4):
         if inclusive:
-            raise NotImplementedError("inclusive=True (fact=4 oversampling) is not restated")
-        ranges = self.query_disc_ranges(vec, radius)
+            ranges = self.query_disc_inclusive_ranges(vec, radius, fact)
+        else:
+            ranges = self.query_disc_ranges(vec, radius)
         if not ranges:
             return np.empty(0, dtype=np.int64)
         return np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in ranges])

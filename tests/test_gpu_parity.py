@@ -704,3 +704,56 @@ def test_disc_edge_cases_on_device(nside):
     one = torch.ones(1, dtype=torch.float64, device=dev)
     eng.paint_profile(halos, nside, 0, [one], d_map)          # AP_CONSTANT: coverage count
     assert np.array_equal(d_map.cpu().numpy(), cover)
+
+
+# ------------------------------------------------------------------ Canvas(inclusive=True)
+@pytest.mark.parametrize("name,nside,R_times", [("test6", 64, 1), ("test6", 16, 40), ("box", 128, 5), ("box", 32, 1),
+                                                ("websky", 2048, 5), ("websky", 8192, 5), ("websky", 4096, 1)])
+def test_inclusive_pixel_sets_bit_exact(cats, name, nside, R_times):
+    """Canvas(inclusive=True): hp.query_disc(..., inclusive=True) (paint_bucket.py:782, :1228) per halo --
+    device pixel sets == the oracle's restatement of healpix query_disc_inclusive (fact 4), R alongside."""
+    import astropaint_b200 as ap
+    ref, _, _ = _oracle()
+    cat = cats[name]
+    canvas = ap.Canvas(cat, nside, R_times=R_times, inclusive=True)
+    discs = ref.Discs(cat.data, nside, R_times, inclusive=True)
+    excl = ref.Discs(cat.data, nside, R_times)
+    n = n_excl = 0
+    for halo, (pix, R) in enumerate(zip(canvas.discs.gen_pixel_index(), canvas.discs.gen_cent2pix_mpc())):
+        want = discs.pixel_index(halo)
+        assert np.array_equal(pix, want), f"halo {halo}: {len(pix)} vs {len(want)} pixels"
+        wantR = discs.cent2pix_mpc(halo)
+        assert np.abs(R - wantR).max() <= 1e-9 * max(wantR.max(), 1e-300)
+        n += len(pix)
+        n_excl += len(excl.pixel_index(halo))
+    assert n > n_excl > 0
+
+
+@pytest.mark.parametrize("template", ["gaussian", "kSZ", "BG", "python"])
+def test_inclusive_spray_matches_oracle(cats, template):
+    """the fused painter (built-in, tabulated + bypass, R_vec) and the flat path under Canvas(inclusive=True)"""
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import spherical, Battaglia16, NFW
+    ref, oprof, _ = _oracle()
+    if template == "gaussian":
+        cat, nside, tmpl, otmpl = cats["box"], 64, spherical.gaussian_2D, oprof.gaussian_readme
+    elif template == "kSZ":
+        cat, nside, tmpl, otmpl = cats["websky"], 2048, Battaglia16.kSZ_T, oprof.b16_kSZ_T
+    elif template == "BG":
+        cat, nside, tmpl, otmpl = cats["websky"], 2048, NFW.BG, oprof.nfw_BG
+    else:
+        def tmpl(R, R_200c, v_r):
+            return np.cos(R / R_200c) * v_r
+        cat, nside, otmpl = cats["box"], 64, tmpl
+    canvas = ap.Canvas(cat, nside, R_times=5, inclusive=True)
+    ap.Painter(tmpl).spray(canvas)
+    want = np.zeros(12 * nside * nside)
+    ref.spray(want, cat.data, nside, otmpl, R_times=5, inclusive=True)
+    map_close(canvas.pixels, want)
+    plain = np.zeros_like(want)
+    ref.spray(plain, cat.data, nside, otmpl, R_times=5)
+    assert np.count_nonzero(want) > np.count_nonzero(plain)     # the inclusive map really is wider
+    # the mode is scoped to the spray: an exclusive canvas afterwards is unaffected
+    canvas2 = ap.Canvas(cat, nside, R_times=5)
+    ap.Painter(tmpl).spray(canvas2)
+    map_close(canvas2.pixels, plain)

@@ -18,6 +18,10 @@ def hc():
     L = C.CDLL(os.path.join(here, "astropaint_b200", "_native", "libap_hostcheck.so"))
     L.hc_query_disc.restype = i64
     L.hc_query_disc.argtypes = [i64, d, d, d, d, C.c_void_p, i64]
+    L.hc_query_disc_inclusive.restype = i64
+    L.hc_query_disc_inclusive.argtypes = [i64, d, d, d, d, C.c_int, C.c_void_p, i64]
+    L.hc_max_pixrad.restype = d
+    L.hc_max_pixrad.argtypes = [i64]
     L.hc_disc_R.restype = i64
     L.hc_disc_R.argtypes = [i64, d, d, d, d, d, d, d, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p]
     L.hc_vec2pix.argtypes = [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -53,6 +57,33 @@ def test_disc_pixel_sets_bit_exact(hc, nside):
         n = hc.hc_query_disc(nside, v[0], v[1], v[2], r, _p(buf), len(buf))
         assert n == len(want)
         assert np.array_equal(buf[:n], want)
+
+
+@pytest.mark.parametrize("nside", [1, 2, 3, 8, 64, 1024, 8192])
+def test_inclusive_disc_pixel_sets_bit_exact(hc, nside):
+    """query_disc(inclusive=True, fact) of the device header (host build) == the oracle, fact 4 (healpy's
+    default, what Canvas(inclusive=True) gets), 1 (no trimming) and 2."""
+    hp = H.HealpixRing(nside)
+    assert hc.hc_max_pixrad(nside) == hp.max_pixrad()
+    rng = np.random.default_rng(300 + nside)
+    pixsize = np.sqrt(4 * np.pi / hp.npix)
+    n_cases = 40 if nside <= 64 else 16
+    buf = np.empty(min(hp.npix, 1 << 22), dtype=np.int64)
+    for t in range(n_cases):
+        v = rng.normal(size=3) * rng.uniform(0.1, 100)
+        if t % 8 == 0:
+            v = np.array([0.0, 0.0, 1.0 if t % 16 else -1.0])
+        if t % 8 == 1:
+            v = np.array([1e-9, 1e-9, 1.0])
+        if nside <= 64:
+            r = [0.0, pixsize * rng.uniform(0, 4), rng.uniform(0, 3.2), pixsize * 0.01][t % 4]
+        else:
+            r = pixsize * rng.uniform(0, 20) if t % 4 else pixsize * rng.uniform(30, 80)
+        for fact in (4, 1, 2):
+            want = hp.query_disc(v, r, inclusive=True, fact=fact)
+            n = hc.hc_query_disc_inclusive(nside, v[0], v[1], v[2], r, fact, _p(buf), len(buf))
+            assert n == len(want), (t, v, r, fact)
+            assert np.array_equal(buf[:n], want)
 
 
 def test_R_and_R_vec_match_healpy_formulas(hc):

@@ -54,6 +54,53 @@ def test_query_disc_is_brute_force_disc(nside):
         assert len(diff) == 0 or np.abs(d[diff] - r).max() < 1e-9   # only exact boundary ties may differ
 
 
+@pytest.mark.parametrize("nside", [2, 4, 16, 64])
+def test_inclusive_query_covers_every_overlapping_pixel(nside):
+    """hp.query_disc(inclusive=True) (paint_bucket.py:1228 with Canvas(inclusive=True), :782) by construction:
+    (a) sorted and unique, (b) a superset of the exclusive query, (c) EVERY point inside the disc falls in a
+    returned pixel (so every overlapping pixel is returned), (d) no returned pixel has its centre farther
+    than radius + max_pixrad, (e) fact=1 (no trimming) is a superset of fact=4."""
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(40 + nside)
+    pixsize = np.sqrt(4 * np.pi / hp.npix)
+    for t in range(40):
+        v = rng.normal(size=3) * rng.uniform(0.1, 100)
+        if t % 10 == 0:
+            v = np.array([1e-3, -2e-3, 1.0 if t % 20 else -1.0])   # pole inside the disc
+        r = [rng.uniform(0, 4) * pixsize, rng.uniform(0, 1.5), 0.0, rng.uniform(1.5, 3.3)][t % 4]
+        inc = hp.query_disc(v, r, inclusive=True)
+        exc = hp.query_disc(v, r)
+        assert np.all(np.diff(inc) > 0)
+        assert np.isin(exc, inc).all()
+        assert np.isin(inc, hp.query_disc(v, r, inclusive=True, fact=1)).all()
+        vn = v / np.linalg.norm(v)
+        m = 3000
+        u = rng.normal(size=(m, 3))
+        u -= (u @ vn)[:, None] * vn
+        u /= np.linalg.norm(u, axis=1)[:, None]
+        ang = min(r, np.pi) * np.sqrt(rng.uniform(0, 1, m))
+        ang[:300] = min(r, np.pi) * (1 - 1e-9)          # the rim, where inclusion is decided
+        pts = np.cos(ang)[:, None] * vn + np.sin(ang)[:, None] * u
+        assert np.isin(hp.vec2pix(pts[:, 0], pts[:, 1], pts[:, 2]), inc).all()
+        if len(inc):
+            cx, cy, cz = hp.pix2vec(inc)
+            dist = np.arccos(np.clip(cx * vn[0] + cy * vn[1] + cz * vn[2], -1, 1))
+            assert (dist <= r + hp.max_pixrad() + 1e-9).all()
+
+
+@pytest.mark.parametrize("nside", [1, 2, 5, 16, 128])
+def test_ring_xyf_round_trip_and_max_pixrad(nside):
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(nside)
+    for pix in np.unique(np.concatenate([rng.integers(0, hp.npix, 300), [0, hp.npix - 1, hp.ncap, hp.npix - hp.ncap - 1]])):
+        ix, iy, face = hp.ring2xyf(int(pix))
+        assert 0 <= ix < nside and 0 <= iy < nside and 0 <= face < 12
+        assert hp.xyf2ring(ix, iy, face) == pix
+    # max_pixrad bounds the centre-to-corner distance: between half a pixel side and a full one
+    side = np.sqrt(4 * np.pi / hp.npix)
+    assert 0.5 * side < hp.max_pixrad() < 1.1 * side
+
+
 def test_cartesian_projection_orientation():
     """centre of the cutout is the halo; +y is north; +x is west (astro flip)."""
     nside = 256
