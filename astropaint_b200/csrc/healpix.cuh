@@ -20,6 +20,7 @@ struct Hpx {
   // rad_small / rad_big = max_pixrad() at incl_fct * nside and at nside, formed on the host (hpx_set_inclusive)
   int32_t incl_fct;
   double rad_small, rad_big;
+  double pad_cos, pad_sin;  // cos / sin of 1.02 * max_pixrad(nside): the trimming pre-filter of ring_span
 };
 
 AP_HD Hpx make_hpx(int64_t nside) {
@@ -31,6 +32,8 @@ AP_HD Hpx make_hpx(int64_t nside) {
   h.fact1 = (double)(nside << 1) * h.fact2;
   h.incl_fct = 0;
   h.rad_small = h.rad_big = 0.0;
+  h.pad_cos = 1.0;
+  h.pad_sin = 0.0;
   return h;
 }
 
@@ -64,6 +67,9 @@ inline void hpx_set_inclusive(Hpx& h, int fct) {
     h.rad_small = max_pixrad(h.nside * fct);
     h.rad_big = max_pixrad(h.nside);
   }
+  const double pad = 1.02 * max_pixrad(h.nside);
+  h.pad_cos = cos(pad);
+  h.pad_sin = sin(pad);
 }
 
 AP_HD int64_t ring_above(const Hpx& h, double z) {
@@ -206,6 +212,27 @@ AP_HD RingSpan ring_span(const Hpx& h, const DiscHeader& d, int64_t iz) {
   if (h.incl_fct > 1) {  // trim both ends while the end pixel provably does not overlap the disc
     const Hpx b2 = make_hpx(h.nside * h.incl_fct);
     const int64_t cpix = loc2pix_ring(h, d.z0, tt_of_phi(d.phi), 0.0, false);  // zphi2pix(z0, phi)
+    // Pre-filter, equivalent to the two loops below: a pixel whose CENTRE is farther from the disc centre
+    // than rsafe = rsmall + 1.02 max_pixrad(nside) has every boundary sub-pixel centre farther than rsmall
+    // (each lies within max_pixrad of the pixel centre), so check_pixel_ring is certainly true for it and
+    // the loops would step over it.  The centres within rsafe form the azimuth range phi +- dsafe; the
+    // loops start at its ends (one pixel of slack).  Without this, a ring that the widened ring range adds
+    // just outside the disc (ysq <= 0 above) is walked pixel by pixel: 4 nside * 12 sub-pixel tests.
+    if (d.cosrs > -h.pad_cos) {  // rsafe < pi
+      const double cs = AP_SUB(AP_MUL(d.cosrs, h.pad_cos),
+                               AP_MUL(sqrt(fmax(0.0, AP_SUB(1.0, AP_MUL(d.cosrs, d.cosrs)))), h.pad_sin));
+      const double sring = sqrt(AP_MUL(AP_SUB(1.0, z), AP_ADD(1.0, z)));
+      const double c = AP_MUL(AP_SUB(cs, AP_MUL(z, d.z0)), d.xa) / sring;
+      if (c >= 1.0) {
+        ip_lo = ip_hi + 1;  // no pixel centre of this ring within rsafe: everything is trimmed
+      } else if (c > -1.0) {
+        const double dsafe = AP_ADD(acos(c), 1e-9);
+        const double glo = floor(AP_SUB(AP_MUL(f, AP_SUB(d.phi, dsafe)), shift)) - 1.0;
+        const double ghi = floor(AP_SUB(AP_MUL(f, AP_ADD(d.phi, dsafe)), shift)) + 2.0;
+        if (glo > (double)ip_lo) ip_lo = (int32_t)fmin(glo, (double)ip_hi + 1.0);
+        if (ghi < (double)ip_hi) ip_hi = (int32_t)fmax(ghi, (double)ip_lo - 1.0);
+      }
+    }
     while (ip_lo <= ip_hi && check_pixel_ring(h, b2, ip_lo, s.nr, s.startpix, h.incl_fct, d.z0, d.phi, d.cosrs, cpix))
       ++ip_lo;
     while (ip_hi > ip_lo && check_pixel_ring(h, b2, ip_hi, s.nr, s.startpix, h.incl_fct, d.z0, d.phi, d.cosrs, cpix))

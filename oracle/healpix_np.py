@@ -246,12 +246,17 @@ class HealpixRing:
         return True
 
     # -- healpix_base.cc: query_disc_internal, RING, fact > 0 (query_disc_inclusive) -
-    def query_disc_inclusive_ranges(self, vec, radius, fact=4):
+    def query_disc_inclusive_ranges(self, vec, radius, fact=4, fast=False):
         """healpy.query_disc(..., inclusive=True, fact=4): every pixel OVERLAPPING the disc, possibly a
         few more.  Same ring walk as the exclusive query with (a) the radius enlarged by the pixel radius
         at nside (span boundaries) and at fact*nside (ring range, trimming test), (b) one more ring on
         each side, (c) whole rings when the enlarged disc swallows the ring, and (d) each span trimmed
-        from both ends while check_pixel_ring proves the end pixel does not overlap."""
+        from both ends while check_pixel_ring proves the end pixel does not overlap.
+
+        fast=True is a TEST SPEED-UP, not part of the restatement: before the two trimming loops it steps over
+        the pixels whose centre is farther than rsmall + 1.02 max_pixrad from the disc centre (for those
+        check_pixel_ring is certainly true), which is what keeps a ring of 4 nside pixels lying just outside
+        the disc from being walked pixel by pixel in Python.  tests/test_oracle.py proves fast == plain."""
         fct = int(fact)
         assert fct >= 1
         x, y, zc = (float(v) for v in vec)
@@ -315,6 +320,21 @@ class HealpixRing:
                 ipix2 = ipix1 + nr - 1
                 ip_lo = int(math.floor(nr * INV_TWOPI * (phi - dphi) - shift)) + 1
                 ip_hi = int(math.floor(nr * INV_TWOPI * (phi + dphi) - shift))
+                if fct > 1 and fast:
+                    pad = 1.02 * self.max_pixrad()
+                    if rsmall + pad < math.pi:
+                        sring = math.sqrt((1.0 - z) * (1.0 + z))
+                        c = (math.cos(rsmall + pad) - z * z0) * xa / sring if sring > 0 else -2.0
+                        if c >= 1.0:
+                            ip_lo = ip_hi + 1
+                        elif c > -1.0:
+                            dsafe = math.acos(c) + 1e-9
+                            glo = int(math.floor(nr * INV_TWOPI * (phi - dsafe) - shift)) - 1
+                            ghi = int(math.floor(nr * INV_TWOPI * (phi + dsafe) - shift)) + 2
+                            if glo > ip_lo:
+                                ip_lo = min(glo, ip_hi + 1)
+                            if ghi < ip_hi:
+                                ip_hi = max(ghi, ip_lo - 1)
                 if fct > 1:
                     while ip_lo <= ip_hi and self._check_pixel_ring(b2, ip_lo, nr, ipix1, fct, z0, phi, cosrsmall, cpix):
                         ip_lo += 1
@@ -334,9 +354,9 @@ class HealpixRing:
             append(sp, self.npix)
         return ranges
 
-    def query_disc(self, vec, radius, inclusive=False, fact=4):
+    def query_disc(self, vec, radius, inclusive=False, fact=4, fast=False):
         if inclusive:
-            ranges = self.query_disc_inclusive_ranges(vec, radius, fact)
+            ranges = self.query_disc_inclusive_ranges(vec, radius, fact, fast)
         else:
             ranges = self.query_disc_ranges(vec, radius)
         if not ranges:

@@ -97,7 +97,9 @@ def build_dataframe(data, default_redshift=0):
 # Canvas.Disc generators (per halo)
 # ---------------------------------------------------------------------------------
 class Discs:
-    def __init__(self, df, nside, R_times=1, inclusive=False):
+    def __init__(self, df, nside, R_times=1, inclusive=False, fast_inclusive=True):
+        # fast_inclusive: the validated pre-filter of HealpixRing.query_disc_inclusive_ranges (test speed only)
+        self.fast_inclusive = fast_inclusive
         self.df = df
         self.nside = nside
         self.R_times = R_times
@@ -115,7 +117,7 @@ class Discs:
         """gen_pixel_index, paint_bucket.py:1215-1229"""
         return self.hp.query_disc((self._x[halo], self._y[halo], self._z[halo]),
                                   self.R_times * arcmin2rad(self._rang[halo]),
-                                  inclusive=self.inclusive)
+                                  inclusive=self.inclusive, fast=self.fast_inclusive)
 
     def cent2pix_rad(self, halo, pixel_index=None):
         """gen_cent2pix_rad, :1256-1264"""

@@ -88,6 +88,26 @@ def test_inclusive_query_covers_every_overlapping_pixel(nside):
             assert (dist <= r + hp.max_pixrad() + 1e-9).all()
 
 
+@pytest.mark.parametrize("nside", [1, 3, 16, 256, 8192])
+def test_inclusive_fast_path_equals_plain_restatement(nside):
+    """the pre-filter used to keep the inclusive oracle fast in the big parity tests changes nothing"""
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(70 + nside)
+    pixsize = np.sqrt(4 * np.pi / hp.npix)
+    for t in range(60 if nside <= 256 else 6):
+        v = rng.normal(size=3) * rng.uniform(0.1, 100)
+        if t % 10 == 0:
+            v = np.array([1e-3, -2e-3, 1.0 if t % 20 else -1.0])
+        if nside <= 256:
+            r = [rng.uniform(0, 6) * pixsize, rng.uniform(0, 1.5), 0.0, rng.uniform(1.5, 3.3)][t % 4]
+        else:
+            r = rng.uniform(0, 12) * pixsize
+        for fact in (4, 2):
+            a = hp.query_disc(v, r, inclusive=True, fact=fact)
+            b = hp.query_disc(v, r, inclusive=True, fact=fact, fast=True)
+            assert np.array_equal(a, b), (nside, t, fact)
+
+
 @pytest.mark.parametrize("nside", [1, 2, 5, 16, 128])
 def test_ring_xyf_round_trip_and_max_pixrad(nside):
     hp = H.HealpixRing(nside)
