@@ -246,6 +246,31 @@ def table_spray(halos, nside, kind, args, scale, n_samples, method, d_map, d_cou
 # ---------------------------------------------------------------------------------------------
 # kernel wrappers
 # ---------------------------------------------------------------------------------------------
+CATALOG_OUT = ("D_c", "redshift", "lat", "lon", "theta", "phi", "D_a", "R_200c", "c_200c", "R_ang_200c", "rho_s",
+               "R_s", "v_r", "v_th", "v_ph", "v_lat", "v_lon")   # order of the AP_CAT_* indices
+
+
+def catalog_build(cols, default_redshift, crit_dens_0, h, device=None):
+    """Catalog.build_dataframe's derived columns on the device (ap_catalog_build).  cols: dict of host fp64
+    arrays x, y, z, v_x, v_y, v_z, M_200c and optionally redshift.  Returns {column: numpy view} over ONE
+    pinned (17, n) host buffer (kept alive by the arrays)."""
+    dev = require_cuda(device)
+    n = len(cols["x"])
+    names = ["x", "y", "z", "v_x", "v_y", "v_z", "M_200c"] + (["redshift"] if "redshift" in cols else [])
+    d_in = [to_device(np.ascontiguousarray(cols[k], dtype=np.float64), dev) for k in names]
+    if "redshift" not in cols:
+        d_in.append(None)
+    d_out = torch.empty((len(CATALOG_OUT), n), dtype=torch.float64, device=dev)
+    outs = (c_ptr * len(CATALOG_OUT))(*[d_out[k].data_ptr() for k in range(len(CATALOG_OUT))])
+    check(_capi.lib().ap_catalog_build(n, *[ptr(t) for t in d_in], float(default_redshift), float(crit_dens_0),
+                                       float(h), outs, stream_ptr()))
+    h_out = torch.empty((len(CATALOG_OUT), n), dtype=torch.float64, pin_memory=True)
+    h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    arr = h_out.numpy()
+    return {name: arr[k] for k, name in enumerate(CATALOG_OUT)}
+
+
 class disc_mode:
     """`with disc_mode(canvas.inclusive):` -- every disc query issued by this thread inside the block is
     healpy's query_disc(inclusive=True) (oversampling factor 4, healpy's default; Canvas(..., inclusive=True),

@@ -122,6 +122,90 @@ extern "C" int ap_disc_radius(int64_t n, const double* d_R_ang_200c, double R_ti
 }
 
 // ------------------------------------------------------------------------------------------
+// K0: Catalog.build_dataframe (paint_bucket.py:308-364) -- the 17 derived columns of the halo catalog,
+// one thread per halo, structure-of-arrays in and out (coalesced).  HBM-bound: 64-72 B read + 136 B written.
+// ------------------------------------------------------------------------------------------
+struct CatalogIn {
+  const double *x, *y, *z, *vx, *vy, *vz, *M, *redshift;  // redshift may be NULL -> default_redshift
+};
+struct CatalogOut {
+  double* col[AP_CATALOG_N_OUT];
+};
+
+__global__ void __launch_bounds__(256) catalog_build_kernel(int64_t n, CatalogIn in, double default_redshift,
+                                                            double crit_dens_0, double hubble_h, CatalogOut out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = in.x[i], y = in.y[i], z = in.z[i];
+  // astropy cartesian_to_spherical: r, lat in [-pi/2, pi/2], lon wrapped into [0, 2 pi)
+  const double s = hypot(x, y);
+  const double D_c = hypot(s, z);
+  const double lat = atan2(z, s);
+  double lon = atan2(y, x);
+  if (lon < 0.0) lon = AP_ADD(lon, kTwoPi);
+  const double zr = in.redshift ? in.redshift[i] : default_redshift;
+  const double theta = AP_SUB(kHalfPi, lat), phi = lon;
+  const double zp1 = AP_ADD(1.0, zr);
+  const double D_a = D_c / zp1;                                            // transform.D_c_to_D_a
+  const double M = in.M[i];
+  // transform.M_200c_to_R_200c: (3 M / (800 pi rho_c0 (1+z)^3))^(1/3)
+  const double rho = AP_MUL(crit_dens_0, pow(zp1, 3.0));
+  const double R200 = pow(AP_MUL(3.0, M) / AP_MUL(800.0 * kPi, rho), 1.0 / 3.0);
+  // transform.M_200c_to_c_200c (Coe 2010): A (1+z)^d (M / M_0)^m
+  const double c200 = AP_MUL(AP_MUL(5.71, pow(zp1, -0.047)), pow(M / (2.0e12 / hubble_h), -0.097));
+  const double R_ang = AP_MUL(AP_MUL(R200 / D_a, 180.0 / kPi), 60.0);      // rad2arcmin(R_200c / D_a)
+  const double R_s = R200 / c200;
+  const double A_c = AP_SUB(log(AP_ADD(1.0, c200)), c200 / AP_ADD(1.0, c200));
+  const double rho_s = M / AP_MUL(AP_MUL(16.0 * kPi, pow(R_s, 3.0)), A_c);   // transform.M_200c_to_rho_s
+  // velocities: einsum('ij...,i...->j...', get_cart2sph_jacobian(theta, phi), v_cart)
+  double st, ct, sp, cp;
+  sincos(theta, &st, &ct);
+  sincos(phi, &sp, &cp);
+  const double vx = in.vx[i], vy = in.vy[i], vz = in.vz[i];
+  const double v_r = AP_ADD(AP_ADD(AP_MUL(AP_MUL(st, cp), vx), AP_MUL(AP_MUL(st, sp), vy)), AP_MUL(ct, vz));
+  const double v_th = AP_ADD(AP_ADD(AP_MUL(AP_MUL(ct, cp), vx), AP_MUL(AP_MUL(ct, sp), vy)), AP_MUL(-st, vz));
+  const double v_ph = AP_ADD(AP_ADD(AP_MUL(-sp, vx), AP_MUL(cp, vy)), AP_MUL(AP_MUL(0.0, ct), vz));
+  double* const* o = out.col;
+  o[AP_CAT_D_C][i] = D_c;
+  o[AP_CAT_REDSHIFT][i] = zr;
+  o[AP_CAT_LAT][i] = AP_MUL(lat, 180.0 / kPi);
+  o[AP_CAT_LON][i] = AP_MUL(lon, 180.0 / kPi);
+  o[AP_CAT_THETA][i] = theta;
+  o[AP_CAT_PHI][i] = phi;
+  o[AP_CAT_D_A][i] = D_a;
+  o[AP_CAT_R_200C][i] = R200;
+  o[AP_CAT_C_200C][i] = c200;
+  o[AP_CAT_R_ANG_200C][i] = R_ang;
+  o[AP_CAT_RHO_S][i] = rho_s;
+  o[AP_CAT_R_S][i] = R_s;
+  o[AP_CAT_V_R][i] = v_r;
+  o[AP_CAT_V_TH][i] = v_th;
+  o[AP_CAT_V_PH][i] = v_ph;
+  o[AP_CAT_V_LAT][i] = -v_th;
+  o[AP_CAT_V_LON][i] = v_ph;
+}
+
+extern "C" int ap_catalog_build(int64_t n, const double* d_x, const double* d_y, const double* d_z, const double* d_vx,
+                                const double* d_vy, const double* d_vz, const double* d_M_200c,
+                                const double* d_redshift, double default_redshift, double crit_dens_0, double h,
+                                double* const* h_out, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n == 0) return 0;
+  if (!d_x || !d_y || !d_z || !d_vx || !d_vy || !d_vz || !d_M_200c || !h_out) return fail("catalog_build: NULL pointer");
+  if (!(crit_dens_0 > 0.0) || !(h > 0.0)) return fail("catalog_build: cosmology constants must be positive");
+  CatalogIn in{d_x, d_y, d_z, d_vx, d_vy, d_vz, d_M_200c, d_redshift};
+  CatalogOut out;
+  for (int k = 0; k < AP_CATALOG_N_OUT; ++k) {
+    if (!h_out[k]) return fail("catalog_build: NULL output column");
+    out.col[k] = h_out[k];
+  }
+  catalog_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, in, default_redshift, crit_dens_0, h,
+                                                                                    out);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // K1b: flat pixel list (+R, +R_vec); one warp per halo
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) disc_pixels_kernel(Hpx hpx, HalosDev H, const int64_t* pix_off, int64_t* pix,

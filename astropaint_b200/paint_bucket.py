@@ -33,10 +33,13 @@ def _say(*a):
 class Catalog:
     """Halo catalog: positions [Mpc], velocities [km/s], M_200c [M_sun] (+ derived columns)."""
 
-    def __init__(self, data=None, calculate_redshifts=False, default_redshift=0):
+    def __init__(self, data=None, calculate_redshifts=False, default_redshift=0, *, device=None):
+        """`device` (extra, keyword-only): where build_dataframe computes the derived columns -- None = the
+        device kernel for large catalogs when a GPU is present, True / False to force."""
         self._build_counter = 0
         self.calculate_redshifts = calculate_redshifts
         self.default_redshift = default_redshift
+        self.device_build = device
         if data is None:
             self.data = self._initialize_catalog(1)
         elif isinstance(data, str):
@@ -65,7 +68,7 @@ class Catalog:
         if self._build_counter > 0:
             _say("Catalog data has been modified...\n")
         self.build_dataframe(calculate_redshifts=self.calculate_redshifts,
-                             default_redshift=self.default_redshift)
+                             default_redshift=self.default_redshift, device=self.device_build)
 
     def pin_memory(self):
         """Stage every numeric column in page-locked host memory (torch pinned tensors) so that each
@@ -156,10 +159,20 @@ class Catalog:
             return catalog
 
     # ------------------------ methods ------------------------
-    def build_dataframe(self, calculate_redshifts=False, default_redshift=0):
-        """Derived columns the painting path reads (reference: paint_bucket.py:308-364)."""
+    #: catalogs at least this long get their derived columns from the device kernel (ap_catalog_build) when a
+    #: GPU is present: 1e7 halos take 3.2 s in numpy/pandas on the host against a 0.22 s spray
+    DEVICE_BUILD_MIN = 200_000
+
+    def build_dataframe(self, calculate_redshifts=False, default_redshift=0, device=None):
+        """Derived columns the painting path reads (reference: paint_bucket.py:308-364).
+        device: None = the device kernel for catalogs of DEVICE_BUILD_MIN halos or more if CUDA is available,
+        True / False to force."""
         self._build_counter = 1
         d = self.data
+        if device is None:
+            device = len(d) >= self.DEVICE_BUILD_MIN and eng.torch.cuda.is_available()
+        if device:
+            return self._build_dataframe_device(calculate_redshifts, default_redshift)
         x, y, z = (d[k].values.astype(np.float64) for k in ("x", "y", "z"))
         # cartesian -> spherical: D_c, latitude in [-pi/2, pi/2], longitude in [0, 2 pi)
         s = np.hypot(x, y)
@@ -186,6 +199,21 @@ class Catalog:
         d["v_r"], d["v_th"], d["v_ph"] = np.einsum("ij...,i...->j...", J, v_cart)
         d["v_lat"] = -d["v_th"]
         d["v_lon"] = d["v_ph"]
+
+    def _build_dataframe_device(self, calculate_redshifts, default_redshift):
+        """the same 17 columns from csrc/kernels.cu::catalog_build_kernel, one pinned read-back"""
+        d = self.data
+        cols = {k: d[k].values.astype(np.float64, copy=False) for k in ("x", "y", "z", "v_x", "v_y", "v_z", "M_200c")}
+        if calculate_redshifts:   # z_at_value per halo in the reference (:321-323); table inversion here, on the host
+            cols["redshift"] = np.asarray(transform.D_c_to_redshift(np.hypot(np.hypot(cols["x"], cols["y"]), cols["z"])))
+        elif "redshift" in d.columns:
+            cols["redshift"] = d["redshift"].values.astype(np.float64, copy=False)
+        out = eng.catalog_build(cols, default_redshift, transform.crit_dens_0, transform.h)
+        had_z = "redshift" in d.columns and not calculate_redshifts
+        for name in eng.CATALOG_OUT:
+            if name == "redshift" and had_z:
+                continue   # the user's column stays as given (dtype included)
+            d[name] = out[name]
 
     def _get_box_size(self):
         return tuple(self.data[k].max() - self.data[k].min() for k in ("x", "y", "z"))

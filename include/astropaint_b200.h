@@ -59,6 +59,20 @@ int ap_version(void);
  * normal build.                                                                               */
 long long ap_debug_bounds_errors(void);
 
+/* Catalog.build_dataframe (paint_bucket.py:308-364, calculate_redshifts=False): the derived columns of the
+ * halo catalog from x, y, z [Mpc], v_x, v_y, v_z [km/s], M_200c [M_sun] and an optional redshift column
+ * (d_redshift == NULL -> default_redshift for every halo).  crit_dens_0 [M_sun / Mpc^3] and h are the
+ * cosmology constants the reference's lib/transform.py:30-44 takes from astropy.  h_out is a HOST array of
+ * AP_CATALOG_N_OUT DEVICE pointers (n doubles each) in the order of the AP_CAT_* indices below.            */
+enum {
+  AP_CAT_D_C = 0, AP_CAT_REDSHIFT, AP_CAT_LAT, AP_CAT_LON, AP_CAT_THETA, AP_CAT_PHI, AP_CAT_D_A, AP_CAT_R_200C,
+  AP_CAT_C_200C, AP_CAT_R_ANG_200C, AP_CAT_RHO_S, AP_CAT_R_S, AP_CAT_V_R, AP_CAT_V_TH, AP_CAT_V_PH, AP_CAT_V_LAT,
+  AP_CAT_V_LON, AP_CATALOG_N_OUT
+};
+int ap_catalog_build(int64_t n, const double* d_x, const double* d_y, const double* d_z, const double* d_vx,
+                     const double* d_vy, const double* d_vz, const double* d_M_200c, const double* d_redshift,
+                     double default_redshift, double crit_dens_0, double h, double* const* h_out, void* stream);
+
 /* Disc-query mode of the calling thread, honoured by every entry point below that runs a disc query
  * (count, pixels, paint, LOS bypass): 0 = hp.query_disc(..., inclusive=False), the Canvas default
  * (paint_bucket.py:782, :1228); f > 0 = inclusive=True with healpy's oversampling factor f (healpy's own
