@@ -805,6 +805,9 @@ __global__ void __launch_bounds__(128, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64
                                                                            const double* p2, int32_t ns, const double* nodes,
                                                                            const int32_t* n_nodes, double* values) {
   fm_smem_init();
+  // one thread per (halo, node).  A persistent grid-stride form (each resident thread reusing ONE local-memory
+  // frame, which removes the ~138 GB of dead local-memory write-back per 1e7 halos) measured 191 ms against
+  // 170 ms: resident warps then run in lockstep through the fp64-heavy and the bookkeeping phases.
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * ns) return;
   int64_t h = t / ns;
