@@ -432,6 +432,41 @@ def stack_cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize, we
     return stack
 
 
+def _win(win, dev):
+    if win is None:
+        return None, None
+    wy, wx = win
+    return to_device(np.ascontiguousarray(wy, dtype=np.float64), dev), to_device(np.ascontiguousarray(wx, dtype=np.float64), dev)
+
+
+def patch_rotate(d_patches, angle_deg, win=None, weight=None, stack=None):
+    """transform.rotate_patch = scipy.ndimage.rotate(patch, angle, reshape=False) on a batch of device cutouts
+    (n, ysize, xsize): cubic prefilter IN PLACE (d_patches becomes spline coefficients), then rotation;
+    optionally fused with a taper window (wy, wx), per-cutout weights and accumulation into `stack`."""
+    from scipy import special
+    n, ysize, xsize = d_patches.shape
+    dev = d_patches.device
+    L = _capi.lib()
+    check(L.ap_patch_spline_prefilter(n, ysize, xsize, ptr(d_patches), stream_ptr()))
+    ang = np.broadcast_to(np.asarray(angle_deg, dtype=np.float64), (n,))
+    d_c, d_s = to_device(np.ascontiguousarray(special.cosdg(ang)), dev), to_device(np.ascontiguousarray(special.sindg(ang)), dev)
+    wy, wx = _win(win, dev)
+    out = stack if stack is not None else torch.empty_like(d_patches)
+    check(L.ap_patch_rotate(n, ysize, xsize, ptr(d_patches), ptr(d_c), ptr(d_s), ptr(wy), ptr(wx), ptr(weight),
+                            int(stack is not None), ptr(out), stream_ptr()))
+    return out
+
+
+def patch_scale(d_patches, win=None, weight=None, stack=None):
+    """transform.taper_patch (window = outer(hanning, hanning)) and / or per-cutout weights; in place, or
+    accumulated into `stack`."""
+    n, ysize, xsize = d_patches.shape
+    wy, wx = _win(win, d_patches.device)
+    check(_capi.lib().ap_patch_scale(n, ysize, xsize, ptr(d_patches), ptr(wy), ptr(wx), ptr(weight), ptr(stack),
+                                     stream_ptr()))
+    return stack if stack is not None else d_patches
+
+
 # ---------------------------------------------------------------------------------------------
 # spray flows
 # ---------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 //   table_nodes_kernel, los_nodes_kernel<KIND>, spline_build(_uniform)_kernel   K4 @interpolate tables
 //   paint_los_small_kernel<KIND>  the len(R) < n_samples bypass of @interpolate
 //   cutout_kernel<STACK>          K5  CartesianProj cutouts and their stack
+//   patch_ops.cuh                 K6  apply_func library: spline prefilter + rotate, taper, weight, stack
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -797,11 +798,14 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
 // 6 blocks of 128 threads per SM (80 registers): measured 176.1 / 173.5 / 180.9 / 182.9 ms
 // per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers); the kernel is fp64-pipe bound
 // (66% of the DFMA issue rate, profiles/), not occupancy bound
+#ifndef AP_QAGI_THREADS
+#define AP_QAGI_THREADS 128
+#endif
 #ifndef AP_QAGI_MINBLOCKS
 #define AP_QAGI_MINBLOCKS 6
 #endif
 template <int KIND>
-__global__ void __launch_bounds__(128, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64_t n, const double* p0, const double* p1,
+__global__ void __launch_bounds__(AP_QAGI_THREADS, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64_t n, const double* p0, const double* p1,
                                                                            const double* p2, int32_t ns, const double* nodes,
                                                                            const int32_t* n_nodes, double* values) {
   fm_smem_init();
@@ -828,7 +832,7 @@ extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const doubl
   if (n == 0) return 0;
   if (!d_p0 || !d_p1 || (kind != LOS_NFW_RHO && !d_p2) || !d_nodes || !d_n_nodes || !d_values)
     return fail("los_nodes: NULL pointer");
-  int threads = 128;
+  int threads = AP_QAGI_THREADS;
   int64_t total = n * n_samples;
   unsigned blocks = (unsigned)((total + threads - 1) / threads);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1360,3 +1364,6 @@ extern "C" int ap_spray_host(int profile, int64_t nside, int64_t n, const double
   cleanup();
   return rc;
 }
+
+// K6: per-cutout operators (rotate / taper / weight / stack) for Canvas.cutouts(apply_func=...)
+#include "patch_ops.cuh"

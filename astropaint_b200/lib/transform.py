@@ -114,3 +114,17 @@ def taper_patch(patch):
     han = np.hanning(patch.shape[0])
     patch *= np.outer(han, han)
     return patch
+
+
+def scale_patch(patch, weight=1.0):
+    """Multiply a cutout by a (per-halo) number -- the sign flip / weighting of oriented stacking
+    (parallel_stacking.ipynb).  Not in the reference's transform.py; provided so that the common
+    `lambda patch, w: patch * w` has a device twin."""
+    return patch * weight
+
+
+# Canvas.cutouts / stack_cutouts run chains made ONLY of these on the device (csrc/patch_ops.cuh); any other
+# callable in `apply_func` keeps the reference's per-halo host loop.  value = (op, name of its keyword)
+rotate_patch._ap_patch_op = ("rotate", "angle")
+taper_patch._ap_patch_op = ("taper", None)
+scale_patch._ap_patch_op = ("scale", "weight")

@@ -559,11 +559,18 @@ class Canvas:
         lon = self.catalog.data["lon"].values
         lat = self.catalog.data["lat"].values
         batch = max(1, self.CUTOUT_BATCH_BYTES // (8 * xpix * ypix))
+        plan = self._patch_plan(apply_func, func_kwargs, xpix, ypix)
         for b in range(0, len(idx), batch):
             rows = idx[b:b + batch]
             d_lon = eng.to_device(lon[rows], d_map.device)
             d_lat = eng.to_device(lat[rows], d_map.device)
-            cuts = eng.cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix).cpu().numpy()
+            d_cuts = eng.cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix)
+            if plan is not None:      # every function of the chain has a device twin: no per-halo host work
+                cuts = self._run_patch_plan(plan, d_cuts, rows).cpu().numpy()
+                for i in range(len(rows)):
+                    yield cuts[i]
+                continue
+            cuts = d_cuts.cpu().numpy()
             for i, halo in enumerate(rows):
                 cut_out = cuts[i]
                 if apply_func is not None:
@@ -572,6 +579,47 @@ class Canvas:
                                      for key, value in f_kw.items()}
                         cut_out = func(cut_out, **func_dict)
                 yield cut_out
+
+    @staticmethod
+    def _patch_plan(apply_func, func_kwargs, xpix, ypix):
+        """[(op, per-halo-or-scalar value)] when every callable of the (already list-normalised) apply_func
+        chain is one of the library operators with a device twin (transform.rotate_patch / taper_patch /
+        scale_patch), else None."""
+        if apply_func is None:
+            return None
+        plan = []
+        for func, f_kw in zip(apply_func, func_kwargs):
+            spec = getattr(func, "_ap_patch_op", None)
+            if spec is None:
+                return None
+            op, key = spec
+            extra = set(f_kw) - ({key} if key else set())
+            if extra or (key and key not in f_kw and op == "rotate"):
+                return None
+            if op == "taper" and xpix != ypix:
+                return None       # the reference's window is square (np.hanning(patch.shape[0]) twice)
+            plan.append((op, f_kw.get(key) if key else None))
+        return plan
+
+    def _run_patch_plan(self, plan, d_cuts, rows, stack=None):
+        """Apply the chain to the device batch d_cuts (n, ypix, xpix) for catalog rows `rows`; with `stack`
+        the last operator accumulates into it (returns stack), otherwise returns the processed batch."""
+        def per_halo(value):    # the reference indexes length-N kwargs by halo label, scalars are shared
+            v = np.asarray(value, dtype=np.float64).reshape(-1)
+            return v[rows] if len(v) > 1 else np.full(len(rows), v[0])
+        dev = d_cuts.device
+        n_ops = len(plan)
+        for k, (op, value) in enumerate(plan):
+            st = stack if k == n_ops - 1 else None
+            if op == "rotate":
+                d_cuts = eng.patch_rotate(d_cuts, per_halo(value), stack=st)
+            elif op == "taper":
+                han = np.hanning(d_cuts.shape[1])
+                d_cuts = eng.patch_scale(d_cuts, win=(han, han), stack=st)
+            else:
+                w = eng.to_device(per_halo(1.0 if value is None else value), dev)
+                d_cuts = eng.patch_scale(d_cuts, weight=w, stack=st)
+        return d_cuts
 
     def stack_cutouts(self, halo_list="all", lon_range=[-1, 1], lat_range=None, xpix=200, ypix=None,
                       inplace=True, parallel=False, apply_func=None, func_kwargs=dict()):
@@ -587,14 +635,42 @@ class Canvas:
             d_lat = eng.to_device(self.catalog.data["lat"].values[idx], d_map.device)
             stack = eng.stack_cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix).cpu().numpy()
         else:
-            stack = np.zeros((xpix, ypix))
-            for cut_out in self.cutouts(halo_list, lon_range, lat_range, xpix, ypix, apply_func, func_kwargs):
-                stack += cut_out
+            stack = self._stack_cutouts_device(halo_list, lon_range, lat_range, xpix, ypix, apply_func, func_kwargs)
+            if stack is None:       # some callable has no device twin: the reference's loop over cutouts
+                stack = np.zeros((xpix, ypix))
+                for cut_out in self.cutouts(halo_list, lon_range, lat_range, xpix, ypix, apply_func, func_kwargs):
+                    stack += cut_out
         _say("Checkout the result with canvas.stack")
         if inplace:
             self.stack = stack
         else:
             return stack
+
+
+    def _stack_cutouts_device(self, halo_list, lon_range, lat_range, xpix, ypix, apply_func, func_kwargs):
+        """stack_cutouts with an apply_func chain of library operators: cutouts, operators and the sum all
+        stay on the device; only the (ypix, xpix) stack comes back."""
+        import copy
+        import torch
+        if not isinstance(apply_func, list):
+            apply_func, func_kwargs = [apply_func], [func_kwargs]
+        func_kwargs = [copy.copy(kw) for kw in func_kwargs]
+        plan = self._patch_plan(apply_func, func_kwargs, xpix, ypix)
+        if plan is None:
+            return None
+        idx, lonra, latra, xpix, ypix = self._cutout_setup(halo_list, lon_range, lat_range, xpix, ypix)
+        d_map = self.pixels_device
+        lon = self.catalog.data["lon"].values
+        lat = self.catalog.data["lat"].values
+        stack = torch.zeros((ypix, xpix), dtype=torch.float64, device=d_map.device)
+        batch = max(1, self.CUTOUT_BATCH_BYTES // (16 * xpix * ypix))
+        for b in range(0, len(idx), batch):
+            rows = idx[b:b + batch]
+            d_lon = eng.to_device(lon[rows], d_map.device)
+            d_lat = eng.to_device(lat[rows], d_map.device)
+            d_cuts = eng.cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix)
+            self._run_patch_plan(plan, d_cuts, rows, stack=stack)
+        return stack.cpu().numpy()
 
 
 #########################################################

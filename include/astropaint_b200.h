@@ -212,6 +212,27 @@ int ap_spray_host(int profile, int64_t nside, int64_t n, const double* h_x, cons
                   const double* h_D_a, const double* const* h_params, const int32_t* h_strides,
                   int32_t n_params, double* h_map, uint64_t* h_n_painted);
 
+/* ---- per-cutout operators: Canvas.cutouts / stack_cutouts `apply_func` (paint_bucket.py:1729-1742) on a batch
+ * of device-resident cutouts d_patches[n][ysize][xsize] (what ap_cutouts writes).                          */
+
+/* In-place cubic B-spline prefilter of every cutout (scipy.ndimage.spline_filter, order 3, the filter
+ * scipy.ndimage.rotate applies first for mode='constant': mirror extension, axis 0 then axis 1).           */
+int ap_patch_spline_prefilter(int64_t n, int32_t ysize, int32_t xsize, double* d_patches, void* stream);
+
+/* transform.rotate_patch (lib/transform.py:266-275) = scipy.ndimage.rotate(patch, angle, reshape=False) on
+ * prefiltered coefficients d_coef: out = spline(M out_index + offset), M = [[cos, sin], [-sin, cos]] with
+ * d_cos/d_sin[n] = scipy.special.cosdg/sindg(angle) per cutout, 0 outside the cutout.  Optionally fused:
+ * taper (d_win_y[ysize], d_win_x[xsize], both or neither), per-cutout d_weight[n] (NULL = 1), and with
+ * stack != 0 the result is ACCUMULATED into d_out[ysize][xsize] instead of stored to d_out[n][ysize][xsize]. */
+int ap_patch_rotate(int64_t n, int32_t ysize, int32_t xsize, const double* d_coef, const double* d_cos,
+                    const double* d_sin, const double* d_win_y, const double* d_win_x, const double* d_weight,
+                    int stack, double* d_out, void* stream);
+
+/* transform.taper_patch (lib/transform.py:278-283: patch *= outer(hanning, hanning)) and/or per-cutout weights
+ * without rotation: in place when d_stack == NULL, otherwise accumulated into d_stack[ysize][xsize].          */
+int ap_patch_scale(int64_t n, int32_t ysize, int32_t xsize, double* d_patches, const double* d_win_y,
+                   const double* d_win_x, const double* d_weight, double* d_stack, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

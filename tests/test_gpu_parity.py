@@ -789,3 +789,75 @@ def test_device_catalog_build_matches_host(with_redshift):
     ap.Painter(NFW.kSZ_T).spray(a)
     ap.Painter(NFW.kSZ_T).spray(b)
     map_close(a.pixels, b.pixels)      # columns differ in the last bits (CUDA pow/atan2 vs numpy's): map bar 1e-6
+
+
+# ------------------------------------------------------------------ apply_func library on the device (K6)
+@pytest.mark.parametrize("shape", [(200, 200), (33, 33), (24, 41), (7, 7)])
+def test_patch_ops_match_scipy(shape):
+    """csrc/patch_ops.cuh against scipy itself (the reference's transform.rotate_patch IS
+    scipy.ndimage.rotate(reshape=False), lib/transform.py:266-275): prefilter, rotation with per-cutout
+    angles, taper, weights, and the fused accumulate.  Tolerance 1e-12 of the patch scale."""
+    import torch
+    from scipy import ndimage
+    from astropaint_b200 import _engine as eng, _capi
+    from astropaint_b200._capi import ptr
+    rng = np.random.default_rng(shape[0] + shape[1])
+    n = 9
+    patches = rng.normal(size=(n,) + shape)
+    angles = np.array([0.0, 13.7, 45.0, 90.0, -120.3, 180.0, 271.1, 359.99, 33.3])
+    dev = torch.device("cuda", 0)
+    d = torch.from_numpy(patches).to(dev)
+    coef = d.clone()
+    _capi.check(_capi.lib().ap_patch_spline_prefilter(n, shape[0], shape[1], ptr(coef), None))
+    want_coef = np.stack([ndimage.spline_filter(p, order=3, mode="constant") for p in patches])
+    assert np.abs(coef.cpu().numpy() - want_coef).max() < 1e-12
+    got = eng.patch_rotate(d.clone(), angles).cpu().numpy()
+    want = np.stack([ndimage.rotate(p, a, reshape=False) for p, a in zip(patches, angles)])
+    assert np.abs(got - want).max() < 1e-12
+    assert (np.count_nonzero((got == 0) != (want == 0))) <= 2 * n      # border ties of in-bounds tests only
+    w = rng.normal(size=n)
+    if shape[0] == shape[1]:
+        han = np.hanning(shape[0])
+        stack = torch.zeros(shape, dtype=torch.float64, device=dev)
+        eng.patch_rotate(d.clone(), angles, win=(han, han), weight=torch.from_numpy(w).to(dev), stack=stack)
+        want_stack = sum(wi * r * np.outer(han, han) for wi, r in zip(w, want))
+        assert np.abs(stack.cpu().numpy() - want_stack).max() < 1e-11
+    scaled = eng.patch_scale(d.clone(), weight=torch.from_numpy(w).to(dev)).cpu().numpy()
+    assert np.array_equal(scaled, patches * w[:, None, None])
+
+
+def test_stack_with_library_apply_funcs_stays_on_device(cats):
+    """Canvas.cutouts / stack_cutouts with apply_func = [rotate_patch, taper_patch, scale_patch]
+    (oriented stacking, Birkinshaw_Gull_stacking.ipynb) == the reference loop calling scipy per halo."""
+    import astropaint_b200 as ap
+    from astropaint_b200 import transform
+    from astropaint_b200.profiles import NFW
+    ref, _, _ = _oracle()
+    cat = cats["box"]
+    nside = 256
+    canvas = ap.Canvas(cat, nside, R_times=5)
+    ap.Painter(NFW.kSZ_T).spray(canvas)
+    pixels = canvas.pixels.copy()
+    n = len(cat.data)
+    angle = np.rad2deg(np.arctan2(cat.data.v_th.values, cat.data.v_ph.values))
+    sign = -np.sign(cat.data.v_r.values)
+    halos = np.arange(0, 30, 2)
+    funcs = [transform.rotate_patch, transform.taper_patch, transform.scale_patch]
+    kw = lambda: [{"angle": angle.copy()}, {}, {"weight": sign.copy()}]  # noqa: E731
+    want_cuts = list(ref.cutouts(pixels, cat.data, nside, halos, [-1, 1], None, 48, None, funcs, kw()))
+    got_cuts = list(canvas.cutouts(halos, lon_range=[-1, 1], xpix=48, apply_func=funcs, func_kwargs=kw()))
+    assert len(got_cuts) == len(want_cuts)
+    scale = max(np.abs(w).max() for w in want_cuts)
+    for g, w in zip(got_cuts, want_cuts):
+        assert np.abs(g - w).max() <= 1e-12 * scale
+    got = canvas.stack_cutouts(halos, lon_range=[-1, 1], xpix=48, inplace=False, apply_func=funcs, func_kwargs=kw())
+    want = ref.stack_cutouts(pixels, cat.data, nside, halos, [-1, 1], None, 48, None, funcs, kw())
+    assert np.abs(got - want).max() <= 1e-11 * scale
+    # single callable + shared scalar kwarg
+    got = canvas.stack_cutouts(halos, lon_range=[-1, 1], xpix=48, inplace=False, apply_func=transform.rotate_patch,
+                               func_kwargs={"angle": 30.0})
+    want = ref.stack_cutouts(pixels, cat.data, nside, halos, [-1, 1], None, 48, None, transform.rotate_patch,
+                             {"angle": 30.0})
+    assert np.abs(got - want).max() <= 1e-11 * scale
+    assert canvas._patch_plan([lambda p: p], [{}], 48, 48) is None      # unknown callables keep the host loop
+

@@ -207,3 +207,23 @@ def test_catalog_columns_match_oracle_build_dataframe():
     assert len(cat.data.columns) == 24
     for c in want.columns:
         assert np.allclose(cat.data[c].values, want[c].values, rtol=1e-14, atol=0), c
+
+
+@pytest.mark.parametrize("shape", [(16, 16), (21, 21), (12, 19), (5, 5)])
+def test_patch_rotate_restatement_is_scipy_rotate(shape):
+    """oracle/patch_ops_np.py (what csrc/patch_ops.cuh is read against) == scipy.ndimage.rotate itself, the
+    function the reference's transform.rotate_patch calls (lib/transform.py:266-275): a PINNED oracle."""
+    from scipy import ndimage
+    from oracle import patch_ops_np as P
+    rng = np.random.default_rng(shape[0])
+    p = rng.normal(size=shape)
+    assert np.abs(ndimage.spline_filter(p, order=3, mode="constant") - P.spline_prefilter(p)).max() < 1e-13
+    for angle in [0, 13.7, 45, 90, -120.3, 180, 271.1, 359.99]:
+        want = ndimage.rotate(p, angle, reshape=False)
+        got = P.rotate_patch(p, angle)
+        assert np.array_equal(want == 0, got == 0)           # same pixels fall outside the source
+        assert np.abs(got - want).max() < 1e-13
+    if shape[0] == shape[1]:     # the reference's window is square
+        from astropaint_b200.lib import transform
+        assert np.array_equal(P.taper_patch(p), transform.taper_patch(p.copy()))
+
