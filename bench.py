@@ -302,11 +302,12 @@ def run_b200(args):
     # the dominant kernel is the QUADPACK node kernel: fp64-pipe / issue bound (DRAM < 1% of peak), so an
     # HBM or tensor roofline does not apply; report its rate and the ncu-measured pipe utilisation instead
     n_quad = ns * n_big
-    roofline_dominant = {"kernel": "b16_tau_nodes_kernel (QUADPACK dqagie per (halo, node))", "bound": "fp64-pipe",
+    roofline_dominant = {"kernel": "los_nodes_kernel<b16_tau> (QUADPACK dqagie per (halo, node))", "bound": "fp64-pipe",
                          "achieved": n_quad / (phase_ms["los_nodes"] / 1e3), "unit": "quadratures/s",
                          "launch_ms": phase_ms["los_nodes"], "share_of_step": phase_ms["los_nodes"] / ms_step,
-                         "fp64_pipe_active_pct_ncu": 55, "peak": None, "frac": None,
-                         "note": "see profiles/README.md; 165 integrand evaluations per quadrature (scipy neval)"}
+                         "fp64_pipe_active_pct_ncu": 65.7, "peak": None, "frac": None,
+                         "note": "profiles/r1b_ncu_final.csv: fp64 pipe 65.7% active, issue slots 65.3% busy; 165 "
+                                 "integrand evaluations per quadrature (scipy neval), ~164 warp instructions each"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
