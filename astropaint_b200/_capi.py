@@ -28,6 +28,7 @@ SIGNATURES = {
     "ap_version": (C.c_int, []),
     "ap_debug_bounds_errors": (C.c_longlong, []),
     "ap_disc_mode": (C.c_int, [C.c_int]),
+    "ap_quad_fast_path": (C.c_int, [C.c_int]),
     "ap_catalog_build": (C.c_int, [c_i64] + [c_ptr] * 8 + [c_dbl, c_dbl, c_dbl, C.POINTER(c_ptr), c_ptr]),
     "ap_disc_radius": (C.c_int, [c_i64, c_ptr, c_dbl, c_ptr, c_ptr]),
     "ap_disc_count": (C.c_int, [c_i64, C.POINTER(ApHalos), C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -145,6 +145,30 @@ int hc_los(int kind, double R, double p0, double p1, double p2, double* result, 
   return 0;
 }
 
+// the rightmost-bisection fast path alone: returns 1 if it accepted the quadrature (result/abserr/neval/ier
+// filled), 0 if it bailed out to the general routine; kind as hc_los
+int hc_los_fast_path(int kind, double R, double p0, double p1, double p2, double* result, double* abserr, int* neval,
+                     int* ier) {
+  double ctx[kCtx];
+  QagiResult q;
+  bool ok;
+  if (kind == LOS_NFW_RHO) {
+    los_setup<LOS_NFW_RHO>(p0, p1, p2, ctx);
+    NfwRhoIntegrand f;
+    f.K8 = ctx[0]; f.rs = ctx[1]; f.RR = R * R;
+    ok = qagi_upper_rm(f, R, 0.0, 1.0e-2, q);
+  } else {
+    b16_setup(p0, p1, p2, ctx);
+    B16Integrand f;
+    f.inv_R200xc = ctx[0]; f.alpha = ctx[1]; f.expo = ctx[2]; f.RR = R * R;
+    ok = qagi_upper_rm(f, R, 0.0, 1.0e-2, q);
+    if (ok) { q.result *= 2.0 * ctx[3]; q.abserr *= 2.0 * ctx[3]; }
+  }
+  if (!ok) return 0;
+  *result = q.result; *abserr = q.abserr; *neval = q.neval; *ier = q.ier;
+  return 1;
+}
+
 double hc_b16_tau_3D(double r, double R_200c, double M_200c, double redshift) {
   double ctx[kCtx];
   b16_setup(R_200c, M_200c, redshift, ctx);

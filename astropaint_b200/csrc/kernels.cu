@@ -41,6 +41,14 @@ extern "C" int ap_disc_mode(int inclusive_fact) {
   if (inclusive_fact >= 0) g_incl_fact = inclusive_fact;  // negative: query only
   return prev;
 }
+// 1 (default): ap_los_nodes uses the rightmost-bisection fast path of dqagie (qagi.cuh) and falls back to the
+// general routine per quadrature; 0: the general routine only (parity tests compare the two bit for bit)
+static int g_quad_fast = 1;
+extern "C" int ap_quad_fast_path(int enable) {
+  int prev = g_quad_fast;
+  if (enable >= 0) g_quad_fast = enable ? 1 : 0;
+  return prev;
+}
 static Hpx disc_hpx(int64_t nside) {
   Hpx h = make_hpx(nside);
   hpx_set_inclusive(h, g_incl_fact);
@@ -636,6 +644,8 @@ template <int P>
 static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& pp, const TableArgs& tab, void* d_map,
                         unsigned long long* d_n_painted, void* stream, const StatsArgs* stats = nullptr,
                         bool f32 = false) {
+  if ((P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) && rm_ensure_tables(stream))
+    return fail("could not initialise the quadrature tables");
   int g = pick_halos_per_block(halos->n);
   int64_t blocks = (halos->n + g - 1) / g;
   if (blocks > 0x7fffffffLL) return fail("too many blocks");
@@ -804,7 +814,7 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
 #ifndef AP_QAGI_MINBLOCKS
 #define AP_QAGI_MINBLOCKS 6
 #endif
-template <int KIND>
+template <int KIND, int FAST>
 __global__ void __launch_bounds__(AP_QAGI_THREADS, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64_t n, const double* p0, const double* p1,
                                                                            const double* p2, int32_t ns, const double* nodes,
                                                                            const int32_t* n_nodes, double* values) {
@@ -821,7 +831,7 @@ __global__ void __launch_bounds__(AP_QAGI_THREADS, AP_QAGI_MINBLOCKS) los_nodes_
   }
   double ctx[kCtx];
   los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
-  values[t] = los_eval<KIND>(ctx, nodes[t]);
+  values[t] = los_eval<KIND, FAST>(ctx, nodes[t]);
 }
 
 extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const double* d_p1, const double* d_p2,
@@ -832,16 +842,23 @@ extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const doubl
   if (n == 0) return 0;
   if (!d_p0 || !d_p1 || (kind != LOS_NFW_RHO && !d_p2) || !d_nodes || !d_n_nodes || !d_values)
     return fail("los_nodes: NULL pointer");
+  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
   int threads = AP_QAGI_THREADS;
   int64_t total = n * n_samples;
   unsigned blocks = (unsigned)((total + threads - 1) / threads);
   cudaStream_t st = (cudaStream_t)stream;
+#define AP_LOS_NODES(K)                                                                                                  \
+  if (g_quad_fast)                                                                                                       \
+    los_nodes_kernel<K, 1><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values);    \
+  else                                                                                                                   \
+    los_nodes_kernel<K, 0><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values)
   switch (kind) {
-    case LOS_B16_TAU: los_nodes_kernel<LOS_B16_TAU><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
-    case LOS_B16_NE: los_nodes_kernel<LOS_B16_NE><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
-    case LOS_B16_RHO_GAS: los_nodes_kernel<LOS_B16_RHO_GAS><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
-    case LOS_NFW_RHO: los_nodes_kernel<LOS_NFW_RHO><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values); break;
+    case LOS_B16_TAU: AP_LOS_NODES(LOS_B16_TAU); break;
+    case LOS_B16_NE: AP_LOS_NODES(LOS_B16_NE); break;
+    case LOS_B16_RHO_GAS: AP_LOS_NODES(LOS_B16_RHO_GAS); break;
+    case LOS_NFW_RHO: AP_LOS_NODES(LOS_NFW_RHO); break;
   }
+#undef AP_LOS_NODES
   AP_LAUNCH_CHECK();
   return 0;
 }
@@ -873,6 +890,7 @@ extern "C" int ap_b16_tau_eval(int64_t n, const double* d_R, const double* d_R_2
   if (n < 0) return fail("n < 0");
   if (n == 0) return 0;
   if (!d_R || !d_R_200c || !d_M_200c || !d_redshift || !d_result) return fail("b16_tau_eval: NULL pointer");
+  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
   int threads = 128;
   b16_tau_eval_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       n, d_R, d_R_200c, d_M_200c, d_redshift, d_result, d_abserr, d_neval);
@@ -1083,6 +1101,7 @@ static int paint_los_items_impl(int kind, int64_t nside, const ap_halos* halos, 
   if (n_items == 0 || halos->n == 0) return 0;
   if (!p0 || !p1 || (kind != LOS_NFW_RHO && !p2) || !item_halo || !item_ord || !d_map)
     return fail("paint_los_items: NULL pointer");
+  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
   unsigned blocks = (unsigned)((n_items + 127) / 128);
   Hpx hpx = disc_hpx(nside);
   HalosDev H = to_dev(halos);
@@ -1128,6 +1147,7 @@ static int paint_los_small_impl(int kind, int64_t nside, const ap_halos* halos, 
   if (halos->n == 0) return 0;
   if (!d_R_200c || !d_M_200c || (kind != LOS_NFW_RHO && !d_redshift) || !d_n_pix || !d_map)
     return fail("paint_los_small: NULL pointer");
+  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
   int threads = 128;
   int64_t blocks = (halos->n * 32 + threads - 1) / threads;
   {

@@ -183,7 +183,7 @@ AP_HD void los_setup(double p0, double p1, double p2, double* ctx) {
   }
 }
 
-template <int KIND>
+template <int KIND, int FAST = 1>
 AP_HD double los_eval(const double* ctx, double R, QagiResult* info = nullptr) {
   QagiResult q;
   if (KIND == LOS_NFW_RHO) {
@@ -191,14 +191,14 @@ AP_HD double los_eval(const double* ctx, double R, QagiResult* info = nullptr) {
     f.K8 = ctx[0];
     f.rs = ctx[1];
     f.RR = AP_MUL(R, R);
-    q = qagi_upper(f, R, 0.0, 1.0e-2);
+    q = qagi_upper_auto<decltype(f), FAST>(f, R, 0.0, 1.0e-2);
   } else {
     B16Integrand f;
     f.inv_R200xc = ctx[0];
     f.alpha = ctx[1];
     f.expo = ctx[2];
     f.RR = AP_MUL(R, R);
-    q = qagi_upper(f, R, 0.0, 1.0e-2);  // utils.py:448
+    q = qagi_upper_auto<decltype(f), FAST>(f, R, 0.0, 1.0e-2);  // utils.py:448
     const double K2 = 2.0 * ctx[3];
     q.result = AP_MUL(q.result, K2);
     q.abserr = AP_MUL(q.abserr, K2);
@@ -213,7 +213,7 @@ AP_HD double b16_tau_2D(const double* ctx, double R, QagiResult* info = nullptr)
   f.alpha = ctx[1];
   f.expo = ctx[2];
   f.RR = AP_MUL(R, R);
-  QagiResult q = qagi_upper(f, R, 0.0, 1.0e-2);  // utils.py:448
+  QagiResult q = qagi_upper_auto(f, R, 0.0, 1.0e-2);  // utils.py:448
   const double K2 = 2.0 * ctx[3];
   q.result = AP_MUL(q.result, K2);
   q.abserr = AP_MUL(q.abserr, K2);

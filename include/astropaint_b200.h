@@ -73,6 +73,11 @@ int ap_catalog_build(int64_t n, const double* d_x, const double* d_y, const doub
                      const double* d_vy, const double* d_vz, const double* d_M_200c, const double* d_redshift,
                      double default_redshift, double crit_dens_0, double h, double* const* h_out, void* stream);
 
+/* ap_los_nodes integrates with the rightmost-bisection fast path of dqagie (bit-identical to the general
+ * routine whenever it accepts a quadrature, general routine otherwise).  enable = 0 forces the general routine
+ * (used by the parity tests), 1 restores the default, negative only queries.  Returns the previous setting.  */
+int ap_quad_fast_path(int enable);
+
 /* Disc-query mode of the calling thread, honoured by every entry point below that runs a disc query
  * (count, pixels, paint, LOS bypass): 0 = hp.query_disc(..., inclusive=False), the Canvas default
  * (paint_bucket.py:782, :1228); f > 0 = inclusive=True with healpy's oversampling factor f (healpy's own

@@ -861,3 +861,31 @@ def test_stack_with_library_apply_funcs_stays_on_device(cats):
     assert np.abs(got - want).max() <= 1e-11 * scale
     assert canvas._patch_plan([lambda p: p], [{}], 48, 48) is None      # unknown callables keep the host loop
 
+
+def test_quadrature_fast_path_equals_general_routine_on_device():
+    """ap_los_nodes with the rightmost-bisection fast path == the general dqagie kernel, bit for bit, on every
+    (halo, node) of a Websky-shaped catalog and for all four LOS integrands."""
+    import torch
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic, _engine as eng, _capi
+    cat = ap.Catalog(synthetic.websky_like(30_000, seed=4))
+    dev = torch.device("cuda", 0)
+    halos = eng.DeviceHalos(cat.data, 5, dev)
+    n_pix, _, rmin, rmax = eng.disc_count(halos, 8192, want_range=True)
+    L = _capi.lib()
+    for kind, names, method in [("b16_tau", ("R_200c", "M_200c", "redshift"), "linspace"),
+                                ("b16_ne", ("R_200c", "M_200c", "redshift"), "linspace"),
+                                ("b16_rho_gas", ("R_200c", "M_200c", "redshift"), "linspace"),
+                                ("nfw_rho", ("rho_s", "R_s"), "logspace")]:
+        cols = [eng.to_device(cat.data[c].to_numpy(), dev) for c in names]
+        nodes, n_nodes = eng.table_nodes(halos, n_pix, rmin, rmax, 15, method)
+        try:
+            assert L.ap_quad_fast_path(1) in (0, 1)
+            fast = eng.los_nodes(kind, halos, cols, nodes, n_nodes).cpu().numpy()
+            L.ap_quad_fast_path(0)
+            general = eng.los_nodes(kind, halos, cols, nodes, n_nodes).cpu().numpy()
+        finally:
+            L.ap_quad_fast_path(1)
+        assert np.isfinite(general).all() and np.abs(general).max() > 0
+        assert np.array_equal(fast, general), kind
+

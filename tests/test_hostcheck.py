@@ -30,6 +30,10 @@ def hc():
     L.hc_critical_density.argtypes = [d]
     L.hc_b16_tau_3D.restype = d
     L.hc_b16_tau_3D.argtypes = [d, d, d, d]
+    L.hc_los_fast_path.restype = C.c_int
+    L.hc_los_fast_path.argtypes = [C.c_int, d, d, d, d, C.POINTER(d), C.POINTER(d), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.hc_los.restype = C.c_int
+    L.hc_los.argtypes = [C.c_int, d, d, d, d, C.POINTER(d), C.POINTER(C.c_int)]
     L.hc_profile_R.argtypes = [C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p]
     L.hc_profile_vec.argtypes = [C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p]
     L.hc_spline.argtypes = [C.c_int, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p]
@@ -289,3 +293,44 @@ def test_disc_edge_cases_bit_exact(hc, nside):
             assert np.array_equal(buf[:n], want), (nside, c, r)
             n_cases += 1
     assert n_cases > 300
+
+
+def test_rightmost_fast_path_is_bit_identical_to_dqagie(hc):
+    """qagi_upper_rm (the rightmost-bisection specialisation of dqagie, csrc/qagi.cuh) against scipy.integrate.quad
+    -- the reference's LOS_integrate (lib/utils.py:448) -- on Websky-shaped halos x 15 linspace nodes plus
+    degenerate R: wherever it accepts a quadrature, neval equals scipy's and the value agrees to 1e-7 (the bar
+    of the general restatement); it must accept nearly all of them; and the public entry (fast path + general
+    fallback) must give neval == scipy everywhere."""
+    from scipy import integrate
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    ap.paint_bucket.verbose = False
+    D = ap.Catalog(synthetic.websky_like(400, seed=2), device=False).data
+    rng = np.random.default_rng(1)
+    pix = np.sqrt(4 * np.pi / (12 * 8192 ** 2))
+    n_acc = n_tot = 0
+    import warnings
+    for i in range(120):
+        rad = 5 * np.deg2rad(D.R_ang_200c[i] / 60)
+        Rs = list(np.linspace(D.D_a[i] * pix * 0.3 * rng.random(), D.D_a[i] * rad, 15))
+        if i % 10 == 0:
+            Rs += [1e-9, 1e-5 * D.R_200c[i], 50 * D.R_200c[i]]
+        for R in Rs[::3] if i % 4 else Rs:
+            args = (float(D.R_200c[i]), float(D.M_200c[i]), float(D.redshift[i]))
+            r1, e1, n1, i1 = d(), d(), C.c_int(), C.c_int()
+            ok = hc.hc_los_fast_path(0, R, *args, C.byref(r1), C.byref(e1), C.byref(n1), C.byref(i1))
+            r3, n3 = d(), C.c_int()
+            hc.hc_los(0, R, *args, C.byref(r3), C.byref(n3))
+            f = lambda r: oprof.b16_tau_3D(r, *args) * 2. * r / np.sqrt(r ** 2 - R ** 2)  # noqa: E731
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                v, e, info = integrate.quad(f, R, np.inf, epsabs=0., epsrel=1.e-2, full_output=1)[:3]
+            assert n3.value == info["neval"] and abs(r3.value - v) <= 1e-7 * abs(v)
+            n_tot += 1
+            if ok:
+                n_acc += 1
+                assert n1.value == info["neval"], (i, R, n1.value, info["neval"])
+                assert r1.value == r3.value            # the public entry returned the fast path's bits
+                assert abs(e1.value - e) <= 1e-3 * abs(e) + 1e-300
+    assert n_acc >= 0.97 * n_tot, (n_acc, n_tot)
+
