@@ -374,7 +374,7 @@ struct PaintShared {
 // the span lengths gives the flat pixel numbering; phase 2 walks the pixels with consecutive lanes
 // on consecutive pixels of a ring (sector-coalesced fp64 RED traffic), evaluates separation,
 // template and accumulates.  No work list ever touches HBM.
-template <int P, class MapT>
+template <int P, class MapT, bool INCL>
 __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
                                                                StatsArgs st, int halos_per_block,
                                                                MapT* __restrict__ map,
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
   // phase 0
   if (tid < G) {
     int64_t h = h0 + tid;
-    DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+    DiscHeader d = disc_header_t<INCL>(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
     if (P == P_TABLE && tab.n_nodes[h] == 0) {  // bypass halo: painted elsewhere
       d.ir_first = 1;
       d.ir_last = 0;
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       d.phi = hh.phi; d.z0 = hh.z0; d.xa = hh.xa; d.cosr = hh.cosr; d.cosrs = hh.cosrs;
       d.irmin = hh.irmin; d.irmax = hh.irmax; d.ir_first = hh.ir_first; d.ir_last = hh.ir_last;
       int64_t iz = d.ir_first + (it - sm.ring_off[lo]);
-      RingSpan s = ring_span(hpx, d, iz);
+      RingSpan s = ring_span_t<INCL>(hpx, d, iz);
       len = s.len;
       RingItem& r = sm.item[tid];
       r.len = s.len;
@@ -652,12 +652,20 @@ static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& p
   StatsArgs st;
   memset(&st, 0, sizeof(st));
   if (stats) st = *stats;
-  if (f32 && P != P_STATS)
-    paint_kernel<P, float><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(
-        disc_hpx(nside), to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
-  else
-    paint_kernel<P, double><<<(unsigned)blocks, kPaintThreads, 0, (cudaStream_t)stream>>>(
-        disc_hpx(nside), to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+  const Hpx hpx = disc_hpx(nside);
+  const unsigned nb = (unsigned)blocks;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (f32 && P != P_STATS) {
+    if (hpx.incl_fct)
+      paint_kernel<P, float, true><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+    else
+      paint_kernel<P, float, false><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+  } else {
+    if (hpx.incl_fct)
+      paint_kernel<P, double, true><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+    else
+      paint_kernel<P, double, false><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+  }
   AP_LAUNCH_CHECK();
   return 0;
 }

@@ -372,7 +372,10 @@ def test_c_abi_error_codes_and_host_entry(cats):
     n_pix = torch.empty(halos.n, dtype=torch.int64, device=dev)
     assert L.ap_disc_count(0, C.byref(s), 0, _capi.ptr(n_pix), None, None, None, None) != 0
     assert b"nside" in L.ap_last_error()
-    assert L.ap_disc_count(64, C.byref(s), 1, _capi.ptr(n_pix), None, None, None, None) != 0
+    n_inc = torch.empty_like(n_pix)                                        # inclusive != 0: healpy's inclusive query
+    assert L.ap_disc_count(64, C.byref(s), 1, _capi.ptr(n_inc), None, None, None, None) == 0
+    assert L.ap_disc_count(64, C.byref(s), 0, _capi.ptr(n_pix), None, None, None, None) == 0
+    assert bool((n_inc >= n_pix).all()) and bool((n_inc > n_pix).any())
     assert L.ap_disc_count(64, C.byref(s), 0, None, None, None, None, None) != 0
     d_map = torch.zeros(12 * 64 * 64, dtype=torch.float64, device=dev)
     assert L.ap_paint_profile(3, 64, C.byref(s), None, None, 2, _capi.ptr(d_map), None, None) != 0
