@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "healpix.cuh"
+#include "fastmath.cuh"
 
 namespace ap {
 
@@ -71,36 +72,77 @@ AP_HD int32_t span_j_of_ip(const RingSpan& s, int32_t ip) {
   return j >= s.nr ? j - s.nr : j;
 }
 
+// The per-pixel geometry below is CALL-FREE on the device: no libdevice sin / asin / sqrt / rsqrt / division,
+// whose out-of-line slow paths put CALLs into the painter's pixel loop -- after every call site ptxas
+// rematerialises the loop's fp64 constants (265 UMOVs in the phase-2 loop of paint_kernel<P_TABLE>, SASS in
+// profiles/).  Accuracy stays at a few ulp (tests/test_hostcheck.py runs the same code on the host).
+
+// sin(x) for |x| <= pi/4: Taylor series to x^17 (next term (pi/4)^19 / 19! = 8e-20)
+AP_HD double sin_quarter(double x) {
+  const double x2 = x * x;
+  double p = 1.0 / 355687428096000.0;
+  p = p * x2 - 1.0 / 1307674368000.0;
+  p = p * x2 + 1.0 / 6227020800.0;
+  p = p * x2 - 1.0 / 39916800.0;
+  p = p * x2 + 1.0 / 362880.0;
+  p = p * x2 - 1.0 / 5040.0;
+  p = p * x2 + 1.0 / 120.0;
+  p = p * x2 - 1.0 / 6.0;
+  return x + x * (x2 * p);
+}
+
 // sin^2(d / 2); small arguments (every disc that is not polar or sky-sized) take a 5-term series
 AP_HD double sin2_half(double d) {
   double x = 0.5 * d, s;
   if (fabs(x) < 0.125) {
     double x2 = x * x;  // next term x^10 / 39916800 < 2.4e-17 relative
     s = x * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0 + x2 * (-1.0 / 5040.0 + x2 * (1.0 / 362880.0)))));
-  } else {
-    s = sin(x);
+    return s * s;
   }
+  // sin^2 has period pi: fold x into [-pi/2, pi/2], then sin^2(x) = 1 - sin^2(pi/2 - |x|) above pi/4
+  x = x - kPi * rint(x * (1.0 / kPi));
+  const double ax = fabs(x);
+  if (ax > 0.25 * kPi) {
+    s = sin_quarter(kHalfPi - ax);
+    return 1.0 - s * s;
+  }
+  s = sin_quarter(ax);
   return s * s;
 }
 
 AP_HD double hav_of(const RingGeom& g, int32_t j) { return g.A + g.B * sin2_half(g.d0 + (double)j * g.phi_step); }
 
+// asin(x) for 0 <= x <= 1/2: x + x R(x^2), the rational approximation of fdlibm's e_asin.c (|error| < 2^-58)
+AP_HD double asin_half(double x) {
+  const double t = x * x;
+  const double p = t * (1.66666666666666657415e-01 + t * (-3.25565818622400915405e-01 + t * (2.01212532134862925881e-01 +
+                   t * (-4.00555345006794114027e-02 + t * (7.91534994289814532176e-04 + t * 3.47933107596021167570e-05)))));
+  const double q = 1.0 + t * (-2.40339491173441421878e+00 + t * (2.02094576023350569471e+00 +
+                   t * (-6.88283971605453293030e-01 + t * 7.70381505559019352791e-02)));
+  return x + x * (p * fm_rcp(q));
+}
+
+// 2 asin(sqrt(u)) for 0 < u <= 1/2 (normal u): direct below u = 1/4, else through
+// asin(s) = pi/2 - 2 asin(sqrt((1 - s) / 2)) so that asin_half always sees an argument <= 1/2
+AP_HD double two_asin_sqrt(double u) {
+  const double s = u * fm_rsqrt(u);
+  if (u <= 0.25) return 2.0 * asin_half(s);
+  const double w = 0.5 * (1.0 - s);
+  return kPi - 4.0 * asin_half(w * fm_rsqrt(w));
+}
+
 // separation [rad] from its haversine: theta = 2 asin(sqrt(hav)); series below hav = 1e-4
 AP_HD double sep_from_hav(double hav) {
   if (hav < 1.0e-4) {
-    if (!(hav > 0.0)) return 0.0;
-#if defined(__CUDA_ARCH__)
-    double sq = hav * rsqrt(hav);
-#else
-    double sq = sqrt(hav);
-#endif
+    if (!(hav > 1.0e-290)) return 0.0;   // hav is 0 or >= ~1e-35 by construction; keeps fm_rsqrt on normal numbers
+    double sq = hav * fm_rsqrt(hav);
     // asin(s)/s = 1 + h/6 + 3h^2/40 + 15h^3/336 + 105h^4/3456 + ..., h = s^2 (next term < 3e-22)
     return 2.0 * sq * (1.0 + hav * (1.0 / 6.0 + hav * (3.0 / 40.0 + hav * (15.0 / 336.0 + hav * (105.0 / 3456.0)))));
   }
-  if (hav < 0.5) return 2.0 * asin(sqrt(hav));
+  if (hav <= 0.5) return two_asin_sqrt(hav);
   double co = 1.0 - hav;
-  if (co < 0.0) co = 0.0;
-  return kPi - 2.0 * asin(sqrt(co));
+  if (!(co > 1.0e-290)) return kPi;
+  return kPi - two_asin_sqrt(co);
 }
 
 // angular separation [rad] between span pixel j of the ring and the halo centre

@@ -57,6 +57,14 @@ int64_t hc_query_disc_inclusive(int64_t nside, double x, double y, double z, dou
 
 double hc_max_pixrad(int64_t nside) { return max_pixrad(nside); }
 
+// the call-free per-pixel geometry of geom.cuh: sin^2(d/2) and the separation 2 asin(sqrt(hav))
+void hc_geom_funcs(int64_t n, const double* d, const double* hav, double* s2, double* sep) {
+  for (int64_t i = 0; i < n; ++i) {
+    if (s2) s2[i] = sin2_half(d[i]);
+    if (sep) sep[i] = sep_from_hav(hav[i]);
+  }
+}
+
 // per-halo pixel count and sum of pixel ids for n halos (near-tie scans against the device)
 void hc_query_disc_stats(int64_t nside, int64_t n, const double* x, const double* y, const double* z,
                          const double* radius, int64_t* count, int64_t* pixsum) {

@@ -4,6 +4,7 @@
 // cubic) through n_samples nodes and evaluates it on the halo's pixels.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace ap {
 
@@ -54,7 +55,8 @@ AP_HD_NOINLINE void spline_build_nak(int n, const double* x, const double* y, do
 
 // interval i with x_i <= X < x_{i+1} (clamped): uniform guess, then fix up (nodes may be log-spaced)
 AP_HD int spline_interval(int n, const double* x, double X) {
-  int i = (int)((X - x[0]) / (x[n - 1] - x[0]) * (double)(n - 1));
+  // a guess only (the loops below fix it up): reciprocal instead of a division keeps the painter's pixel loop call-free
+  int i = (int)((X - x[0]) * fm_rcp(x[n - 1] - x[0]) * (double)(n - 1));
   if (i < 0) i = 0;
   if (i > n - 2) i = n - 2;
   while (i > 0 && X < x[i]) --i;

@@ -334,3 +334,26 @@ def test_rightmost_fast_path_is_bit_identical_to_dqagie(hc):
                 assert abs(e1.value - e) <= 1e-3 * abs(e) + 1e-300
     assert n_acc >= 0.97 * n_tot, (n_acc, n_tot)
 
+
+def test_call_free_pixel_geometry(hc):
+    """geom.cuh: sin^2(d/2) (series / folded Taylor) and 2 asin(sqrt(hav)) (series / fdlibm rational) against
+    numpy over their whole domains: a few ulp, far inside the 1e-6 map bar"""
+    hc.hc_geom_funcs.argtypes = [i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    dd = np.concatenate([rng.uniform(-3 * np.pi, 3 * np.pi, 200000), rng.uniform(-0.3, 0.3, 100000),
+                         10.0 ** rng.uniform(-12, 0, 50000), [0.0, np.pi, -np.pi, np.pi / 2, 0.25, -0.25, 2 * np.pi]])
+    hav = np.concatenate([rng.uniform(0, 1, 200000), 10.0 ** rng.uniform(-30, 0, 100000),
+                          1.0 - 10.0 ** rng.uniform(-16, 0, 50000), [0.0, 1.0, 0.25, 0.5, 1e-4, 0.9999]])
+    n = min(len(dd), len(hav))
+    dd, hav = np.ascontiguousarray(dd[:n]), np.ascontiguousarray(hav[:n])
+    s2, sep = np.empty(n), np.empty(n)
+    hc.hc_geom_funcs(n, _p(dd), _p(hav), _p(s2), _p(sep))
+    want_s2 = np.sin(0.5 * dd) ** 2
+    assert np.abs(s2 - want_s2).max() <= 1e-15                      # absolute (values in [0, 1])
+    small = np.abs(dd) < 0.25
+    assert (np.abs(s2[small] - want_s2[small]) <= 1e-15 * want_s2[small] + 1e-300).all()
+    want_sep = 2.0 * np.arctan2(np.sqrt(hav), np.sqrt(1.0 - hav))   # = 2 asin(sqrt(hav)), accurate at both ends
+    ok = hav > 0
+    assert (np.abs(sep[ok] - want_sep[ok]) <= 2e-15 * want_sep[ok] + 1e-15).all()   # near pi: pi - small, absolute
+    assert sep[hav == 0.0].max() == 0.0
+
