@@ -432,6 +432,15 @@ def stack_cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize, we
     return stack
 
 
+def ud_grade(d_map, nside_in, nside_out, pess=False, power=None):
+    """healpy.ud_grade of a device RING map (fp64) -> new device map at nside_out"""
+    d_map = d_map if d_map.dtype == torch.float64 else d_map.double()
+    out = torch.empty(12 * nside_out * nside_out, dtype=torch.float64, device=d_map.device)
+    check(_capi.lib().ap_ud_grade(nside_in, ptr(d_map), nside_out, int(bool(pess)), float(power or 0.0),
+                                  int(bool(power)), ptr(out), stream_ptr()))
+    return out
+
+
 def _win(win, dev):
     if win is None:
         return None, None

@@ -209,3 +209,69 @@ extern "C" int ap_patch_scale(int64_t n, int32_t ysize, int32_t xsize, double* d
   AP_LAUNCH_CHECK();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Map sink: Canvas.ud_grade (paint_bucket.py:2233-2257) = healpy.ud_grade(RING map, nside_out, pess, power).
+// healpy reorders to NEST, averages (degrade) the good children of each parent or replicates (upgrade) the
+// parent, and reorders back; NEST children of a parent are the (ix, iy) block of its face, so one thread per
+// OUTPUT ring pixel walks that block through ring2xyf / xyf2ring (healpix.cuh) -- no reordered copy of the map.
+// ------------------------------------------------------------------------------------------
+namespace patchops {
+
+constexpr double kUnseen = -1.6375e30;
+
+__device__ __forceinline__ bool ud_bad(double v) {
+  return fabs(v - kUnseen) <= 1.0e-8 + 1.0e-5 * 1.6375e30 || !isfinite(v);
+}
+
+__global__ void __launch_bounds__(256) ud_grade_kernel(ap::Hpx hin, ap::Hpx hout, const double* __restrict__ map_in,
+                                                       double* __restrict__ map_out, int pess, double power_fact) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hout.npix) return;
+  int64_t ix, iy;
+  int face;
+  ap::ring2xyf(hout, p, ix, iy, face);
+  if (hin.nside > hout.nside) {  // degrade: children in NEST (Morton) order, as healpy's reshape(npix_out, rat2) sums them
+    const int64_t r = hin.nside / hout.nside;
+    const int64_t rat2 = r * r;
+    double sum = 0.0;
+    int64_t nhit = 0;
+    for (int64_t c = 0; c < rat2; ++c) {
+      int64_t dx = 0, dy = 0;
+      for (int b = 0; (int64_t(1) << b) < r; ++b) {
+        dx |= ((c >> (2 * b)) & 1) << b;
+        dy |= ((c >> (2 * b + 1)) & 1) << b;
+      }
+      const double v = __ldg(map_in + ap::xyf2ring(hin, ix * r + dx, iy * r + dy, face));
+      if (!ud_bad(v)) {
+        sum += v;
+        ++nhit;
+      }
+    }
+    const bool badout = pess ? (nhit != rat2) : (nhit == 0);
+    double hits = (double)nhit;
+    if (power_fact != 1.0) hits = hits / power_fact;   // nhit / ratio**power
+    map_out[p] = badout ? kUnseen : (nhit ? sum / hits : sum);
+  } else {                       // upgrade (or copy): the parent's value times ratio**power
+    const int64_t r = hout.nside / hin.nside;
+    map_out[p] = __ldg(map_in + ap::xyf2ring(hin, ix / r, iy / r, face)) * power_fact;
+  }
+}
+
+}  // namespace patchops
+
+extern "C" int ap_ud_grade(int64_t nside_in, const double* d_map_in, int64_t nside_out, int pess, double power,
+                           int use_power, double* d_map_out, void* stream) {
+  if (check_nside(nside_in) || check_nside(nside_out)) return 1;
+  if ((nside_in & (nside_in - 1)) || (nside_out & (nside_out - 1)))
+    return fail("ud_grade: healpy degrades through NEST ordering, both nside must be powers of two");
+  if (!d_map_in || !d_map_out) return fail("ud_grade: NULL map");
+  const ap::Hpx hin = ap::make_hpx(nside_in), hout = ap::make_hpx(nside_out);
+  const double ratio = (double)nside_out / (double)nside_in;
+  const double pf = use_power ? pow(ratio, power) : 1.0;
+  patchops::ud_grade_kernel<<<(unsigned)((hout.npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hin, hout, d_map_in,
+                                                                                                  d_map_out, pess, pf);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+

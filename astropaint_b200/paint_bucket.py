@@ -385,6 +385,40 @@ class Canvas:
         self._state = "device"
         return self._dmap
 
+    # ---- map sinks ---------------------------------------------------------------
+    def ud_grade(self, nside_out, inplace=True, **kwargs):
+        """healpy.ud_grade of canvas.pixels on the device (reference: paint_bucket.py:2233-2257).  kwargs: `pess`,
+        `power` (healpy's); RING in and out.  inplace=True also switches the canvas to nside_out."""
+        unknown = set(kwargs) - {"pess", "power"}
+        if unknown:
+            raise TypeError(f"ud_grade() got unsupported healpy arguments {sorted(unknown)}")
+        new_map = eng.ud_grade(self.pixels_device, self.nside, int(nside_out), kwargs.get("pess", False),
+                               kwargs.get("power", None))
+        if self.accumulate == "fp32":
+            new_map = new_map.float()
+        if not inplace:
+            return new_map.cpu().numpy()
+        self._cancel_prefetch()
+        self._nside = int(nside_out)
+        self._npix = 12 * self._nside * self._nside
+        self._lmax = 3 * self._nside - 1
+        self._dmap, self._dmap_spare, self._host_buf, self._pixels = new_map, None, None, None
+        self._state = "device"
+        self.discs = self.Disc(self.catalog, self.nside, self.R_times, self.inclusive)
+        self._mark_painted()
+
+    def discs_coverage(self):
+        """The 0/1 map Canvas.show_discs draws (paint_bucket.py:1433-1458: junk_pixels[disc] = 1 for every halo's
+        disc), built on the device; plotting itself is outside the path."""
+        import torch
+        dev = eng.require_cuda()
+        halos = eng.DeviceHalos(self.catalog.data, self.R_times, dev)
+        cover = torch.zeros(self.npix, dtype=torch.float64, device=dev)
+        one = torch.ones(1, dtype=torch.float64, device=dev)
+        with eng.disc_mode(self.inclusive):
+            eng.paint_profile(halos, self.nside, 0, [one], cover)      # AP_CONSTANT: hits per pixel
+        return (cover > 0).to(torch.float64).cpu().numpy()
+
     def _mark_painted(self):
         # the reference's serial spray leaves alm/Cl flags untouched (:2387) while the threaded one
         # goes through the setter (:2433); a drop-in marks them stale in both cases.

@@ -238,6 +238,13 @@ int ap_patch_rotate(int64_t n, int32_t ysize, int32_t xsize, const double* d_coe
 int ap_patch_scale(int64_t n, int32_t ysize, int32_t xsize, double* d_patches, const double* d_win_y,
                    const double* d_win_x, const double* d_weight, double* d_stack, void* stream);
 
+/* Canvas.ud_grade (paint_bucket.py:2233-2257) = healpy.ud_grade(map, nside_out, pess, power) for RING maps:
+ * degrade = mean over the good (not UNSEEN, finite) NEST children of each parent (UNSEEN if none is good, or if
+ * any is bad when pess != 0), upgrade = the parent's value; times (nside_out / nside_in)**power when
+ * use_power != 0.  Both nside powers of two.  d_map_out holds 12 nside_out^2 doubles.                        */
+int ap_ud_grade(int64_t nside_in, const double* d_map_in, int64_t nside_out, int pess, double power, int use_power,
+                double* d_map_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

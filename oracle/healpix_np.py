@@ -586,3 +586,59 @@ def cartesian_projmap(hpx, healpix_map, lon_deg, lat_deg, lonra, latra, xsize, y
     vs = np.tensordot(m, v, axes=(1, 0))
     pix = hpx.vec2pix(vs[0], vs[1], vs[2])
     return np.asarray(healpix_map)[pix]
+
+
+# ---------------------------------------------------------------------------------
+# healpy.pixelfunc.ud_grade (RING in, RING out, power-of-two nsides)
+# ---------------------------------------------------------------------------------
+UNSEEN = -1.6375e30
+
+
+def ring2nest(hp, pix):
+    """T_Healpix_Base::ring2nest = xyf2nest(ring2xyf): nest index = face * nside^2 + Morton(ix, iy)."""
+    ix, iy, face = hp.ring2xyf(int(pix))
+    m = 0
+    for b in range(hp.nside.bit_length()):
+        m |= ((ix >> b) & 1) << (2 * b)
+        m |= ((iy >> b) & 1) << (2 * b + 1)
+    return face * hp.nside * hp.nside + m
+
+
+def ud_grade(map_in, nside_out, pess=False, power=None):
+    """healpy.ud_grade(map_in, nside_out, pess=False, order_in='RING', power=None) as the reference's
+    Canvas.ud_grade calls it (paint_bucket.py:2233-2257): reorder to NEST, then (degrade) average the good
+    children of every parent -- UNSEEN / non-finite children are skipped, a parent with no good child
+    (pess: with any bad child) becomes UNSEEN -- or (upgrade) replicate the parent; reorder back to RING."""
+    map_in = np.asarray(map_in, dtype=np.float64)
+    nside_in = int(round(math.sqrt(len(map_in) / 12)))
+    assert 12 * nside_in * nside_in == len(map_in)
+    for ns in (nside_in, nside_out):
+        assert ns > 0 and (ns & (ns - 1)) == 0, "ud_grade goes through NEST ordering: power-of-two nside"
+    hin, hout = HealpixRing(nside_in), HealpixRing(nside_out)
+    r2n_in = np.array([ring2nest(hin, p) for p in range(hin.npix)])
+    r2n_out = np.array([ring2nest(hout, p) for p in range(hout.npix)])
+    nest_in = np.empty_like(map_in)
+    nest_in[r2n_in] = map_in
+    if nside_out < nside_in:
+        rat2 = hin.npix // hout.npix
+        ratio = nside_out / nside_in
+        mr = nest_in.reshape(hout.npix, rat2)
+        bad = (np.abs(mr - UNSEEN) <= 1e-8 + 1e-5 * abs(UNSEEN)) | ~np.isfinite(mr)
+        goods = ~bad
+        out = np.sum(np.where(goods, mr, 0.0), axis=1)
+        nhit = goods.sum(axis=1).astype(np.float64)
+        badout = (nhit != rat2) if pess else (nhit == 0)
+        if power:
+            nhit = nhit / ratio ** power
+        nz = nhit != 0
+        out[nz] = out[nz] / nhit[nz]
+        out[badout] = UNSEEN
+        nest_out = out
+    elif nside_out > nside_in:
+        rat2 = hout.npix // hin.npix
+        fact = (nside_out / nside_in) ** power if power else 1.0
+        nest_out = np.repeat(nest_in * fact, rat2)
+    else:
+        nest_out = nest_in
+    return nest_out[r2n_out]
+

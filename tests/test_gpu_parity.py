@@ -892,3 +892,39 @@ def test_quadrature_fast_path_equals_general_routine_on_device():
         assert np.isfinite(general).all() and np.abs(general).max() > 0
         assert np.array_equal(fast, general), kind
 
+
+# ------------------------------------------------------------------ map sinks
+def test_ud_grade_and_coverage_match_oracle(cats):
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import spherical
+    ref, _, ohp = _oracle()
+    cat = cats["box"]
+    canvas = ap.Canvas(cat, 32, R_times=3)
+    ap.Painter(spherical.gaussian_2D).spray(canvas)
+    pixels = canvas.pixels.copy()
+    for nside_out, kw in [(8, {}), (16, {"power": -2}), (64, {}), (128, {"power": 1}), (32, {}), (4, {"pess": True})]:
+        got = canvas.ud_grade(nside_out, inplace=False, **kw)
+        want = ohp.ud_grade(pixels, nside_out, **kw)
+        map_close(got, want, 1e-12)
+    holed = pixels.copy()
+    holed[::7] = ohp.UNSEEN
+    canvas.pixels = holed
+    for pess in (False, True):
+        got = canvas.ud_grade(8, inplace=False, pess=pess)
+        want = ohp.ud_grade(holed, 8, pess=pess)
+        assert np.array_equal(got == ohp.UNSEEN, want == ohp.UNSEEN)
+        ok = want != ohp.UNSEEN
+        assert np.abs(got[ok] - want[ok]).max() <= 1e-12 * np.abs(want[ok]).max()
+    canvas.pixels = pixels
+    canvas.ud_grade(16)                                   # in place: the canvas itself changes resolution
+    assert canvas.nside == 16 and canvas.npix == 12 * 256 and canvas.lmax == 47 and len(canvas.pixels) == 12 * 256
+    map_close(canvas.pixels, ohp.ud_grade(pixels, 16), 1e-12)
+    # show_discs' coverage map (paint_bucket.py:1433-1458) for both disc-query modes
+    for inclusive in (False, True):
+        c2 = ap.Canvas(cat, 32, R_times=2, inclusive=inclusive)
+        discs = ref.Discs(cat.data, 32, 2, inclusive=inclusive)
+        want = np.zeros(c2.npix)
+        for h in range(len(cat.data)):
+            want[discs.pixel_index(h)] = 1
+        assert np.array_equal(c2.discs_coverage(), want)
+

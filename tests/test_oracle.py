@@ -227,3 +227,29 @@ def test_patch_rotate_restatement_is_scipy_rotate(shape):
         from astropaint_b200.lib import transform
         assert np.array_equal(P.taper_patch(p), transform.taper_patch(p.copy()))
 
+
+def test_ud_grade_restatement_by_construction():
+    """oracle ud_grade (healpy.ud_grade as Canvas.ud_grade calls it, paint_bucket.py:2233-2257; unpinned): ring2nest
+    is a bijection, the children of a parent tile the parent (their mean direction is the parent's centre),
+    degrade(upgrade(m)) == m, means are preserved, UNSEEN children are skipped / poison under pess."""
+    hp8, hp4 = H.HealpixRing(8), H.HealpixRing(4)
+    nest = np.array([H.ring2nest(hp8, p) for p in range(hp8.npix)])
+    assert np.array_equal(np.sort(nest), np.arange(hp8.npix))
+    x, y, z = hp8.pix2vec(np.arange(hp8.npix))
+    x4, y4, z4 = hp4.pix2vec(np.arange(hp4.npix))
+    for fine, coarse in ((x, x4), (y, y4), (z, z4)):
+        assert np.abs(H.ud_grade(fine, 4) - coarse).max() < 0.02       # pixel size at nside 4 is 0.25 rad
+    rng = np.random.default_rng(0)
+    m = rng.normal(size=hp4.npix)
+    up = H.ud_grade(m, 16)
+    assert np.array_equal(np.sort(np.unique(up)), np.sort(m)) and len(up) == 12 * 256
+    assert np.allclose(H.ud_grade(up, 4), m, rtol=0, atol=1e-15)
+    fine = rng.normal(size=hp8.npix)
+    assert abs(H.ud_grade(fine, 2).mean() - fine.mean()) < 1e-15
+    holed = fine.copy()
+    holed[rng.integers(0, hp8.npix, 40)] = H.UNSEEN
+    d = H.ud_grade(holed, 4)
+    dp = H.ud_grade(holed, 4, pess=True)
+    assert (d != H.UNSEEN).all() and (dp == H.UNSEEN).sum() >= 10
+    assert np.allclose(H.ud_grade(m, 8, power=-2), H.ud_grade(m, 8) * 2.0 ** -2)
+
