@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE — CPU oracle, never imported by the product path.
 
 numpy/scipy restatement of the reference's templates and decorators, each function citing
-the reference lines it follows.  astropy is absent (parity unpinned for the constants): the
-Planck18_arXiv_v2 cosmology and the CODATA constants are restated from their published values.
+the reference lines it follows.  astropy is absent: the Planck18_arXiv_v2 cosmology and the CODATA
+constants are restated from their published values.  H0 / Om0 / critical density / G enter R_200c, c_200c,
+rho_s, R_s and R_ang_200c, which ARE pinned to ~1e-6 against the real reference's committed notebook output
+(tests/golden/notebook_catalog_head.json); sigma_T, m_p, T_cmb and the Battaglia16 fit stay unpinned.
 
   astropaint/lib/utils.py:406-425   sample_array
   astropaint/lib/utils.py:428-454   LOS_integrate

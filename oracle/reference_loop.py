@@ -1,7 +1,10 @@
 """TEST INFRASTRUCTURE — CPU oracle, never imported by the product path.
 
-Line-by-line CPU restatement of the reference's hot path (parity unpinned: healpy/astropy
-are absent, see oracle/healpix_np.py):
+Line-by-line CPU restatement of the reference's hot path.  Pinning status: build_dataframe IS pinned
+against the real reference (the `catalog.data.head()` output its author committed in
+examples/Birkinshaw_Gull_stacking.ipynb cell 3 -> tests/golden/notebook_catalog_head.json, 12 derived columns
+to printed precision); everything through healpy is parity unpinned (healpy/astropy are absent, see
+oracle/healpix_np.py):
 
   Catalog.build_dataframe      astropaint/paint_bucket.py:308-364 (+ lib/transform.py:49-133,153-179)
   Canvas.Disc generators       astropaint/paint_bucket.py:1175-1290

@@ -928,3 +928,13 @@ def test_ud_grade_and_coverage_match_oracle(cats):
             want[discs.pixel_index(h)] = 1
         assert np.array_equal(c2.discs_coverage(), want)
 
+
+
+def test_device_catalog_build_matches_reference_notebook_output():
+    """ap_catalog_build against the REAL reference's printed output (examples/Birkinshaw_Gull_stacking.ipynb
+    cell 3, tests/golden/notebook_catalog_head.json; tolerance = printed precision, see test_oracle.py)."""
+    import astropaint_b200 as ap
+    from .test_oracle import notebook_head, check_against_notebook
+    g, inp = notebook_head()
+    cat = ap.Catalog(inp.copy(), device=True)
+    check_against_notebook(cat.data, g)

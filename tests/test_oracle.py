@@ -253,3 +253,51 @@ def test_ud_grade_restatement_by_construction():
     assert (d != H.UNSEEN).all() and (dp == H.UNSEEN).sum() >= 10
     assert np.allclose(H.ud_grade(m, 8, power=-2), H.ud_grade(m, 8) * 2.0 ** -2)
 
+
+
+# ------------------------------------------------------------------ the one output of the REAL reference
+NB_GOLD = os.path.join(os.path.dirname(GOLD), "notebook_catalog_head.json")
+NB_INPUTS = ("x", "y", "z", "v_x", "v_y", "v_z", "M_200c", "redshift")
+NB_DERIVED = ("D_c", "lat", "R_200c", "c_200c", "R_ang_200c", "rho_s", "R_s", "v_r", "v_th", "v_ph", "v_lat", "v_lon")
+
+
+def notebook_head():
+    import json
+    import pandas as pd
+    g = json.load(open(NB_GOLD))
+    inp = pd.DataFrame({k: g["values"][k] for k in NB_INPUTS})
+    return g, inp
+
+
+def check_against_notebook(df, g):
+    """Tolerance, written out: the notebook prints inputs with 6-9 significant digits (redshift: 6), so a
+    derived column can only be reproduced to the propagated input rounding (<= 1e-6 relative: rho_c(z) and
+    c_200c(M, z) move by ~1e-6 per 1e-6 in z) plus half a unit of the last printed digit of the output.
+    Velocity components are sums with cancellation: relative to |v|."""
+    vnorm = np.sqrt(df.v_x ** 2 + df.v_y ** 2 + df.v_z ** 2).values
+    for col in NB_DERIVED:
+        want = np.array(g["values"][col])
+        half_ulp = np.array([0.5 * 10.0 ** (-len(t.split("e")[0].split(".")[1])) * (10.0 ** int(t.split("e")[1]) if "e" in t else 1.0)
+                             for t in g["printed"][col]])
+        scale = vnorm if col.startswith("v_") else np.abs(want)
+        err = np.abs(df[col].values - want)
+        assert np.all(err <= 1.5e-6 * scale + half_ulp), (col, err / scale)
+
+
+def test_oracle_catalog_matches_reference_notebook_output():
+    """REAL-reference pin: `catalog.data.head()` of examples/Birkinshaw_Gull_stacking.ipynb cell 3 -- the
+    reference's own Catalog.build_dataframe (paint_bucket.py:308-364; astropy Planck18_arXiv_v2, Dutton-Maccio
+    style c(M, z), cart2sph velocity Jacobian) on five WebSky halos.  Pins the oracle's cosmology constants,
+    R_200c / c_200c / rho_s / R_s / R_ang_200c (hence D_a) and the velocity-component conventions (v_lat = -v_th)."""
+    g, inp = notebook_head()
+    check_against_notebook(ref.build_dataframe(inp.copy()), g)
+
+
+def test_host_catalog_matches_reference_notebook_output():
+    from astropaint_b200 import Catalog
+    g, inp = notebook_head()
+    cat = Catalog(inp.copy(), device=False)
+    check_against_notebook(cat.data, g)
+    cols = list(cat.data.columns)                     # the printed frame: "[5 rows x 24 columns]", 10 + ... + 10
+    assert len(cols) == 24 and cols[:10] == g["columns"][:10] and cols[-10:] == g["columns"][-10:]
+    assert sorted(cols[10:14]) == ["D_a", "lon", "phi", "theta"]
