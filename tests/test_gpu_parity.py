@@ -938,3 +938,13 @@ def test_device_catalog_build_matches_reference_notebook_output():
     g, inp = notebook_head()
     cat = ap.Catalog(inp.copy(), device=True)
     check_against_notebook(cat.data, g)
+
+
+def test_device_ud_grade_reproduces_healpy_docstring_example(cats):
+    """hp.ud_grade(np.arange(48.), 1) from healpy's docstring (tests/golden/healpy_docstring_kat.py): RING
+    numbering, RING<->NEST and the averaging of ap_ud_grade against the published known answer."""
+    import astropaint_b200 as ap
+    from .golden import healpy_docstring_kat as K
+    canvas = ap.Canvas(cats["box"], 2)
+    canvas.pixels = np.arange(48.)
+    assert canvas.ud_grade(1, inplace=False).tolist() == K.UD_GRADE_48_TO_1

@@ -357,3 +357,24 @@ def test_call_free_pixel_geometry(hc):
     assert (np.abs(sep[ok] - want_sep[ok]) <= 2e-15 * want_sep[ok] + 1e-15).all()   # near pi: pi - small, absolute
     assert sep[hav == 0.0].max() == 0.0
 
+
+
+def test_device_header_reproduces_healpy_docstring_examples(hc):
+    """healpix.cuh (host build) on healpy's published docstring examples (tests/golden/healpy_docstring_kat.py)."""
+    from .golden import healpy_docstring_kat as K
+    a = K.VEC2PIX_16
+    x, y, z = (np.array(a[k], dtype=np.float64) for k in "xyz")
+    out = np.empty(2, dtype=np.int64)
+    hc.hc_vec2pix(16, 2, _p(x), _p(y), _p(z), _p(out))
+    assert out.tolist() == a["pix"]
+    a = K.ANG2PIX_16                                   # ang2pix == vec2pix(dir2vec(theta, phi))
+    th, ph = np.array(a["theta"], float), np.array(a["phi"], float)
+    x, y, z = np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)
+    out = np.empty(5, dtype=np.int64)
+    hc.hc_vec2pix(16, 5, _p(x), _p(y), _p(z), _p(out))
+    assert out.tolist() == a["pix"]
+    assert abs(hc.hc_max_pixrad(16) - K.MAX_PIXRAD_16) < 5e-11
+    # pix2vec(16, 1504): a disc of one tenth of a pixel around that direction holds exactly pixel 1504
+    buf = np.empty(16, dtype=np.int64)
+    n = hc.hc_query_disc(16, *K.PIX2VEC_16_1504, 0.005, _p(buf), 16)
+    assert buf[:n].tolist() == [1504]

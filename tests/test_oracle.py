@@ -301,3 +301,40 @@ def test_host_catalog_matches_reference_notebook_output():
     cols = list(cat.data.columns)                     # the printed frame: "[5 rows x 24 columns]", 10 + ... + 10
     assert len(cols) == 24 and cols[:10] == g["columns"][:10] and cols[-10:] == g["columns"][-10:]
     assert sorted(cols[10:14]) == ["D_a", "lon", "phi", "theta"]
+
+
+# ------------------------------------------------------------------ healpy's published docstring examples
+def test_oracle_reproduces_healpy_docstring_examples():
+    """Known-answer pin of the RING scheme restatement: every numeric example of healpy.pixelfunc's public
+    docstrings that touches the functions the path calls (tests/golden/healpy_docstring_kat.py)."""
+    from .golden import healpy_docstring_kat as K
+    hp16 = H.HealpixRing(16)
+    a = K.ANG2PIX_16
+    assert hp16.ang2pix(np.array(a["theta"], float), np.array(a["phi"], float)).tolist() == a["pix"]
+    a = K.PIX2ANG_16
+    th, ph = hp16.pix2ang(np.array(a["pix"]))
+    assert np.abs(th - a["theta"]).max() < 5e-9 and np.abs(ph - a["phi"]).max() < 5e-9
+    th, ph = hp16.pix2ang(np.array([1440]))
+    assert abs(th[0] - K.PIX2ANG_16_1440[0]) < 1e-15 and ph[0] == 0.0
+    a = K.PIX2ANG_PIX11
+    for ns, t, p in zip(a["nside"], a["theta"], a["phi"]):
+        th, ph = H.HealpixRing(ns).pix2ang(np.array([11]))
+        assert abs(th[0] - t) < 5e-9 and abs(ph[0] - p) < 5e-9
+    x, y, z = hp16.pix2vec(np.array([1504]))
+    assert np.abs(np.array([x[0], y[0], z[0]]) - K.PIX2VEC_16_1504).max() < 2e-16
+    a = K.PIX2VEC_16
+    x, y, z = hp16.pix2vec(np.array(a["pix"]))
+    assert max(np.abs(x - a["x"]).max(), np.abs(y - a["y"]).max(), np.abs(z - a["z"]).max()) < 5e-9
+    a = K.PIX2VEC_PIX11
+    for i, ns in enumerate(a["nside"]):
+        x, y, z = H.HealpixRing(ns).pix2vec(np.array([11]))
+        assert max(abs(x[0] - a["x"][i]), abs(y[0] - a["y"][i]), abs(z[0] - a["z"][i])) < 5e-9
+    a = K.VEC2PIX_16
+    assert hp16.vec2pix(np.array(a["x"], float), np.array(a["y"], float), np.array(a["z"], float)).tolist() == a["pix"]
+    assert H.ring2nest(hp16, 1504) == K.RING2NEST_16_1504
+    assert [H.ring2nest(H.HealpixRing(2), i) for i in range(10)] == K.RING2NEST_2
+    assert [H.ring2nest(H.HealpixRing(n), 11) for n in K.RING2NEST_PIX11["nside"]] == K.RING2NEST_PIX11["nest"]
+    assert abs(hp16.max_pixrad() - K.MAX_PIXRAD_16) < 5e-11
+    assert abs(np.sqrt(4 * np.pi / H.nside2npix(128)) * 10800 / np.pi - K.NSIDE2RESOL_128_ARCMIN) < 1e-13
+    assert abs(4 * np.pi / H.nside2npix(128) - K.NSIDE2PIXAREA_128) < 1e-19
+    assert H.ud_grade(np.arange(48.), 1).tolist() == K.UD_GRADE_48_TO_1
