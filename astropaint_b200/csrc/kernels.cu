@@ -303,6 +303,12 @@ extern "C" int ap_scatter_add_f32(int64_t n, const int64_t* d_pix, const double*
 // ------------------------------------------------------------------------------------------
 constexpr int kPaintThreads = 256;
 constexpr int kMaxHalosPerBlock = 112;
+// templates that run a quadrature per PIXEL also hold the log/exp tables in shared memory (fastmath.cuh):
+// fewer halos per block keep them inside the 48 KB static limit; their time is all quadrature anyway
+template <int P>
+constexpr int max_halos_per_block() {
+  return (P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) ? 48 : kMaxHalosPerBlock;
+}
 constexpr int kHintMax = 256;     // warp-group hints cover chunks up to 8 Ki pixels
 constexpr int kPixMapMax = 4096;  // pixel -> ring-item byte map for the first 4 Ki pixels of a chunk
 constexpr int kStageHalos = 28;   // spline coefficients staged in shared memory per chunk (P_TABLE)
@@ -348,14 +354,15 @@ struct RingItemVec {  // extra per-ring data of R_vec templates
 
 template <int P>
 struct PaintShared {
+  static constexpr int MAXH = max_halos_per_block<P>();
   static constexpr bool VEC = (P == P_NFW_BG);
   static constexpr int NCTX = (P == P_TABLE) ? 4 : ((P == P_STATS) ? 1 : kCtx);
-  HaloHdr hdr[kMaxHalosPerBlock];
-  double cen_cos[kMaxHalosPerBlock], cen_phi[kMaxHalosPerBlock], cen_sin[kMaxHalosPerBlock],
-      cen_Da[kMaxHalosPerBlock];
-  double cen_vec[VEC ? kMaxHalosPerBlock : 1][3];
-  double ctx[kMaxHalosPerBlock][NCTX];
-  int32_t ring_off[kMaxHalosPerBlock + 1];
+  HaloHdr hdr[MAXH];
+  double cen_cos[MAXH], cen_phi[MAXH], cen_sin[MAXH],
+      cen_Da[MAXH];
+  double cen_vec[VEC ? MAXH : 1][3];
+  double ctx[MAXH][NCTX];
+  int32_t ring_off[MAXH + 1];
   RingItem item[kPaintThreads];
   RingItemVec itemv[VEC ? kPaintThreads : 1];
   int32_t pix_off[kPaintThreads + 1];
@@ -364,8 +371,8 @@ struct PaintShared {
   uint8_t pixmap[P == P_STATS ? 1 : kPixMapMax];  // ring item of each of the first 4 Ki pixels
   double stage[P == P_TABLE ? kStageHalos * (kStageMaxNodes - 1) * 4 : 1];
   // P_STATS accumulators
-  unsigned long long cnt[P == P_STATS ? kMaxHalosPerBlock : 1];
-  unsigned long long hmin[P == P_STATS ? kMaxHalosPerBlock : 1], hmax[P == P_STATS ? kMaxHalosPerBlock : 1];
+  unsigned long long cnt[P == P_STATS ? MAXH : 1];
+  unsigned long long hmin[P == P_STATS ? MAXH : 1], hmax[P == P_STATS ? MAXH : 1];
 };
 
 // One block paints `halos_per_block` consecutive halos.  Phase 0: per-halo disc header, centre and
@@ -632,11 +639,11 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
   if (n_painted && tid == 0 && painted) atomicAdd(n_painted, painted);
 }
 
-static int pick_halos_per_block(int64_t n) {
+static int pick_halos_per_block(int64_t n, int max_halos) {
   // enough blocks to fill 148 SMs several times over; many halos per block amortise phase 0
   int64_t g = n / (148 * 8);
   if (g < 1) g = 1;
-  if (g > kMaxHalosPerBlock) g = kMaxHalosPerBlock;
+  if (g > max_halos) g = max_halos;
   return (int)g;
 }
 
@@ -646,7 +653,7 @@ static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& p
                         bool f32 = false) {
   if ((P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) && rm_ensure_tables(stream))
     return fail("could not initialise the quadrature tables");
-  int g = pick_halos_per_block(halos->n);
+  int g = pick_halos_per_block(halos->n, max_halos_per_block<P>());
   int64_t blocks = (halos->n + g - 1) / g;
   if (blocks > 0x7fffffffLL) return fail("too many blocks");
   StatsArgs st;
