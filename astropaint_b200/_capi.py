@@ -69,6 +69,8 @@ SIGNATURES = {
     "ap_patch_rotate": (C.c_int, [c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
     "ap_patch_scale": (C.c_int, [c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_ud_grade": (C.c_int, [c_i64, c_ptr, c_i64, C.c_int, c_dbl, C.c_int, c_ptr, c_ptr]),
+    "ap_ang2pix": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_pix2ang": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spray_host": (C.c_int, [C.c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                 C.POINTER(c_ptr), C.POINTER(c_i32), c_i32, c_ptr, C.POINTER(C.c_uint64)]),
 }

@@ -441,6 +441,33 @@ def ud_grade(d_map, nside_in, nside_out, pess=False, power=None):
     return out
 
 
+def ang2pix(nside, theta, phi, dev=None):
+    """hp.ang2pix(nside, theta, phi) (RING) on the device; host arrays in, host int64 array out"""
+    dev = dev or torch.device("cuda", torch.cuda.current_device())
+    th = np.ascontiguousarray(np.atleast_1d(theta), dtype=np.float64)
+    ph = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(phi), th.shape), dtype=np.float64)
+    d_th, d_ph = to_device(th, dev), to_device(ph, dev)
+    d_pix = torch.empty(th.size, dtype=torch.int64, device=dev)
+    check(_capi.lib().ap_ang2pix(int(nside), th.size, ptr(d_th), ptr(d_ph), ptr(d_pix), stream_ptr()))
+    pix = d_pix.cpu().numpy()
+    if (pix < 0).any():
+        raise ValueError("THETA is out of range [0,pi]")     # healpy's message
+    return pix
+
+
+def pix2ang(nside, pix, dev=None):
+    """hp.pix2ang(nside, ipix) (RING) on the device; returns host (theta, phi)"""
+    dev = dev or torch.device("cuda", torch.cuda.current_device())
+    p = np.ascontiguousarray(np.atleast_1d(pix), dtype=np.int64)
+    if p.size and (p.min() < 0 or p.max() >= 12 * int(nside) ** 2):
+        raise ValueError("Wrong pixel number (it is not 0<=pixel<12*nside**2)")
+    d_p = torch.from_numpy(p).to(dev)
+    d_th = torch.empty(p.size, dtype=torch.float64, device=dev)
+    d_ph = torch.empty_like(d_th)
+    check(_capi.lib().ap_pix2ang(int(nside), p.size, ptr(d_p), ptr(d_th), ptr(d_ph), stream_ptr()))
+    return d_th.cpu().numpy(), d_ph.cpu().numpy()
+
+
 def _win(win, dev):
     if win is None:
         return None, None

@@ -481,6 +481,28 @@ AP_HD void pix2zphi_ring(const Hpx& h, int64_t pix, double& z, double& phi) {
   }
 }
 
+// hp.pix2ang (RING; paint_bucket.py:1085, 1199, 1238): pix2loc, then theta = atan2(sth, z) where pix2loc supplies
+// sin(theta) (polar-cap pixels with |z| > 0.99) and acos(z) elsewhere -- healpix_base.h pix2ang / pointing(loc).
+AP_HD void pix2ang_ring(const Hpx& h, int64_t pix, double& theta, double& phi) {
+  double z;
+  pix2zphi_ring(h, pix, z, phi);
+  const bool north = pix < h.ncap, south = pix >= h.npix - h.ncap;
+  if ((north || south) && fabs(z) > 0.99) {
+    const int64_t iring = north ? (1 + hp_isqrt(1 + 2 * pix)) >> 1 : (1 + hp_isqrt(2 * (h.npix - pix) - 1)) >> 1;
+    const double tmp = AP_MUL((double)(iring * iring), h.fact2);
+    theta = atan2(sqrt(AP_MUL(tmp, AP_SUB(2.0, tmp))), z);
+  } else {
+    theta = acos(z);
+  }
+}
+
+// hp.ang2pix (RING; paint_bucket.py:996, 1183): healpix_base.h ang2pix -- sin(theta) is handed to loc2pix only
+// within 0.01 rad of a pole (the literal 3.14159 is healpix's)
+AP_HD int64_t ang2pix_ring(const Hpx& h, double theta, double phi) {
+  const bool near_pole = (theta < 0.01) || (theta > 3.14159 - 0.01);
+  return loc2pix_ring(h, cos(theta), tt_of_phi(phi), near_pole ? sin(theta) : 0.0, near_pole);
+}
+
 AP_HD double cosdist_zphi(double z1, double phi1, double z2, double phi2) {
   return AP_ADD(AP_MUL(z1, z2), AP_MUL(cos(AP_SUB(phi1, phi2)),
                                        sqrt(AP_MUL(AP_SUB(1.0, AP_MUL(z1, z1)), AP_SUB(1.0, AP_MUL(z2, z2))))));

@@ -113,6 +113,16 @@ int64_t hc_disc_R(int64_t nside, double x, double y, double z, double radius, do
   return n;
 }
 
+void hc_ang2pix(int64_t nside, int64_t n, const double* theta, const double* phi, int64_t* out) {
+  Hpx h = make_hpx(nside);
+  for (int64_t i = 0; i < n; ++i) out[i] = ang2pix_ring(h, theta[i], phi[i]);
+}
+
+void hc_pix2ang(int64_t nside, int64_t n, const int64_t* pix, double* theta, double* phi) {
+  Hpx h = make_hpx(nside);
+  for (int64_t i = 0; i < n; ++i) pix2ang_ring(h, pix[i], theta[i], phi[i]);
+}
+
 void hc_vec2pix(int64_t nside, int64_t n, const double* x, const double* y, const double* z, int64_t* out) {
   Hpx h = make_hpx(nside);
   for (int64_t i = 0; i < n; ++i) out[i] = vec2pix_ring(h, x[i], y[i], z[i]);

@@ -115,6 +115,7 @@ AP_HD double nfw_g(double x) {
 
 // ---- Battaglia16 tau_3D(r) * 2r / sqrt(r^2 - R^2): the @LOS_integrate integrand ----
 struct B16Integrand {
+  static constexpr bool kPositive = true;  // exp(.) * r / sqrt(r^2 - R^2) >= 0: qk15i_rm skips the resabs sums
   double inv_R200xc, alpha, expo, RR;  // RR = R^2
   // fit = (1 + y^alpha)^expo * y^gamma evaluated as exp(expo * log(1 + e^(alpha L)) + gamma L),
   // L = log y: two logs and two exps instead of three pow() calls (each ~4x a log+exp pair on
@@ -153,6 +154,7 @@ AP_HD void b16_setup(double R_200c, double M_200c, double z, double* ctx) {
 
 // NFW.rho_3D(r) * 2r / sqrt(r^2 - R^2) = 8 rho_s r_s^3 / ((r + r_s)^2 sqrt(r^2 - R^2))   (NFW.py:38-58, 83-93)
 struct NfwRhoIntegrand {
+  static constexpr bool kPositive = false;  // rho_s is a user column: no sign assumption
   double K8, rs, RR;
   AP_HD double operator()(double r) const {
     double q = AP_ADD(r, rs);

@@ -601,7 +601,11 @@ AP_RM_RULE_ATTR void qk15i_rm(const F& f_ref, double boun, int idx, double& resu
   resabs = fabs(resk);
 #if defined(__CUDA_ARCH__) && AP_RM_PAIRS == 2
   // two abscissa pairs (four independent integrand evaluations) per trip: the evaluations are long serial
-  // DFMA chains and the scheduler has only 5-6 warps to hide their latency with; the sums stay in j order
+  // DFMA chains and the scheduler has only 5-6 warps to hide their latency with; the sums stay in j order.
+  // Two bit-identical omissions: (1) the Gauss weights wg[0], wg[2], wg[4], wg[6] are exactly 0 (dqk15i
+  // keeps them so that one loop serves both rules): resg + 0 * fsum == resg for finite fsum, so those
+  // updates are skipped; (2) for an integrand that is >= 0 everywhere (F::kPositive) resabs repeats resk's
+  // operations on the same operands, so it is not accumulated separately.
   {
     const double i1 = T.i1[0], i2 = T.i2[0];
     double f1 = f(fm_fma(T.om1[0], i1, boun));
@@ -611,9 +615,8 @@ AP_RM_RULE_ATTR void qk15i_rm(const F& f_ref, double boun, int idx, double& resu
     fv1[0] = f1;
     fv2[0] = f2;
     double fsum = AP_ADD(f1, f2);
-    resg = AP_ADD(resg, AP_MUL(AP_GK(wg)[0], fsum));
     resk = AP_ADD(resk, AP_MUL(AP_GK(wgk)[0], fsum));
-    resabs = AP_ADD(resabs, AP_MUL(AP_GK(wgk)[0], AP_ADD(fabs(f1), fabs(f2))));
+    if (!F::kPositive) resabs = AP_ADD(resabs, AP_MUL(AP_GK(wgk)[0], AP_ADD(fabs(f1), fabs(f2))));
   }
 #pragma unroll 1
   for (int j = 1; j < 7; j += 2) {
@@ -633,12 +636,12 @@ AP_RM_RULE_ATTR void qk15i_rm(const F& f_ref, double boun, int idx, double& resu
     double fsum = AP_ADD(f1, f2);
     resg = AP_ADD(resg, AP_MUL(AP_GK(wg)[j], fsum));
     resk = AP_ADD(resk, AP_MUL(AP_GK(wgk)[j], fsum));
-    resabs = AP_ADD(resabs, AP_MUL(AP_GK(wgk)[j], AP_ADD(fabs(f1), fabs(f2))));
+    if (!F::kPositive) resabs = AP_ADD(resabs, AP_MUL(AP_GK(wgk)[j], AP_ADD(fabs(f1), fabs(f2))));
     fsum = AP_ADD(f3, f4);
-    resg = AP_ADD(resg, AP_MUL(AP_GK(wg)[j + 1], fsum));
     resk = AP_ADD(resk, AP_MUL(AP_GK(wgk)[j + 1], fsum));
-    resabs = AP_ADD(resabs, AP_MUL(AP_GK(wgk)[j + 1], AP_ADD(fabs(f3), fabs(f4))));
+    if (!F::kPositive) resabs = AP_ADD(resabs, AP_MUL(AP_GK(wgk)[j + 1], AP_ADD(fabs(f3), fabs(f4))));
   }
+  if (F::kPositive) resabs = fabs(resk);
 #else
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1

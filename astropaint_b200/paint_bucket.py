@@ -509,12 +509,37 @@ class Canvas:
                     a, e = off[i], off[i + 1]
                     yield rows[i], pix[a:e], (R[a:e] if R is not None else None), (Rv[a:e] if Rv is not None else None)
 
+        def _center_ipix(self, halo_list):
+            """hp.ang2pix of the listed centres in one device launch (ap_ang2pix)"""
+            d = self.catalog.data
+            rows = np.asarray(list(self._halos(halo_list)), dtype=np.int64)
+            return rows, eng.ang2pix(self.nside, d.theta.values[rows], d.phi.values[rows])
+
+        def gen_center_ipix(self, halo_list="All"):
+            """ipix of the halo centres (paint_bucket.py:1175-1185)"""
+            for ipix in self._center_ipix(halo_list)[1]:
+                yield int(ipix)
+
         def gen_center_ang(self, halo_list="All", snap2pixel=False):
+            """(theta, phi) of the halo centres; snap2pixel=True returns the centre pixel's own coordinates
+            (paint_bucket.py:1187-1203)"""
             if snap2pixel:
-                raise NotImplementedError("snap2pixel=True is not part of the painting path")
+                theta, phi = eng.pix2ang(self.nside, self._center_ipix(halo_list)[1])
+                for t, f in zip(theta, phi):
+                    yield (t, f)
+                return
             d = self.catalog.data
             for halo in self._halos(halo_list):
                 yield (d.theta[halo], d.phi[halo])
+
+        def find_centers_indx(self):
+            """sets .center_index to the centre pixel of every halo (paint_bucket.py:984-1000)"""
+            self.center_index = self._center_ipix("All")[1]
+
+        def find_centers_ang(self):
+            """sets .center_ang to [theta, phi] of every halo (paint_bucket.py:1002-1016)"""
+            d = self.catalog.data
+            self.center_ang = np.asarray([d.theta.to_list(), d.phi.to_list()])
 
         def gen_center_vec(self, halo_list="All"):
             d = self.catalog.data

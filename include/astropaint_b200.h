@@ -245,6 +245,12 @@ int ap_patch_scale(int64_t n, int32_t ysize, int32_t xsize, double* d_patches, c
 int ap_ud_grade(int64_t nside_in, const double* d_map_in, int64_t nside_out, int pess, double power, int use_power,
                 double* d_map_out, void* stream);
 
+/* hp.ang2pix(nside, theta, phi) (paint_bucket.py:996 find_centers_indx, :1183 gen_center_ipix) and
+ * hp.pix2ang(nside, ipix) (:1085, :1199 gen_center_ang(snap2pixel=True), :1238 gen_pixel_ang), RING scheme.
+ * theta outside [0, pi] gives pixel -1 (healpy raises); a pixel outside [0, npix) gives NaN angles.        */
+int ap_ang2pix(int64_t nside, int64_t n, const double* d_theta, const double* d_phi, int64_t* d_pix, void* stream);
+int ap_pix2ang(int64_t nside, int64_t n, const int64_t* d_pix, double* d_theta, double* d_phi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

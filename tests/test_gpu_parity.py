@@ -948,3 +948,48 @@ def test_device_ud_grade_reproduces_healpy_docstring_example(cats):
     canvas = ap.Canvas(cats["box"], 2)
     canvas.pixels = np.arange(48.)
     assert canvas.ud_grade(1, inplace=False).tolist() == K.UD_GRADE_48_TO_1
+
+
+@pytest.mark.parametrize("nside", [2, 16, 1024, 8192])
+def test_device_ang2pix_pix2ang(cats, nside):
+    """ap_ang2pix / ap_pix2ang (hp.ang2pix, hp.pix2ang) against the oracle, healpy's docstring examples, and through
+    the public generators gen_center_ipix / gen_center_ang(snap2pixel=True) / find_centers_indx."""
+    import astropaint_b200 as ap
+    from astropaint_b200 import _engine as eng
+    from .golden import healpy_docstring_kat as K
+    _, _, ohp = _oracle()
+    hp = ohp.HealpixRing(nside)
+    rng = np.random.default_rng(nside)
+    n = 200_000
+    theta = np.arccos(rng.uniform(-1, 1, n))
+    theta[:500] = rng.uniform(0, 0.02, 500)
+    theta[500:1000] = np.pi - rng.uniform(0, 0.02, 500)
+    theta[1000:1002] = [0.0, np.pi]
+    phi = rng.uniform(-4 * np.pi, 4 * np.pi, n)
+    pix = eng.ang2pix(nside, theta, phi)
+    assert np.array_equal(pix, hp.ang2pix(theta, phi))
+    th, ph = eng.pix2ang(nside, pix)
+    wt, wp = hp.pix2ang(pix)
+    assert np.abs(th - wt).max() <= 4.5e-16 and np.abs(ph - wp).max() <= 9e-16
+    assert np.array_equal(eng.ang2pix(nside, th, ph), pix)          # round trip through the pixel centre
+    with pytest.raises(ValueError):
+        eng.ang2pix(nside, np.array([-0.1]), np.array([0.0]))
+    with pytest.raises(ValueError):
+        eng.pix2ang(nside, np.array([12 * nside * nside]))
+    if nside == 16:
+        a = K.ANG2PIX_16
+        assert eng.ang2pix(16, a["theta"], a["phi"]).tolist() == a["pix"]
+        a = K.PIX2ANG_16
+        t, f = eng.pix2ang(16, a["pix"])
+        assert np.abs(t - a["theta"]).max() < 5e-9 and np.abs(f - a["phi"]).max() < 5e-9
+    cat = cats["box"]
+    canvas = ap.Canvas(cat, nside)
+    d = cat.data
+    want = hp.ang2pix(d.theta.values, d.phi.values)
+    assert list(canvas.discs.gen_center_ipix()) == want.tolist()
+    assert list(canvas.discs.gen_center_ipix([3, 1])) == want[[3, 1]].tolist()
+    snapped = np.array(list(canvas.discs.gen_center_ang(snap2pixel=True)))
+    wt, wp = hp.pix2ang(want)
+    assert np.abs(snapped[:, 0] - wt).max() <= 4.5e-16 and np.abs(snapped[:, 1] - wp).max() <= 9e-16
+    canvas.discs.find_centers_indx()
+    assert np.array_equal(canvas.discs.center_index, want)

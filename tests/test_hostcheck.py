@@ -25,6 +25,8 @@ def hc():
     L.hc_disc_R.restype = i64
     L.hc_disc_R.argtypes = [i64, d, d, d, d, d, d, d, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p]
     L.hc_vec2pix.argtypes = [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hc_ang2pix.argtypes = [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hc_pix2ang.argtypes = [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_qagi_b16.argtypes = [d, d, d, d, C.POINTER(d), C.POINTER(d), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.hc_critical_density.restype = d
     L.hc_critical_density.argtypes = [d]
@@ -374,7 +376,49 @@ def test_device_header_reproduces_healpy_docstring_examples(hc):
     hc.hc_vec2pix(16, 5, _p(x), _p(y), _p(z), _p(out))
     assert out.tolist() == a["pix"]
     assert abs(hc.hc_max_pixrad(16) - K.MAX_PIXRAD_16) < 5e-11
+    out = np.empty(5, dtype=np.int64)
+    hc.hc_ang2pix(16, 5, _p(th), _p(ph), _p(out))
+    assert out.tolist() == a["pix"]
+    a = K.PIX2ANG_16
+    pix, t, f = np.array(a["pix"], dtype=np.int64), np.empty(5), np.empty(5)
+    hc.hc_pix2ang(16, 5, _p(pix), _p(t), _p(f))
+    assert np.abs(t - a["theta"]).max() < 5e-9 and np.abs(f - a["phi"]).max() < 5e-9
+    assert abs(t[0] - K.PIX2ANG_16_1440[0]) < 1e-15
+    a = K.PIX2ANG_PIX11
+    for ns, wt, wf in zip(a["nside"], a["theta"], a["phi"]):
+        pix = np.array([11], dtype=np.int64)
+        hc.hc_pix2ang(ns, 1, _p(pix), _p(t), _p(f))
+        assert abs(t[0] - wt) < 5e-9 and abs(f[0] - wf) < 5e-9
     # pix2vec(16, 1504): a disc of one tenth of a pixel around that direction holds exactly pixel 1504
     buf = np.empty(16, dtype=np.int64)
     n = hc.hc_query_disc(16, *K.PIX2VEC_16_1504, 0.005, _p(buf), 16)
     assert buf[:n].tolist() == [1504]
+
+
+@pytest.mark.parametrize("nside", [1, 2, 3, 16, 100, 1024, 8192])
+def test_ang2pix_pix2ang_bit_exact(hc, nside):
+    """healpix.cuh ang2pix_ring / pix2ang_ring (hp.ang2pix, hp.pix2ang: paint_bucket.py:996, 1183, 1199, 1238)
+    against the oracle: pixel numbers equal, angles equal to 1 ulp (atan2 / acos of the same z), round trip."""
+    hp = H.HealpixRing(nside)
+    rng = np.random.default_rng(nside)
+    n = 20000
+    theta = np.arccos(rng.uniform(-1, 1, n))
+    theta[:200] = rng.uniform(0, 0.02, 200)                    # inside healpix's sin(theta) branch (< 0.01) and just outside
+    theta[200:400] = np.pi - rng.uniform(0, 0.02, 200)
+    theta[400:404] = [0.0, np.pi, np.pi / 2, np.arccos(2 / 3)]
+    phi = rng.uniform(-4 * np.pi, 4 * np.pi, n)                 # hp.ang2pix wraps any phi
+    phi[400:404] = [0.0, 0.0, 2 * np.pi, np.pi / 4]
+    pix = np.empty(n, dtype=np.int64)
+    hc.hc_ang2pix(nside, n, _p(theta), _p(phi), _p(pix))
+    assert np.array_equal(pix, hp.ang2pix(theta, phi))
+    if hp.npix <= 40000:
+        allp = np.arange(hp.npix, dtype=np.int64)
+    else:
+        allp = np.unique(np.concatenate([pix, np.arange(4000), hp.npix - 1 - np.arange(4000)]))
+    th, ph = np.empty(allp.size), np.empty(allp.size)
+    hc.hc_pix2ang(nside, allp.size, _p(allp), _p(th), _p(ph))
+    wt, wp = hp.pix2ang(allp)
+    assert np.abs(th - wt).max() <= 4.5e-16 and np.array_equal(ph, wp)
+    back = np.empty(allp.size, dtype=np.int64)
+    hc.hc_ang2pix(nside, allp.size, _p(th), _p(ph), _p(back))
+    assert np.array_equal(back, allp)
