@@ -125,7 +125,7 @@ def run_reference(args):
                              "sample": f"first {n} halos of the workload catalog per step ({pairs} halo-pixels), oracle "
                                        f"restatement of the reference loop split over {cores} processes"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -305,9 +305,10 @@ def run_b200(args):
     roofline_dominant = {"kernel": "los_nodes_kernel<b16_tau> (QUADPACK dqagie per (halo, node))", "bound": "fp64-pipe",
                          "achieved": n_quad / (phase_ms["los_nodes"] / 1e3), "unit": "quadratures/s",
                          "launch_ms": phase_ms["los_nodes"], "share_of_step": phase_ms["los_nodes"] / ms_step,
-                         "fp64_pipe_active_pct_ncu": 65.7, "peak": None, "frac": None,
-                         "note": "profiles/r1b_ncu_final.csv: fp64 pipe 65.7% active, issue slots 65.3% busy; 165 "
-                                 "integrand evaluations per quadrature (scipy neval), ~164 warp instructions each"}
+                         "fp64_pipe_active_pct_ncu": 63.0, "peak": None, "frac": None,
+                         "note": "profiles/r1c_ncu_final.csv: fp64 pipe 63.0% active; 165 integrand evaluations per "
+                                 "quadrature (scipy neval), ~142 warp instructions each; hot loop bound by dependent "
+                                 "fp64 chains (46% stall_wait), see DESIGN.md section 7"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -363,13 +364,30 @@ def run_b200(args):
                                 "sample": f"first {args.cpu_halos} halos of the workload catalog ({pairs} halo-pixels, "
                                           f"{dt:.1f} s): oracle restatement of the reference's serial spray loop"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the process's original stdout"""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # Libraries write banners to file descriptor 1 (NCCL prints "NCCL version ..." there when /etc/nccl.conf or
+    # the environment asks for NCCL_DEBUG=VERSION): keep the original stdout for the JSON line and point fd 1
+    # at stderr for everything else.
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
