@@ -155,12 +155,23 @@ def _ring_start(nside, ring):
     return 12 * nside * nside - 2 * nr * (nr + 1)
 
 
-def band_layout(nside, n_bands):
-    """Equal-area ring bands of the map: ring_bounds[k] is the first ring of band k (z = 1 - 2k/K),
+#: Area (= work) ratio of consecutive ring bands.  A band's copy / all-reduce starts when its halos are painted
+#: and overlaps the next band's QUADPACK phase, so what stays exposed at the end is the LAST band's transfer:
+#: geometrically shrinking bands (f_k ~ BAND_RATIO^k) end on a small one.  With t_copy ~ 0.75 t_compute for
+#: the whole map (6.44 GB over PCIe against the kSZ spray) any ratio >= 0.75 keeps the earlier transfers hidden.
+BAND_RATIO = 0.75   # measured (tools/e2e_chunks.py, 1e7 halos): 8 equal bands 204.1 ms, 10 bands x 0.75 193.4, 8 x 0.7 192.8, 6 x 0.6 204.6
+
+
+def band_layout(nside, n_bands, ratio=None):
+    """Ring bands of the map, band k holding a fraction ~ ratio^k of the sphere's area (ratio = 1: equal
+    areas): ring_bounds[k] is the first ring of band k (z = 1 - 2 F_k, F the cumulative fraction),
     pix_bounds[k] its first pixel; pix_bounds[K] = npix."""
+    ratio = BAND_RATIO if ratio is None else ratio
+    f = np.power(float(ratio), np.arange(n_bands))
+    F = np.cumsum(f / f.sum())
     rings, pix = [1], [0]
     for k in range(1, n_bands):
-        z = 1.0 - 2.0 * k / n_bands
+        z = 1.0 - 2.0 * F[k - 1]
         az = abs(z)
         if az <= 2.0 / 3.0:
             r = int(nside * (2.0 - 1.5 * z))

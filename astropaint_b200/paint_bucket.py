@@ -901,7 +901,7 @@ class Painter:
     #: catalogs at least this large stream finished ring bands of the map to the host while the remaining
     #: halos are still being integrated (only once the host copy has been read before)
     PREFETCH_MIN_HALOS = 200000
-    PREFETCH_CHUNKS = 8
+    PREFETCH_CHUNKS = 10     # ring bands of geometrically shrinking area (eng.BAND_RATIO): the exposed tail is the last one
 
     def _paint_device_table(self, info, halos, nside, col, template_kwargs, d_map, d_count, prefetch=None,
                             band_done=None):
