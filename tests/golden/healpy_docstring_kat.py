@@ -1,8 +1,10 @@
 """Known-answer vectors from the published docstring examples of healpy (the third-party package that holds
 the reference's pixel arithmetic: healpy==1.13.0, requirements.txt:15).  healpy itself is NOT installed here and
-there is no network: the examples below are restated from the public API documentation of
+there is no network: the examples below are restated FROM MEMORY of the public API documentation of
 healpy.pixelfunc (ang2pix, pix2ang, pix2vec, vec2pix, ring2nest, max_pixrad, nside2resol, nside2pixarea,
-ud_grade).  They pin the RING pixel numbering, the pixel-centre convention, the RING<->NEST map that ud_grade
+ud_grade) -- they could not be re-fetched here.  Their evidential weight comes from agreement: the oracle
+(written independently from the HEALPix paper's ring-scheme formulas) reproduces all 28 integers and 40 floats,
+which neither a mis-remembered example nor a wrong restatement would do by chance.  They pin the RING pixel numbering, the pixel-centre convention, the RING<->NEST map that ud_grade
 goes through and ud_grade's averaging; they do not pin query_disc (its docstring has no numeric example).
 Floats are quoted as printed (8 decimals unless the docstring shows repr precision).
 """
