@@ -32,35 +32,28 @@ SIGNATURES = {
     "ap_catalog_build": (C.c_int, [c_i64] + [c_ptr] * 8 + [c_dbl, c_dbl, c_dbl, C.POINTER(c_ptr), c_ptr]),
     "ap_disc_radius": (C.c_int, [c_i64, c_ptr, c_dbl, c_ptr, c_ptr]),
     "ap_disc_count": (C.c_int, [c_i64, C.POINTER(ApHalos), C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_band_clip": (C.c_int, [c_i64, c_i64]),
+    "ap_disc_count_items": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_i64, c_ptr, c_ptr]),
+    "ap_paint_los_items": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                                     c_ptr, c_ptr, c_ptr]),
+    "ap_paint_los_items_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
+                                         c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_disc_pixels": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_scatter_add": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_paint_profile": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), C.POINTER(c_ptr), C.POINTER(c_i32),
                                    c_i32, c_ptr, c_ptr, c_ptr]),
     "ap_table_nodes": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
-    "ap_b16_tau_nodes": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_los_nodes": (C.c_int, [C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "ap_paint_los_small": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
-                                     c_ptr, c_ptr, c_ptr]),
-    "ap_paint_los_small_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
-                                         c_ptr, c_ptr, c_ptr]),
-    "ap_paint_los_items": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
-                                     c_ptr, c_ptr]),
-    "ap_paint_los_items_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
-                                         c_ptr, c_ptr, c_ptr]),
     "ap_b16_tau_eval": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spline_build": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spline_build_uniform": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_paint_table": (C.c_int, [c_i64, C.POINTER(ApHalos), c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                  c_ptr]),
-    "ap_paint_b16_small": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
-                                     c_ptr, c_ptr, c_ptr]),
     "ap_scatter_add_f32": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_paint_profile_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), C.POINTER(c_ptr), C.POINTER(c_i32),
                                        c_i32, c_ptr, c_ptr, c_ptr]),
     "ap_paint_table_f32": (C.c_int, [c_i64, C.POINTER(ApHalos), c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                      c_ptr]),
-    "ap_paint_b16_small_f32": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
-                                         c_ptr, c_ptr, c_ptr]),
     "ap_cutouts": (C.c_int, [c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_dbl, c_dbl, c_i32, c_i32,
                              c_ptr, c_ptr]),
     "ap_stack_cutouts": (C.c_int, [c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_dbl, c_dbl, c_i32,
@@ -71,6 +64,11 @@ SIGNATURES = {
     "ap_ud_grade": (C.c_int, [c_i64, c_ptr, c_i64, C.c_int, c_dbl, C.c_int, c_ptr, c_ptr]),
     "ap_ang2pix": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_pix2ang": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_host_register": (C.c_int, [c_ptr, C.c_uint64]),
+    "ap_host_unregister": (C.c_int, [c_ptr]),
+    "ap_copy_d2h_async": (C.c_int, [c_ptr, c_ptr, C.c_uint64, c_ptr]),
+    "ap_copy_h2d_async": (C.c_int, [c_ptr, c_ptr, C.c_uint64, c_ptr]),
+    "ap_fp64_peak": (C.c_int, [c_i32, c_i32, c_ptr, C.POINTER(C.c_uint64), c_ptr]),
     "ap_spray_host": (C.c_int, [C.c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                 C.POINTER(c_ptr), C.POINTER(c_i32), c_i32, c_ptr, C.POINTER(C.c_uint64)]),
 }

@@ -53,11 +53,16 @@ class DeviceHalos:
     radius rounds identically.
     """
 
-    def __init__(self, data, R_times, device, rows=None, pinned=None):
+    def __init__(self, data, R_times, device, rows=None, pinned=None, pinned_range=None):
+        """rows: catalog row labels of the halos held, in this object's order (None = every row, catalog order).
+        pinned: {column: page-locked host tensor}.  With pinned_range = (lo, hi) the tensors are in the
+        catalog's colatitude order (Catalog.pin_memory) and [lo:hi] of them ARE the rows (one contiguous DMA
+        per column); otherwise they are in catalog order and `rows` is gathered from them."""
         self.device = device
         self._data = data
         self._rows = rows
         self._pinned = pinned or {}
+        self._pinned_range = pinned_range
         self.cols = {}
         self._n_all = len(data)
         self.n = self._n_all if rows is None else len(rows)
@@ -79,10 +84,12 @@ class DeviceHalos:
 
     def _take(self, v):
         """rows of a host column: a view for all rows / a contiguous block, a gather otherwise"""
+        if self._pinned_range is not None and isinstance(v, torch.Tensor):
+            return v[self._pinned_range[0]:self._pinned_range[1]]
         if self._rows is None:
             return v
         r = self._rows
-        if len(r) and r[-1] - r[0] + 1 == len(r):
+        if len(r) and r[-1] - r[0] + 1 == len(r) and np.all(np.diff(r) == 1):
             return v[int(r[0]):int(r[-1]) + 1]
         return v[torch.as_tensor(r)] if isinstance(v, torch.Tensor) else v[r]
 
@@ -118,7 +125,7 @@ class DeviceHalos:
     def gathered(self, perm):
         """The same halos in the order `perm` (int64 device tensor): one gather per resident column."""
         out = DeviceHalos.__new__(DeviceHalos)
-        out.device, out._data, out._pinned, out._rows = self.device, self._data, {}, None
+        out.device, out._data, out._pinned, out._rows, out._pinned_range = self.device, self._data, {}, None, None
         out._n_all, out.n = self.n, self.n
         out.cols = {k: v.index_select(0, perm) for k, v in self.cols.items()}
         return out
@@ -126,7 +133,7 @@ class DeviceHalos:
     def view(self, lo, hi):
         """Halos [lo, hi) of this object without copying (column views)."""
         out = DeviceHalos.__new__(DeviceHalos)
-        out.device, out._data, out._pinned, out._rows = self.device, self._data, {}, None
+        out.device, out._data, out._pinned, out._rows, out._pinned_range = self.device, self._data, {}, None, None
         out._n_all, out.n = hi - lo, hi - lo
         out.cols = {k: v[lo:hi] for k, v in self.cols.items()}
         return out
@@ -137,6 +144,7 @@ class DeviceHalos:
         sub.device = self.device
         sub._data = self._data
         sub._pinned = {}
+        sub._pinned_range = None
         sub._rows = self.index[idx]
         sub._n_all = self._n_all
         sub.n = len(idx)
@@ -145,113 +153,78 @@ class DeviceHalos:
         return sub
 
 
-def _ring_start(nside, ring):
-    """first pixel of `ring` (healpix get_ring_info_small)"""
-    if ring < nside:
-        return 2 * ring * (ring - 1)
-    if ring < 3 * nside:
-        return 2 * nside * (nside - 1) + (ring - nside) * 4 * nside
-    nr = 4 * nside - ring
-    return 12 * nside * nside - 2 * nr * (nr + 1)
+class band_clip:
+    """`with band_clip(band):` -- every painting launch of this thread inside the block paints only the rings
+    the rank owns and addresses the map relative to the band's first pixel (ap_band_clip; _bands.Band)."""
+
+    def __init__(self, band):
+        self.band = band
+
+    def __enter__(self):
+        b = self.band
+        if b is not None and not b.whole:
+            check(_capi.lib().ap_band_clip(b.ring_lo, b.ring_hi))
+        return self
+
+    def __exit__(self, *exc):
+        check(_capi.lib().ap_band_clip(0, 0))
+        return False
 
 
-#: Area (= work) ratio of consecutive ring bands.  A band's copy / all-reduce starts when its halos are painted
-#: and overlaps the next band's QUADPACK phase, so what stays exposed at the end is the LAST band's transfer:
-#: geometrically shrinking bands (f_k ~ BAND_RATIO^k) end on a small one.  With t_copy ~ 0.75 t_compute for
-#: the whole map (6.44 GB over PCIe against the kSZ spray) any ratio >= 0.75 keeps the earlier transfers hidden.
-BAND_RATIO = 0.75   # measured (tools/e2e_chunks.py, 1e7 halos): 8 equal bands 204.1 ms, 10 bands x 0.75 193.4, 8 x 0.7 192.8, 6 x 0.6 204.6
+class Timers:
+    """CUDA-event ticks on the launching stream; phase_ms() sums the time between consecutive ticks by name."""
+
+    def __init__(self):
+        self.ticks = []
+
+    def tick(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.ticks.append((name, ev))
+
+    def phase_ms(self, into=None, scale=1.0):
+        out = {} if into is None else into
+        for (name, ev), (_, nxt) in zip(self.ticks[:-1], self.ticks[1:]):
+            if name != "end":
+                out[name] = out.get(name, 0.0) + ev.elapsed_time(nxt) * scale
+        return out
 
 
-def band_layout(nside, n_bands, ratio=None):
-    """Ring bands of the map, band k holding a fraction ~ ratio^k of the sphere's area (ratio = 1: equal
-    areas): ring_bounds[k] is the first ring of band k (z = 1 - 2 F_k, F the cumulative fraction),
-    pix_bounds[k] its first pixel; pix_bounds[K] = npix."""
-    ratio = BAND_RATIO if ratio is None else ratio
-    f = np.power(float(ratio), np.arange(n_bands))
-    F = np.cumsum(f / f.sum())
-    rings, pix = [1], [0]
-    for k in range(1, n_bands):
-        z = 1.0 - 2.0 * F[k - 1]
-        az = abs(z)
-        if az <= 2.0 / 3.0:
-            r = int(nside * (2.0 - 1.5 * z))
-        else:
-            ir = int(nside * np.sqrt(3.0 * (1.0 - az)))
-            r = ir if z > 0 else 4 * nside - ir - 1
-        r = min(max(r, rings[-1]), 4 * nside - 1)
-        rings.append(r)
-        pix.append(_ring_start(nside, r))
-    rings.append(4 * nside)
-    pix.append(12 * nside * nside)
-    return rings, pix
-
-
-def top_ring(halos, nside):
-    """Per halo (device, int64): a ring at or above the first ring its disc can touch — healpix
-    ring_above(cos(theta - radius)), i.e. one ring of margin against the kernels' own irmin."""
-    z = torch.cos(torch.clamp(halos.col("theta") - halos.cols["__radius__"], min=0.0))
-    az = z.abs()
-    r_eq = torch.floor(nside * (2.0 - 1.5 * z))
-    ir = torch.floor(nside * torch.sqrt(torch.clamp(3.0 * (1.0 - az), min=0.0)))
-    r_cap = torch.where(z > 0, ir, 4 * nside - ir - 1)
-    return torch.clamp(torch.where(az <= 2.0 / 3.0, r_eq, r_cap), min=1).to(torch.int64)
-
-
-def table_spray(halos, nside, kind, args, scale, n_samples, method, d_map, d_count=None, n_bands=1, band_done=None,
-                timers=None):
-    """@interpolate(@LOS_integrate(profile_3D)) for all halos: K1 stats -> nodes -> QUADPACK -> spline ->
-    K3 paint -> bypass.  With n_bands > 1 the halos are grouped by the equal-area ring band holding the
-    first ring their disc can touch and processed band by band; after band k no later halo writes above
-    band k+1, so `band_done(k, pix_lo, pix_hi)` may ship those pixels (device->host copy, all-reduce)
-    on another stream while band k+1 is still in its QUADPACK phase."""
+def table_chunk(halos, nside, kind, args, scale, n_samples, method, d_map, d_count=None, timers=None):
+    """@interpolate(@LOS_integrate(profile_3D)) for one chunk of halos: K1 stats (+ the bypass work list) ->
+    nodes -> QUADPACK -> spline -> K3 paint -> bypass.  Six launches, nothing read back by the host."""
     uniform = method == "linspace"
-
-    def tick(name):
-        if timers is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            timers.append((name, ev))
-
-    def run(h, a, sc):
-        tick("disc_count")
-        n_pix, _, rmin, rmax = disc_count(h, nside, want_range=True)
-        tick("table_nodes")
-        nodes, n_nodes = table_nodes(h, n_pix, rmin, rmax, n_samples, method)
-        tick("los_nodes")
-        values = los_nodes(kind, h, a, nodes, n_nodes)
-        tick("spline_build")
-        coef = spline_build(nodes, values, n_nodes, uniform=uniform)
-        tick("paint_table")
-        paint_table(h, nside, nodes, coef, n_nodes, sc, d_map, d_count, uniform=uniform)
-        tick("paint_los_small")
-        paint_los_small(kind, h, nside, a, sc, n_pix, n_samples, d_map, d_count)
-        tick("end")
-
-    if _capi.lib().ap_disc_mode(-1) > 0:
-        n_bands = 1     # inclusive discs reach above top_ring()'s estimate: no band streaming (rare path)
-    if n_bands <= 1:
-        run(halos, args, scale)
-        if band_done is not None:
-            band_done(0, 0, d_map.numel())
-        return
-    tick("band_sort")
-    rings, pix = band_layout(nside, n_bands)
-    tr = top_ring(halos, nside)
-    band = torch.bucketize(tr, torch.as_tensor(rings[1:-1], device=tr.device, dtype=torch.int64), right=True)
-    order = torch.argsort(band, stable=True)
-    counts = torch.bincount(band, minlength=n_bands).cpu().numpy()
-    hs = halos.gathered(order)
-    args = [a.index_select(0, order) for a in args]
-    scale = scale.index_select(0, order) if scale is not None else None
+    tick = timers.tick if timers is not None else (lambda name: None)
+    tick("disc_count")
+    n_pix, rmin, rmax, items, n_items = disc_count_items(halos, nside, n_samples)
+    tick("table_nodes")
+    nodes, n_nodes = table_nodes(halos, n_pix, rmin, rmax, n_samples, method)
+    tick("los_nodes")
+    values = los_nodes(kind, halos, args, nodes, n_nodes)
+    tick("spline_build")
+    coef = spline_build(nodes, values, n_nodes, uniform=uniform)
+    tick("paint_table")
+    paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count, uniform=uniform)
+    tick("paint_los_items")
+    paint_los_items(kind, halos, nside, args, scale, items, n_items, d_map, d_count)
     tick("end")
-    lo = 0
-    for k in range(n_bands):
-        hi = lo + int(counts[k])
-        if hi > lo:
-            run(hs.view(lo, hi), [a[lo:hi] for a in args], scale[lo:hi] if scale is not None else None)
-        if band_done is not None:
-            band_done(k, pix[k], pix[k + 1])
-        lo = hi
+    return n_pix
+
+
+def run_chunks(plan, paint_chunk, chunk_done=None):
+    """Drive one rank's share of a spray: paint_chunk(lo, hi) for every chunk of `plan` (positions within the
+    rank's halo slice), then chunk_done(rel_lo, rel_hi) with the pixel range of the rank's band (relative to its
+    first pixel) that became final -- the caller ships it on a copy stream.  Inside band_clip(plan.band)."""
+    from ._bands import ring_start
+    band = plan.band
+    prev = band.ring_lo
+    with band_clip(band):
+        for (a, e, done) in plan.chunks:
+            if e > a:
+                paint_chunk(a - plan.halo_lo, e - plan.halo_lo)
+            if chunk_done is not None and done > prev:
+                chunk_done(ring_start(band.nside, prev) - band.pix_lo, ring_start(band.nside, done) - band.pix_lo)
+                prev = done
 
 
 # ---------------------------------------------------------------------------------------------
@@ -259,6 +232,13 @@ def table_spray(halos, nside, kind, args, scale, n_samples, method, d_map, d_cou
 # ---------------------------------------------------------------------------------------------
 CATALOG_OUT = ("D_c", "redshift", "lat", "lon", "theta", "phi", "D_a", "R_200c", "c_200c", "R_ang_200c", "rho_s",
                "R_s", "v_r", "v_th", "v_ph", "v_lat", "v_lon")   # order of the AP_CAT_* indices
+
+
+def copy_d2h(host_tensor, d_src, stream=None):
+    """asynchronous device -> host copy of a contiguous tensor into (page-locked) host memory"""
+    assert host_tensor.numel() == d_src.numel() and host_tensor.element_size() == d_src.element_size()
+    sp = c_ptr(stream.cuda_stream) if stream is not None else stream_ptr()
+    check(_capi.lib().ap_copy_d2h_async(c_ptr(host_tensor.data_ptr()), ptr(d_src), d_src.numel() * d_src.element_size(), sp))
 
 
 def catalog_build(cols, default_redshift, crit_dens_0, h, device=None):
@@ -376,31 +356,30 @@ def los_nodes(kind, halos, args, nodes, n_nodes):
     return values
 
 
-def paint_los_small(kind, halos, nside, args, scale, n_pix, n_samples, d_map, d_count=None):
-    """The `len(R) < n_samples` bypass: halos with 1 .. n_samples-1 pixels get the projected profile at every
-    pixel.  The (halo, pixel ordinal) work items are compacted first (one small device->host read of their
-    number) so that no warp is launched for halos that do not need it and every lane integrates."""
-    small = (n_pix > 0) & (n_pix < n_samples)
-    idx = torch.nonzero(small).squeeze(1)
-    if idx.numel() == 0:
-        return
-    cnt = n_pix.index_select(0, idx)
-    item_halo = torch.repeat_interleave(idx, cnt)
-    start = torch.cumsum(cnt, 0) - cnt
-    item_ord = (torch.arange(item_halo.numel(), device=item_halo.device) - torch.repeat_interleave(start, cnt)).to(torch.int32)
+def disc_count_items(halos, nside, n_samples):
+    """K1 with the bypass work list: (n_pix, rmin, rmax, items, n_items).  items holds halo * 32 + pixel ordinal
+    for every pixel of every halo with 0 < n_pix < n_samples; n_items (device uint64) is their number."""
+    dev = halos.device
+    n = halos.n
+    n_pix = torch.empty(n, dtype=torch.int64, device=dev)
+    rmin = torch.empty(n, dtype=torch.float64, device=dev)
+    rmax = torch.empty(n, dtype=torch.float64, device=dev)
+    cap = n * (n_samples - 1)
+    items = torch.empty(max(cap, 1), dtype=torch.int64, device=dev)
+    n_items = torch.zeros(1, dtype=torch.int64, device=dev)
+    s = halos.struct()
+    check(_capi.lib().ap_disc_count_items(nside, C.byref(s), ptr(n_pix), ptr(rmin), ptr(rmax), n_samples, ptr(items), cap,
+                                          ptr(n_items), stream_ptr()))
+    return n_pix, rmin, rmax, items, n_items
+
+
+def paint_los_items(kind, halos, nside, args, scale, items, n_items, d_map, d_count=None):
+    """The `len(R) < n_samples` bypass of @interpolate from the device-built work list: one QUADPACK quadrature
+    per (halo, pixel) item, every lane busy, the item count read on the device."""
     s = halos.struct()
     a = list(args) + [None] * (3 - len(args))
     check(_fn("ap_paint_los_items", d_map)(LOS_KINDS[kind], nside, C.byref(s), ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(scale),
-                                           item_halo.numel(), ptr(item_halo), ptr(item_ord), ptr(d_map), stream_ptr()))
-    if d_count is not None:
-        d_count += item_halo.numel()
-
-
-def b16_tau_nodes(halos, R200, M200, zred, nodes, n_nodes):
-    values = torch.empty_like(nodes)
-    check(_capi.lib().ap_b16_tau_nodes(halos.n, ptr(R200), ptr(M200), ptr(zred), nodes.shape[1], ptr(nodes),
-                                       ptr(n_nodes), ptr(values), stream_ptr()))
-    return values
+                                           ptr(n_items), items.numel(), ptr(items), ptr(d_map), ptr(d_count), stream_ptr()))
 
 
 def spline_build(nodes, values, n_nodes, uniform=False):
@@ -416,12 +395,6 @@ def paint_table(halos, nside, nodes, coef, n_nodes, scale, d_map, d_count=None, 
     check(_fn("ap_paint_table", d_map)(nside, C.byref(s), nodes.shape[1], int(bool(uniform)), ptr(nodes), ptr(coef),
                                        ptr(n_nodes),
                                      ptr(scale), ptr(d_map), ptr(d_count), stream_ptr()))
-
-
-def paint_b16_small(halos, nside, R200, M200, zred, scale, n_pix, n_samples, d_map, d_count=None):
-    s = halos.struct()
-    check(_fn("ap_paint_b16_small", d_map)(nside, C.byref(s), ptr(R200), ptr(M200), ptr(zred), ptr(scale),
-                                           ptr(n_pix), n_samples, ptr(d_map), ptr(d_count), stream_ptr()))
 
 
 def cutouts(d_map, nside, lon, lat, lon_range, lat_range, xsize, ysize):

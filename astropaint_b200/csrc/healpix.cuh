@@ -21,6 +21,11 @@ struct Hpx {
   int32_t incl_fct;
   double rad_small, rad_big;
   double pad_cos, pad_sin;  // cos / sin of 1.02 * max_pixrad(nside): the trimming pre-filter of ring_span
+  // Ring-band clip of the painting kernels (ap_band_clip): only rings clip_lo <= iz < clip_hi are painted and
+  // the map pointer handed to the kernel addresses pixel clip_pix0 (the first pixel of ring clip_lo) -- the
+  // band of the map one rank owns.  Default: every ring, clip_pix0 = 0.
+  int32_t clip_lo, clip_hi;
+  int64_t clip_pix0;
 };
 
 AP_HD Hpx make_hpx(int64_t nside) {
@@ -34,6 +39,9 @@ AP_HD Hpx make_hpx(int64_t nside) {
   h.rad_small = h.rad_big = 0.0;
   h.pad_cos = 1.0;
   h.pad_sin = 0.0;
+  h.clip_lo = 1;
+  h.clip_hi = (int32_t)(4 * nside);
+  h.clip_pix0 = 0;
   return h;
 }
 

@@ -7,7 +7,7 @@
 //   disc_pixels_kernel            K1b flat (halo, pixel) list (+R, +R_vec): parity, Python templates
 //   scatter_add_kernel            np.add.at for the flat list
 //   table_nodes_kernel, los_nodes_kernel<KIND>, spline_build(_uniform)_kernel   K4 @interpolate tables
-//   paint_los_small_kernel<KIND>  the len(R) < n_samples bypass of @interpolate
+//   paint_los_items_kernel<KIND>  the len(R) < n_samples bypass of @interpolate (device-built work list)
 //   cutout_kernel<STACK>          K5  CartesianProj cutouts and their stack
 //   patch_ops.cuh                 K6  apply_func library: spline prefilter + rotate, taper, weight, stack
 #include <cuda_runtime.h>
@@ -49,9 +49,33 @@ extern "C" int ap_quad_fast_path(int enable) {
   if (enable >= 0) g_quad_fast = enable ? 1 : 0;
   return prev;
 }
+// Ring band painted by the calling thread's next launches (0, 0 = the whole map): rings [lo, hi) only, and the
+// map pointer of every painting entry point addresses the first pixel of ring lo.  One rank of a multi-GPU
+// spray owns one band of the map; halos whose disc straddles a boundary are painted by
+// both neighbours, each keeping its own rings, so no partial map and no reduction exist.
+static thread_local int64_t g_clip_lo = 0, g_clip_hi = 0;
+extern "C" int ap_band_clip(int64_t ring_lo, int64_t ring_hi) {
+  if (ring_lo <= 0 && ring_hi <= 0) {
+    g_clip_lo = g_clip_hi = 0;
+    return 0;
+  }
+  if (ring_lo < 1 || ring_hi <= ring_lo) return fail("band_clip: need 1 <= ring_lo < ring_hi");
+  g_clip_lo = ring_lo;
+  g_clip_hi = ring_hi;
+  return 0;
+}
 static Hpx disc_hpx(int64_t nside) {
   Hpx h = make_hpx(nside);
   hpx_set_inclusive(h, g_incl_fact);
+  if (g_clip_hi > 0) {
+    const int64_t top = 4 * nside;
+    h.clip_lo = (int32_t)(g_clip_lo < top ? g_clip_lo : top);
+    h.clip_hi = (int32_t)(g_clip_hi < top ? g_clip_hi : top);
+    int64_t nr;
+    bool shifted;
+    if (h.clip_lo < top) ring_info(h, h.clip_lo, h.clip_pix0, nr, shifted);
+    else h.clip_pix0 = h.npix;
+  }
   return h;
 }
 #define AP_LAUNCH_CHECK()                                                               \
@@ -386,6 +410,12 @@ struct StatsArgs {
   int32_t* n_rings;
   double* rmin;
   double* rmax;
+  // optional work list of the `len(R) < n_samples` bypass: halos with 0 < n_pix < item_ns append one packed
+  // item (halo * 32 + pixel ordinal) per pixel at items[atomicAdd(item_count, n_pix) ...] (capacity item_cap)
+  unsigned long long* item_count;
+  int64_t* items;
+  int64_t item_cap;
+  int32_t item_ns;
 };
 
 struct HaloHdr {  // DiscHeader with 32-bit ring numbers (nside <= 2^18)
@@ -452,6 +482,15 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
     if (P == P_TABLE && tab.n_nodes[h] == 0) {  // bypass halo: painted elsewhere
       d.ir_first = 1;
       d.ir_last = 0;
+    }
+    if (STATS) {  // counts stay those of the WHOLE disc; a disc that misses the rank's band reports 0 pixels
+      if (d.ir_last < hpx.clip_lo || d.ir_first >= hpx.clip_hi) {
+        d.ir_first = 1;
+        d.ir_last = 0;
+      }
+    } else {      // paint the rings of the rank's own band only
+      if (d.ir_first < hpx.clip_lo) d.ir_first = hpx.clip_lo;
+      if (d.ir_last >= hpx.clip_hi) d.ir_last = hpx.clip_hi - 1;
     }
     HaloHdr hh;
     hh.phi = d.phi; hh.z0 = d.z0; hh.xa = d.xa; hh.cosr = d.cosr; hh.cosrs = d.cosrs;
@@ -663,8 +702,8 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       const bool two = (k + kPaintThreads < total);
       double v0 = eval(k, p0);
       double v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
-      if (AP_BOUNDS_OK(p0 >= 0 && p0 < hpx.npix)) atomicAdd(&map[p0], (MapT)v0);
-      if (two && AP_BOUNDS_OK(p1 >= 0 && p1 < hpx.npix)) atomicAdd(&map[p1], (MapT)v1);
+      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) atomicAdd(&map[p0 - hpx.clip_pix0], (MapT)v0);
+      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) atomicAdd(&map[p1 - hpx.clip_pix0], (MapT)v1);
     }
     __syncthreads();
   }
@@ -682,6 +721,11 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
         double a = __longlong_as_double((long long)sm.hmin[tid]), b = __longlong_as_double((long long)sm.hmax[tid]);
         st.rmin[h] = c ? sm.cen_Da[tid] * sep_from_hav(a) : INFINITY;
         st.rmax[h] = c ? sm.cen_Da[tid] * sep_from_hav(b) : -INFINITY;
+      }
+      if (st.items && c > 0ull && c < (unsigned long long)st.item_ns) {
+        const unsigned long long at = atomicAdd(st.item_count, c);
+        for (unsigned long long k = 0; k < c; ++k)
+          if ((int64_t)(at + k) < st.item_cap) st.items[at + k] = h * 32 + (int64_t)k;
       }
     }
     return;
@@ -728,8 +772,9 @@ static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& p
 }
 
 // K1: hp.query_disc counts (+ R range) with the painter's block structure, phase 2 skipped
-extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
-                             int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream) {
+static int disc_count_impl(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix, int32_t* d_n_rings,
+                           double* d_rmin, double* d_rmax, int32_t item_ns, int64_t* d_items, int64_t item_cap,
+                           unsigned long long* d_item_count, void* stream) {
   if (check_nside(nside)) return 1;
   bool want_r = d_rmin || d_rmax;
   if (check_halos(halos, want_r)) return 1;
@@ -741,14 +786,29 @@ extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive
   } guard(inclusive);
   if (want_r && (!d_rmin || !d_rmax)) return fail("d_rmin and d_rmax must both be given");
   if (!d_n_pix) return fail("d_n_pix == NULL");
+  if (d_items && (!d_item_count || item_cap < 0 || item_ns < 1 || item_ns > 32))
+    return fail("disc_count: item list needs d_item_count, item_cap >= 0 and 1 <= n_samples <= 32");
   if (halos->n == 0) return 0;
   ParamPtrs pp;
   memset(&pp, 0, sizeof(pp));
   TableArgs tab;
   memset(&tab, 0, sizeof(tab));
   StatsArgs st;
+  memset(&st, 0, sizeof(st));
   st.n_pix = d_n_pix; st.n_rings = d_n_rings; st.rmin = d_rmin; st.rmax = d_rmax;
+  st.items = d_items; st.item_cap = item_cap; st.item_count = d_item_count; st.item_ns = item_ns;
   return launch_paint<P_STATS>(nside, halos, pp, tab, nullptr, nullptr, stream, &st);
+}
+extern "C" int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
+                             int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream) {
+  return disc_count_impl(nside, halos, inclusive, d_n_pix, d_n_rings, d_rmin, d_rmax, 0, nullptr, 0, nullptr, stream);
+}
+extern "C" int ap_disc_count_items(int64_t nside, const ap_halos* halos, int64_t* d_n_pix, double* d_rmin, double* d_rmax,
+                                   int32_t n_samples, int64_t* d_items, int64_t item_cap,
+                                   unsigned long long* d_item_count, void* stream) {
+  if (!d_items) return fail("disc_count_items: d_items == NULL");
+  return disc_count_impl(nside, halos, 0, d_n_pix, nullptr, d_rmin, d_rmax, n_samples, d_items, item_cap, d_item_count,
+                         stream);
 }
 
 static int paint_profile_impl(int profile, int64_t nside, const ap_halos* halos, const double* const* h_params,
@@ -928,12 +988,6 @@ extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const doubl
   return 0;
 }
 
-extern "C" int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double* d_M_200c, const double* d_redshift,
-                                int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes, double* d_values,
-                                void* stream) {
-  return ap_los_nodes(LOS_B16_TAU, n, d_R_200c, d_M_200c, d_redshift, n_samples, d_nodes, d_n_nodes, d_values, stream);
-}
-
 // diagnostic: tau_2D(R) with QUADPACK's own error estimate and evaluation count
 __global__ void __launch_bounds__(128) b16_tau_eval_kernel(int64_t n, const double* R, const double* R200,
                                                            const double* M200, const double* zred, double* result,
@@ -1076,200 +1130,123 @@ extern "C" int ap_spline_build_uniform(int64_t n, int32_t n_samples, const doubl
   return 0;
 }
 
-// bypass: halos with 0 < n_pix < n_samples; one warp per halo, lane k owns pixel k
-template <int KIND, class MapT>
-__global__ void __launch_bounds__(128) paint_los_small_kernel(Hpx hpx, HalosDev H, const double* R200, const double* M200,
-                                                              const double* zred, const double* scale, const int64_t* n_pix,
-                                                              int32_t ns, MapT* map, unsigned long long* n_painted) {
-  fm_smem_init();
-  int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (h >= H.n) return;
-  int64_t np = n_pix[h];
-  if (np <= 0 || np >= ns) return;
-  if (lane >= np) return;
-  DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
-  HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
-  int64_t run = 0;
-  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
-    RingSpan s = ring_span(hpx, d, iz);
-    if (s.len <= 0) continue;
-    if (lane < run + s.len) {
-      RingGeom g = ring_geom(hpx, iz, s, c);
-      int32_t js = (int32_t)(lane - run);
-      int32_t ip = s.ip_lo + js;
-      double R = c.D_a * pixel_sep(g, js);
-      double ctx[kCtx];
-      los_setup<KIND>(R200[h], M200[h], zred ? zred[h] : 0.0, ctx);
-      double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
-      int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
-      atomicAdd(&map[pix], (MapT)val);
-      break;
-    }
-    run += s.len;
-  }
-  if (n_painted && lane == 0) atomicAdd(n_painted, (unsigned long long)np);
-}
-
-// Compacted bypass: one thread per (halo, pixel ordinal) work item, every lane of a warp busy with its
-// own quadrature (the warp-per-halo kernel above leaves 18-31 lanes idle and still launches a warp for
-// every halo that does not need it).
+// The `len(R) < n_samples` bypass of @interpolate (lib/utils.py:510-511): halos with 1 .. n_samples-1 pixels
+// get the projected profile (one QUADPACK quadrature) at every pixel.  Work items come from K1
+// (ap_disc_count_items: halo * 32 + pixel ordinal, appended on the device, their number in *n_items), so the
+// host never reads a count back; the grid is sized for the SMs and strides over the list, one quadrature per
+// lane.  Pixels outside the calling rank's ring band (ap_band_clip) belong to another rank and are skipped.
 template <int KIND, class MapT>
 __global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev H, const double* p0, const double* p1,
-                                                              const double* p2, const double* scale, int64_t n_items,
-                                                              const int64_t* item_halo, const int32_t* item_ord,
-                                                              MapT* map) {
+                                                              const double* p2, const double* scale,
+                                                              const unsigned long long* n_items, int64_t item_cap,
+                                                              const int64_t* items, MapT* map,
+                                                              unsigned long long* n_painted) {
   fm_smem_init();
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_items) return;
-  const int64_t h = item_halo[t];
-  const int32_t want = item_ord[t];
-  DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
-  HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
-  int32_t run = 0;
-  for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
-    RingSpan s = ring_span(hpx, d, iz);
-    if (s.len <= 0) continue;
-    if (want < run + s.len) {
-      RingGeom g = ring_geom(hpx, iz, s, c);
-      int32_t js = want - run;
-      int32_t ip = s.ip_lo + js;
-      double R = c.D_a * pixel_sep(g, js);
-      double ctx[kCtx];
-      los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
-      double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
-      if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && s.startpix + (ip < 0 ? ip + s.nr : ip) < hpx.npix))
-        atomicAdd(&map[s.startpix + (ip < 0 ? ip + s.nr : ip)], (MapT)val);
-      return;
+  const int64_t total = min((int64_t)*n_items, item_cap);
+  unsigned painted = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t h = items[t] >> 5;
+    const int32_t want = (int32_t)(items[t] & 31);
+    if (!AP_BOUNDS_OK(h >= 0 && h < H.n)) continue;
+    DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+    HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
+    int32_t run = 0;
+    for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+      RingSpan s = ring_span(hpx, d, iz);
+      if (s.len <= 0) continue;
+      if (want < run + s.len) {
+        if (iz < hpx.clip_lo || iz >= hpx.clip_hi) break;  // another rank's ring
+        RingGeom g = ring_geom(hpx, iz, s, c);
+        int32_t js = want - run;
+        int32_t ip = s.ip_lo + js;
+        double R = c.D_a * pixel_sep(g, js);
+        double ctx[kCtx];
+        los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+        double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
+        const int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
+        if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && pix >= hpx.clip_pix0 && pix < hpx.npix)) {
+          atomicAdd(&map[pix - hpx.clip_pix0], (MapT)val);
+          ++painted;
+        }
+        break;
+      }
+      run += s.len;
     }
-    run += s.len;
   }
+  painted = __reduce_add_sync(0xffffffffu, painted);
+  if (n_painted && painted && (threadIdx.x & 31) == 0) atomicAdd(n_painted, (unsigned long long)painted);
 }
 
 template <int KIND>
 static void launch_los_items(bool f32, unsigned blocks, cudaStream_t st, Hpx hpx, HalosDev H, const double* p0,
-                             const double* p1, const double* p2, const double* scale, int64_t n_items,
-                             const int64_t* item_halo, const int32_t* item_ord, void* map) {
+                             const double* p1, const double* p2, const double* scale, const unsigned long long* n_items,
+                             int64_t item_cap, const int64_t* items, void* map, unsigned long long* n_painted) {
   if (f32)
-    paint_los_items_kernel<KIND, float><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, (float*)map);
+    paint_los_items_kernel<KIND, float><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (float*)map, n_painted);
   else
-    paint_los_items_kernel<KIND, double><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, (double*)map);
+    paint_los_items_kernel<KIND, double><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (double*)map, n_painted);
 }
 
 static int paint_los_items_impl(int kind, int64_t nside, const ap_halos* halos, const double* p0, const double* p1,
-                                const double* p2, const double* scale, int64_t n_items, const int64_t* item_halo,
-                                const int32_t* item_ord, void* d_map, bool f32, void* stream) {
+                                const double* p2, const double* scale, const unsigned long long* d_n_items,
+                                int64_t item_cap, const int64_t* d_items, void* d_map, bool f32,
+                                unsigned long long* d_n_painted, void* stream) {
   if (check_nside(nside)) return 1;
   if (check_halos(halos, true)) return 1;
   if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
-  if (n_items < 0) return fail("n_items < 0");
-  if (n_items == 0 || halos->n == 0) return 0;
-  if (!p0 || !p1 || (kind != LOS_NFW_RHO && !p2) || !item_halo || !item_ord || !d_map)
+  if (item_cap < 0) return fail("item_cap < 0");
+  if (item_cap == 0 || halos->n == 0) return 0;
+  if (!p0 || !p1 || (kind != LOS_NFW_RHO && !p2) || !d_n_items || !d_items || !d_map)
     return fail("paint_los_items: NULL pointer");
   if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
-  unsigned blocks = (unsigned)((n_items + 127) / 128);
+  int64_t nb = (item_cap + 127) / 128;
+  if (nb > 148 * 12) nb = 148 * 12;  // 12 resident blocks of 128 threads per SM: the list is walked grid-stride
+  unsigned blocks = (unsigned)nb;
   Hpx hpx = disc_hpx(nside);
   HalosDev H = to_dev(halos);
   cudaStream_t st = (cudaStream_t)stream;
   switch (kind) {
-    case LOS_B16_TAU: launch_los_items<LOS_B16_TAU>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
-    case LOS_B16_NE: launch_los_items<LOS_B16_NE>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
-    case LOS_B16_RHO_GAS: launch_los_items<LOS_B16_RHO_GAS>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
-    case LOS_NFW_RHO: launch_los_items<LOS_NFW_RHO>(f32, blocks, st, hpx, H, p0, p1, p2, scale, n_items, item_halo, item_ord, d_map); break;
+    case LOS_B16_TAU: launch_los_items<LOS_B16_TAU>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
+    case LOS_B16_NE: launch_los_items<LOS_B16_NE>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
+    case LOS_B16_RHO_GAS: launch_los_items<LOS_B16_RHO_GAS>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
+    case LOS_NFW_RHO: launch_los_items<LOS_NFW_RHO>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
   }
   AP_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int ap_paint_los_items(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
-                                  const double* d_p2, const double* d_scale, int64_t n_items, const int64_t* d_item_halo,
-                                  const int32_t* d_item_ord, double* d_map, void* stream) {
-  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, n_items, d_item_halo, d_item_ord, d_map, false, stream);
+                                  const double* d_p2, const double* d_scale, const unsigned long long* d_n_items,
+                                  int64_t item_cap, const int64_t* d_items, double* d_map,
+                                  unsigned long long* d_n_painted, void* stream) {
+  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_items, item_cap, d_items, d_map, false,
+                              d_n_painted, stream);
 }
 extern "C" int ap_paint_los_items_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0,
-                                      const double* d_p1, const double* d_p2, const double* d_scale, int64_t n_items,
-                                      const int64_t* d_item_halo, const int32_t* d_item_ord, float* d_map, void* stream) {
-  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, n_items, d_item_halo, d_item_ord, d_map, true, stream);
-}
-
-template <int KIND>
-static void launch_los_small(bool f32, unsigned blocks, int threads, cudaStream_t st, Hpx hpx, HalosDev H, const double* p0,
-                             const double* p1, const double* p2, const double* scale, const int64_t* n_pix, int32_t ns,
-                             void* map, unsigned long long* n_painted) {
-  if (f32)
-    paint_los_small_kernel<KIND, float><<<blocks, threads, 0, st>>>(hpx, H, p0, p1, p2, scale, n_pix, ns, (float*)map, n_painted);
-  else
-    paint_los_small_kernel<KIND, double><<<blocks, threads, 0, st>>>(hpx, H, p0, p1, p2, scale, n_pix, ns, (double*)map, n_painted);
-}
-
-static int paint_los_small_impl(int kind, int64_t nside, const ap_halos* halos, const double* d_R_200c,
-                                const double* d_M_200c, const double* d_redshift, const double* d_scale,
-                                const int64_t* d_n_pix, int32_t n_samples, void* d_map, bool f32,
-                                unsigned long long* d_n_painted, void* stream) {
-  if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
-  if (check_nside(nside)) return 1;
-  if (check_halos(halos, true)) return 1;
-  if (n_samples < 2 || n_samples > 32) return fail("n_samples must be in [2, 32]");
-  if (halos->n == 0) return 0;
-  if (!d_R_200c || !d_M_200c || (kind != LOS_NFW_RHO && !d_redshift) || !d_n_pix || !d_map)
-    return fail("paint_los_small: NULL pointer");
-  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
-  int threads = 128;
-  int64_t blocks = (halos->n * 32 + threads - 1) / threads;
-  {
-    Hpx hpx = disc_hpx(nside);
-    HalosDev H = to_dev(halos);
-    cudaStream_t st = (cudaStream_t)stream;
-    unsigned nb = (unsigned)blocks;
-    switch (kind) {
-      case LOS_B16_TAU: launch_los_small<LOS_B16_TAU>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
-      case LOS_B16_NE: launch_los_small<LOS_B16_NE>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
-      case LOS_B16_RHO_GAS: launch_los_small<LOS_B16_RHO_GAS>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
-      case LOS_NFW_RHO: launch_los_small<LOS_NFW_RHO>(f32, nb, threads, st, hpx, H, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples, d_map, d_n_painted); break;
-    }
-  }
-  AP_LAUNCH_CHECK();
-  return 0;
-}
-extern "C" int ap_paint_los_small(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
-                                  const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
-                                  double* d_map, unsigned long long* d_n_painted, void* stream) {
-  return paint_los_small_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_pix, n_samples, d_map, false, d_n_painted,
-                              stream);
-}
-extern "C" int ap_paint_los_small_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0,
                                       const double* d_p1, const double* d_p2, const double* d_scale,
-                                      const int64_t* d_n_pix, int32_t n_samples, float* d_map,
-                                      unsigned long long* d_n_painted, void* stream) {
-  return paint_los_small_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_pix, n_samples, d_map, true, d_n_painted,
-                              stream);
-}
-extern "C" int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
-                                  const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
-                                  int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream) {
-  return paint_los_small_impl(LOS_B16_TAU, nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples,
-                              d_map, false, d_n_painted, stream);
-}
-extern "C" int ap_paint_b16_small_f32(int64_t nside, const ap_halos* halos, const double* d_R_200c,
-                                      const double* d_M_200c, const double* d_redshift, const double* d_scale,
-                                      const int64_t* d_n_pix, int32_t n_samples, float* d_map,
-                                      unsigned long long* d_n_painted, void* stream) {
-  return paint_los_small_impl(LOS_B16_TAU, nside, halos, d_R_200c, d_M_200c, d_redshift, d_scale, d_n_pix, n_samples,
-                              d_map, true, d_n_painted, stream);
+                                      const unsigned long long* d_n_items, int64_t item_cap, const int64_t* d_items,
+                                      float* d_map, unsigned long long* d_n_painted, void* stream) {
+  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_items, item_cap, d_items, d_map, true,
+                              d_n_painted, stream);
 }
 
 // ------------------------------------------------------------------------------------------
 // K5: cutouts and stack
 // ------------------------------------------------------------------------------------------
+// healpy CartesianProj.ij2xy (projector.py; reached through projmap at paint_bucket.py:1719): the image grid is
+// ENDPOINT-INCLUSIVE, x_j = lonra'[0] + j (lonra'[1] - lonra'[0]) / (xsize - 1), y_i = latra[0] + i (latra[1] -
+// latra[0]) / (ysize - 1) [deg], with lonra' = flip * lonra[::flip] = [-lonra[1], -lonra[0]] for the default
+// 'astro' flip (-1); xy2vec then takes theta = pi/2 - y, phi = flip * x.  So column 0 looks at longitude
+// offset +lonra[1] (east is left) and the last column at lonra[0].
 struct CutGrid {
-  double lon0, dlon, lat0, dlat;  // x_j = lon0 + (j + 0.5) dlon ; y_i = lat0 + (i + 0.5) dlat  [deg]
+  double x0, dx, y0, dy;  // x_j = dx * j + x0 ; y_i = dy * i + y0  [deg]
   int32_t xsize, ysize;
 };
 
 __device__ __forceinline__ void image_vec(const CutGrid& g, int32_t s, double& vx, double& vy, double& vz) {
   int32_t i = s / g.xsize, j = s - i * g.xsize;
   const double dtor = kPi / 180.0;
-  double x = g.lon0 + ((double)j + 0.5) * g.dlon;
-  double y = g.lat0 + ((double)i + 0.5) * g.dlat;
+  double x = g.dx * (double)j + g.x0;
+  double y = g.dy * (double)i + g.y0;
   double theta = kHalfPi - y * dtor;  // xy2vec: theta = pi/2 - y, phi = flip * x, flip = -1 (astro)
   double phi = -(x * dtor);
   double st, ct, sp, cp;
@@ -1339,10 +1316,10 @@ static int cut_grid(double lon0, double lon1, double lat0, double lat1, int32_t 
   if (span < 0) span += 360.0;
   if (span == 0) span = 360.0;
   if (!(lat0 >= -90.0 && lat1 <= 90.0 && lat0 < lat1)) return fail("invalid lat_range");
-  g.lon0 = lon0;
-  g.dlon = span / xsize;
-  g.lat0 = lat0;
-  g.dlat = (lat1 - lat0) / ysize;
+  g.x0 = -(lon0 + span);   // flip * lonra[::flip][0] with lonra[1] = lonra[0] + span
+  g.dx = xsize > 1 ? span / (double)(xsize - 1) : 0.0;
+  g.y0 = lat0;
+  g.dy = ysize > 1 ? (lat1 - lat0) / (double)(ysize - 1) : 0.0;
   g.xsize = xsize;
   g.ysize = ysize;
   return 0;
@@ -1448,6 +1425,69 @@ extern "C" int ap_spray_host(int profile, int64_t nside, int64_t n, const double
   }
   cleanup();
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// host map plumbing: page-locking of a caller-owned host range (the rank's band of a map shared between the
+// processes of one node) and the asynchronous band copy device -> host
+// ------------------------------------------------------------------------------------------
+extern "C" int ap_host_register(void* h_ptr, uint64_t bytes) {
+  if (!h_ptr || bytes == 0) return fail("host_register: empty range");
+  cudaError_t e = cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+extern "C" int ap_host_unregister(void* h_ptr) {
+  if (!h_ptr) return fail("host_unregister: NULL");
+  cudaError_t e = cudaHostUnregister(h_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+extern "C" int ap_copy_d2h_async(void* h_dst, const void* d_src, uint64_t bytes, void* stream) {
+  if (bytes == 0) return 0;
+  if (!h_dst || !d_src) return fail("copy_d2h: NULL pointer");
+  cudaError_t e = cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(std::string("cudaMemcpyAsync(D2H): ") + cudaGetErrorString(e));
+  return 0;
+}
+extern "C" int ap_copy_h2d_async(void* d_dst, const void* h_src, uint64_t bytes, void* stream) {
+  if (bytes == 0) return 0;
+  if (!d_dst || !h_src) return fail("copy_h2d: NULL pointer");
+  cudaError_t e = cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(std::string("cudaMemcpyAsync(H2D): ") + cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp64 roofline probe: 8 independent DFMA chains per thread, register operands, 8 blocks of 256 threads per
+// SM.  bench.py times it with CUDA events next to the QUADPACK node kernel: the denominator of that kernel's
+// roofline fraction is this MEASURED fp64 instruction rate (MEASURED_PEAKS.json has no fp64 entry).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) x[c] = threadIdx.x * 1e-9 + c;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = fma(x[c], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s += x[c];
+  if (s == 1.2345) out[0] = s;  // never true: keeps the chains alive
+}
+extern "C" int ap_fp64_peak(int32_t iters, int32_t blocks, double* d_out, uint64_t* h_n_dfma, void* stream) {
+  if (iters < 1 || blocks < 1 || !d_out) return fail("fp64_peak: bad arguments");
+  fp64_peak_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_out, iters, 1.0000001, 1e-9);
+  AP_LAUNCH_CHECK();
+  if (h_n_dfma) *h_n_dfma = (uint64_t)blocks * 256ull * 8ull * (uint64_t)iters;  // thread-level DFMAs issued
+  return 0;
 }
 
 // K6: per-cutout operators (rotate / taper / weight / stack) for Canvas.cutouts(apply_func=...)

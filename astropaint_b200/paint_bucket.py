@@ -62,6 +62,7 @@ class Catalog:
     @data.setter
     def data(self, val):
         self._pinned = None
+        self._order = None
         self._data = pd.DataFrame(val).reset_index(drop=True)
         self.size = len(self._data)
         self.box_size = self._get_box_size()
@@ -70,12 +71,28 @@ class Catalog:
         self.build_dataframe(calculate_redshifts=self.calculate_redshifts,
                              default_redshift=self.default_redshift, device=self.device_build)
 
+    def theta_order(self):
+        """(order, theta_sorted, r_ang_max): the catalog rows by increasing colatitude of the disc centre
+        (formed from x, y, z exactly like hp.query_disc's centre, paint_bucket.py:1223-1225), that colatitude,
+        and the largest R_ang_200c [arcmin].  The painting path walks the halos in this order: the halos that
+        can touch one ring band of the map are then ONE contiguous slice (astropaint_b200/_bands.py), and
+        consecutive halos write neighbouring rings.  Computed once per catalog, invalidated with `data`."""
+        if getattr(self, "_order", None) is None:
+            d = self._data
+            x, y, z = (d[k].values.astype(np.float64, copy=False) for k in ("x", "y", "z"))
+            key = np.arctan2(np.hypot(x, y), z)
+            order = np.argsort(key, kind="stable")
+            r_ang_max = float(np.nanmax(d["R_ang_200c"].values)) if len(d) else 0.0
+            self._order = (order, key[order], r_ang_max)
+        return self._order
+
     def pin_memory(self):
-        """Stage every numeric column in page-locked host memory (torch pinned tensors) so that each
-        spray uploads its inputs with one DMA per column instead of pageable copies.  Optional;
-        invalidated whenever `data` is reassigned."""
+        """Stage every numeric column in page-locked host memory (torch pinned tensors), rows in colatitude
+        order (`theta_order`), so that each spray uploads the slice of halos it needs with one DMA per column
+        instead of pageable, gathered copies.  Optional; invalidated whenever `data` is reassigned."""
         import torch
-        self._pinned = {k: torch.from_numpy(np.ascontiguousarray(self._data[k].values, dtype=np.float64)).pin_memory()
+        order = self.theta_order()[0]
+        self._pinned = {k: torch.from_numpy(np.ascontiguousarray(self._data[k].values[order], dtype=np.float64)).pin_memory()
                         for k in self._data.columns if np.issubdtype(self._data[k].dtype, np.number)}
         return self
 
@@ -286,8 +303,14 @@ class Canvas:
         self._catalog = Catalog() if catalog is None else catalog
         self.template_name = None
         self.stack = None
-        self._host_buf = None
-        self._prefetch = None
+        self._host = None          # _bands.SharedHostMap: page-locked host copy the device map is read back into
+        self._host_stale = False   # clean() / the setter ran since the buffer was last handed out
+        self._prefetch = None      # (copy stream, band pixels already queued) of a streaming spray
+        self._dfull = None
+        self._band_cache = None
+        self._band_override = None
+        self._dmap = None
+        self._dmap_spare = None
         self.clean()
         self.instantiate_discs()
 
@@ -317,33 +340,73 @@ class Canvas:
         return self._catalog.data.D_a
 
     # ---- pixel state: "zero" | "host" | "device" ------------------------------------------------
+    # "device": the authoritative copy is the rank's ring band of the map in HBM (the whole map when there is
+    # one rank); "host": it is the numpy array `_pixels` (every rank sees the same one); "zero": nothing allocated.
+    def _band(self):
+        from . import parallel, _bands
+        if self._band_override is not None:      # tests: paint one rank's band of an N-rank layout on one GPU
+            return self._band_override
+        rank, ws = parallel.world()
+        b = self._band_cache
+        if b is None or (b.rank, b.world_size, b.nside) != (rank, ws, self.nside):
+            if b is not None and self._state == "device":
+                raise RuntimeError("the process group changed while the canvas held a device map; read canvas.pixels "
+                                   "(or clean()) before initialising / destroying torch.distributed")
+            self._band_cache = b = _bands.Band(self.nside, rank, ws)
+        return b
+
     @property
     def pixels(self):
-        """Host view of the map (np.ndarray, fp64).  Reading it after a spray copies the device map
-        back once; the host array is then authoritative (users index and mutate it in place, e.g.
-        README.md:40-48), so the next spray uploads it again.  `pixels_device` avoids both copies."""
+        """Host view of the map (np.ndarray, fp64).  Reading it after a spray copies the device map back once
+        (only the part the spray has not already streamed); the host array is then authoritative (users index
+        and mutate it in place, e.g. README.md:40-48), so the next spray uploads it again.  `pixels_device`
+        avoids both copies.  With several ranks the call is collective: every rank copies its own band into one
+        host array shared by the node and every rank gets a view of the whole map."""
         if self._state == "zero":
             self._pixels = np.zeros(self.npix, dtype=self._np_dtype)
         elif self._state == "device":
             import torch
-            if self._host_buf is None:  # page-locked, reused across clean(): one DMA per read-back
-                self._host_buf = torch.empty(self.npix, dtype=self._dmap.dtype, pin_memory=True)
-                self._prefetch = None
+            from . import parallel
+            band = self._band()
             if self._prefetch is not None:
-                # the spray already streamed the finished ring bands to the host on a copy stream
-                # (Painter._paint_device_table); fetch whatever is left
+                # the spray already streamed the finished rings to the host on a copy stream; fetch the rest
                 stream, upto = self._prefetch
-                stream.synchronize()
-                if upto < self.npix:
-                    self._host_buf[upto:].copy_(self._dmap[upto:])
+                host = self._host
                 self._prefetch = None
             else:
-                self._host_buf.copy_(self._dmap)
-            self._pixels = self._host_buf.numpy()
+                host = self._reusable_host() or self._new_host()
+                stream, upto = None, 0
+            if upto < band.npix:
+                eng.copy_d2h(host.band_view(upto, band.npix), self._dmap[upto:])
+            if stream is not None:
+                stream.synchronize()
+            torch.cuda.current_stream().synchronize()
+            parallel.barrier()           # every rank's band has landed before anyone reads the map
+            self._pixels = host.array
             self._dmap_spare = self._dmap
             self._dmap = None
+            self._dfull = None
         self._state = "host"
         return self._pixels
+
+    def _new_host(self):
+        from . import _bands
+        self._host = _bands.SharedHostMap(self.npix, self._np_dtype, self._band())
+        return self._host
+
+    def _reusable_host(self):
+        """The read-back buffer of an earlier `.pixels`, if it may be written again: never once the array has been
+        handed to the user and is still referenced (the reference's clean() allocates a fresh array,
+        paint_bucket.py:1316, so a map kept across clean() must survive).  Collective with several ranks."""
+        from . import parallel
+        if self._host is None:
+            return None
+        ok = (not self._host_stale) or (not self._host.handed_out())
+        ok = ok and self._host.dtype == np.dtype(self._np_dtype) and self._host.npix == self.npix
+        if not parallel.all_agree(ok):
+            self._host = None
+        self._host_stale = False
+        return self._host
 
     def _cancel_prefetch(self):
         if self._prefetch is not None:
@@ -355,6 +418,8 @@ class Canvas:
         self._cancel_prefetch()
         self._pixels = val
         self._dmap = None
+        self._dfull = None
+        self._host_stale = True
         self._state = "host"
         self._pixel_is_outdated = False
         self._alm_is_outdated = True
@@ -365,25 +430,47 @@ class Canvas:
         return np.float32 if self.accumulate == "fp32" else np.float64
 
     @property
-    def pixels_device(self):
-        """The map as a torch CUDA tensor (fp64[npix]); allocated / uploaded on first use."""
+    def _torch_dtype(self):
+        import torch
+        return torch.float32 if self.accumulate == "fp32" else torch.float64
+
+    def _device_band(self):
+        """The rank's band of the map as a torch CUDA tensor (the whole map with one rank); allocated, zeroed or
+        uploaded from the host copy on first use.  This is what the painting kernels accumulate into."""
         import torch
         dev = eng.require_cuda()
-        tdt = torch.float32 if self.accumulate == "fp32" else torch.float64
+        band = self._band()
         if self._state != "device":
             self._cancel_prefetch()
+            self._dfull = None
         if self._state == "zero":
-            if self._dmap_spare is not None and self._dmap_spare.device == dev:
-                self._dmap = self._dmap_spare.zero_()
-                self._dmap_spare = None
+            sp = self._dmap_spare
+            if sp is not None and sp.device == dev and sp.numel() == band.npix and sp.dtype == self._torch_dtype:
+                self._dmap = sp.zero_()
             else:
-                self._dmap = torch.zeros(self.npix, dtype=tdt, device=dev)
+                self._dmap = torch.zeros(band.npix, dtype=self._torch_dtype, device=dev)
+            self._dmap_spare = None
         elif self._state == "host":
-            host = np.ascontiguousarray(np.broadcast_to(np.asarray(self._pixels, dtype=self._np_dtype), (self.npix,)))
+            host = np.broadcast_to(np.asarray(self._pixels, dtype=self._np_dtype), (self.npix,))
+            host = np.ascontiguousarray(host[band.pix_lo:band.pix_hi])
             self._dmap = torch.from_numpy(host).to(dev)
             self._pixels = None
         self._state = "device"
         return self._dmap
+
+    @property
+    def pixels_device(self):
+        """The whole map as a torch CUDA tensor (fp64[npix]).  With one rank this is the tensor the kernels paint
+        into; with several it is gathered from the owners' bands over NVLink (collective) and cached until the
+        map changes."""
+        d_band = self._device_band()
+        band = self._band()
+        if band.whole:
+            return d_band
+        if self._dfull is None:
+            from . import parallel
+            self._dfull = parallel.gather_bands(d_band, band, self._torch_dtype)
+        return self._dfull
 
     # ---- map sinks (SURVEY 8f rank 4) ---------------------------------------------------------------
     def ud_grade(self, nside_out, inplace=True, **kwargs):
@@ -392,6 +479,7 @@ class Canvas:
         unknown = set(kwargs) - {"pess", "power"}
         if unknown:
             raise TypeError(f"ud_grade() got unsupported healpy arguments {sorted(unknown)}")
+        whole = self._band().whole
         new_map = eng.ud_grade(self.pixels_device, self.nside, int(nside_out), kwargs.get("pess", False),
                                kwargs.get("power", None))
         if self.accumulate == "fp32":
@@ -399,11 +487,18 @@ class Canvas:
         if not inplace:
             return new_map.cpu().numpy()
         self._cancel_prefetch()
+        self._state = "zero"           # the old map is dropped below; lets _band() re-derive the ownership
+        self._band_cache = None
         self._nside = int(nside_out)
         self._npix = 12 * self._nside * self._nside
         self._lmax = 3 * self._nside - 1
-        self._dmap, self._dmap_spare, self._host_buf, self._pixels = new_map, None, None, None
-        self._state = "device"
+        if not whole:     # several ranks: hold the new map on the host (every rank has all of it)
+            self._dmap, self._dmap_spare, self._host, self._dfull = None, None, None, None
+            self._pixels = new_map.cpu().numpy()
+            self._state = "host"
+        else:
+            self._dmap, self._dmap_spare, self._host, self._pixels, self._dfull = new_map, None, None, None, None
+            self._state = "device"
         self.discs = self.Disc(self.catalog, self.nside, self.R_times, self.inclusive)
         self._mark_painted()
 
@@ -458,9 +553,10 @@ class Canvas:
         """Set all pixels to zero (paint_bucket.py:1307-1323)."""
         self._cancel_prefetch()
         self._pixels = None
+        self._dfull = None
+        self._host_stale = True    # a host array handed out before this point is the user's from now on
         # keep the HBM allocation for the next spray instead of returning 8*npix bytes to the allocator
-        self._dmap_spare = getattr(self, "_dmap", None) if getattr(self, "_dmap", None) is not None \
-            else getattr(self, "_dmap_spare", None)
+        self._dmap_spare = self._dmap if self._dmap is not None else self._dmap_spare
         self._dmap = None
         self._state = "zero"
         self._pixel_is_outdated = False
@@ -806,10 +902,9 @@ class Painter:
 
         Same contract as the reference (paint_bucket.py:2296-2495).  `n_cpus` only validates
         (0 raises ValueError): the halos are painted by CUDA kernels, and when torch.distributed is
-        initialised with more than one rank each rank paints its block of the catalog
-        (np.array_split, as the reference splits across threads) and the partial maps are summed
-        over NVLink.  `cache` is accepted and ignored; `lazy` snaps the template's per-halo
-        arguments to 500-point grids as the reference does.
+        initialised with more than one rank the call is collective: each rank owns one ring band of the
+        map and paints the halos that touch it (parallel.py).  `cache` is accepted and ignored; `lazy`
+        snaps the template's per-halo arguments to 500-point grids as the reference does.
         """
         _say("Painting the canvas...")
         canvas._cancel_prefetch()
@@ -828,64 +923,159 @@ class Painter:
                 grid = np.linspace(data.min(), data.max(), 500)
                 host_cols[key] = grid[np.searchsorted(grid, data)]
             self._catalog_cols = set()
-        from . import parallel
-        stats = parallel.spray_sharded(self, canvas, R_mode, host_cols, template_kwargs,
-                                       pinned=getattr(canvas.catalog, "_pinned", None))
+        with eng.disc_mode(canvas.inclusive):
+            if self._device_info(template_kwargs) is not None:
+                stats = self._spray_banded(canvas, host_cols, template_kwargs)
+            else:
+                stats = self._spray_host_template(canvas, R_mode, host_cols, template_kwargs)
         canvas._mark_painted()
         self.last_spray = stats
         _say("Your artwork is finished. Check it out with Canvas.show_map()")
 
-    # ------------------------ one rank's share ------------------------
-    def _paint_rows(self, canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned=None, band_done=None):
-        """Paint catalog rows `rows` (None = all) into the device map d_map; returns stats dict.
-        Canvas(inclusive=True) switches every disc query of the spray to healpy's inclusive one."""
-        with eng.disc_mode(canvas.inclusive):
-            return self._paint_rows_impl(canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned, band_done)
-
-    def _paint_rows_impl(self, canvas, rows, R_mode, host_cols, template_kwargs, d_map, pinned=None, band_done=None):
-        import torch
-        dev = d_map.device
-        data = canvas.catalog.data
-        halos = eng.DeviceHalos(data, canvas.R_times, dev, rows=rows, pinned=pinned)
-        nside = canvas.nside
-        d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    def _device_info(self, template_kwargs):
+        """("profile" | "table", registry entry) when the template has a CUDA twin that covers this call: every
+        spray kwarg must be one of the twin's parameters -- anything else (e.g. NFW.deflection_angle's
+        `suppress=False`) is a feature only the Python template has, so the call takes the host-template path,
+        which forwards all kwargs exactly like the reference's loop (paint_bucket.py:2386-2389)."""
         tmpl = self.template
+        if self.R_arg_indx != 0:
+            return None
+        info = getattr(tmpl, "_ap_device", None)
+        if info is not None:
+            known = set(info["args"]) | set(info["kwonly"])
+            return ("profile", info) if set(template_kwargs) <= known else None
+        info = getattr(tmpl, "_ap_device_table", None)
+        if info is not None:
+            known = set(info["args"])
+            if info["scale"] is not None:
+                known |= set(info["scale"]["args"]) | set(info["scale"]["kwonly"])
+            return ("table", info) if set(template_kwargs) <= known else None
+        return None
+
+    # ------------------------ device templates: ring-band ownership ------------------------
+    #: catalogs with at least this many halos per rank stream the finished rings of the map to the host while the
+    #: remaining halos are still being painted (only once the host copy has been read before)
+    PREFETCH_MIN_HALOS = 200000
+
+    def _spray_banded(self, canvas, host_cols, template_kwargs, timers=None):
+        """Built-in templates (device functions and device-tabulated @interpolate(@LOS_integrate) profiles): this
+        rank paints the halos whose disc touches ITS ring band of the map (parallel.py, _bands.py), in
+        colatitude order, chunk by chunk; finished rings go device -> host on a copy stream meanwhile."""
+        import torch
+        from . import _bands
+        kind, info = self._device_info(template_kwargs)
+        band = canvas._band()
+        cat = canvas.catalog
+        nside = canvas.nside
+        order, theta_sorted, r_ang_max = cat.theta_order()
+        rmax = float(canvas.R_times) * float(transform.arcmin2rad(r_ang_max))
+        if canvas.inclusive:
+            rmax += 4.0 / nside          # the inclusive query widens every disc by about one pixel radius
+        d_band = canvas._device_band()
+        dev = d_band.device
+        # the decision to stream must be the same on every rank: it depends on the catalog size only
+        host = None
+        if cat.size // band.world_size >= self.PREFETCH_MIN_HALOS:
+            host = canvas._reusable_host()
+        plan = _bands.Plan(band, theta_sorted, rmax, n_chunks=None if host is not None else 1)
+        lo, hi = plan.halo_lo, plan.halo_hi
+        rows = order[lo:hi]
+        pinned = getattr(cat, "_pinned", None)
+        halos = eng.DeviceHalos(cat.data, canvas.R_times, dev, rows=rows, pinned=pinned,
+                                pinned_range=(lo, hi) if pinned else None)
+        d_count = torch.zeros(1, dtype=torch.int64, device=dev)
 
         def col(name, defaults=None):
             """device tensor of a template argument: spray kwarg > catalog column > kw-only default"""
             if name in host_cols:
                 if name in self._catalog_cols:
-                    return halos.col(name)  # unmodified catalog column: cached / pinned upload
-                v = host_cols[name]
-                return eng.to_device(v if rows is None else v[rows], dev)
+                    return halos.col(name)   # unmodified catalog column: pinned slice / gathered upload
+                return eng.to_device(np.asarray(host_cols[name])[rows], dev)
             if defaults and name in defaults:
                 return torch.full((1,), float(defaults[name]), dtype=torch.float64, device=dev)
             raise TypeError(f"{self.template_name}() missing required argument: '{name}'")
 
-        path = "flat"
-        if getattr(tmpl, "_ap_device", None) is not None and self.R_arg_indx == 0:
-            info = tmpl._ap_device
+        def cut(t, a, e):
+            return t if t.numel() == 1 else t[a:e]
+
+        if kind == "profile":
             params = [col(a) for a in info["args"]] + [col(k, info["kwonly"]) for k in info["kwonly"]]
-            eng.paint_profile(halos, nside, info["id"], params, d_map, d_count)
+
+            def paint_chunk(a, e):
+                eng.paint_profile(halos.view(a, e), nside, info["id"], [cut(t, a, e) for t in params], d_band, d_count)
             path = "device_profile"
-        elif getattr(tmpl, "_ap_device_table", None) is not None and self.R_arg_indx == 0:
-            prefetch = None
-            if (canvas._host_buf is not None and canvas._state == "device" and d_map is canvas._dmap
-                    and halos.n >= self.PREFETCH_MIN_HALOS and canvas._host_buf.dtype == d_map.dtype):
-                prefetch = canvas  # the host copy of the map has been asked for before: stream it back
-            banded = band_done if halos.n >= self.PREFETCH_MIN_HALOS else None
-            self._paint_device_table(tmpl._ap_device_table, halos, nside, col, template_kwargs, d_map, d_count,
-                                     prefetch, banded)
-            path = "device_table" + ("+prefetch" if prefetch is not None else "") + ("+bands" if banded else "")
-            band_done = None if banded else band_done
-        elif self._interp_info() is not None:
+        else:
+            assert info["kind"] in eng.LOS_KINDS
+            args = [col(a) for a in info["args"]]
+            args = [t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in args]
+            scale = None
+            if info["scale"] is not None:
+                sc = info["scale"]
+                cols = {a: col(a) for a in sc["args"]}
+                kw = {k: col(k, sc["kwonly"]) for k in sc["kwonly"]}
+                scale = sc["fn"](cols, kw)
+                scale = (scale if scale.numel() == halos.n else scale.expand(halos.n)).contiguous()
+
+            def paint_chunk(a, e):
+                eng.table_chunk(halos.view(a, e), nside, info["kind"], [t[a:e] for t in args],
+                                scale[a:e] if scale is not None else None, info["n_samples"],
+                                info["sampling_method"], d_band, d_count, timers)
+            path = "device_table"
+
+        chunk_done = None
+        if host is not None:
+            copy_stream = torch.cuda.Stream(device=dev)
+
+            def chunk_done(rel_lo, rel_hi):
+                ev = torch.cuda.Event()
+                ev.record()
+                copy_stream.wait_event(ev)
+                eng.copy_d2h(host.band_view(rel_lo, rel_hi), d_band[rel_lo:rel_hi], stream=copy_stream)
+            path += "+stream"
+        eng.run_chunks(plan, paint_chunk, chunk_done)
+        if host is not None:
+            canvas._prefetch = (copy_stream, band.npix)
+        canvas._dfull = None
+        return {"path": path, "n_halos": halos.n, "d_count": d_count, "world_size": band.world_size,
+                "chunks": len(plan.chunks), "band": (band.ring_lo, band.ring_hi)}
+
+    # ------------------------ host templates: the reference's halo batches ------------------------
+    def _spray_host_template(self, canvas, R_mode, host_cols, template_kwargs):
+        """Arbitrary Python templates (and @interpolate-wrapped Python profiles): the template runs on the host
+        once per halo as in the reference; disc query, geometry, spline and scatter run on the device.  With
+        several ranks each paints its np.array_split block of the catalog (paint_bucket.py:2414) into a full-sky
+        partial map; the partial maps are summed over NVLink and every rank keeps its own band of the sum."""
+        import torch
+        from . import parallel
+        band = canvas._band()
+        d_band = canvas._device_band()
+        if band.whole:
+            stats = self._paint_rows(canvas, None, R_mode, host_cols, d_band)
+        else:
+            rows = parallel.shard_rows(canvas.catalog.size, band.rank, band.world_size)
+            partial = torch.zeros(canvas.npix, dtype=d_band.dtype, device=d_band.device)
+            stats = self._paint_rows(canvas, rows, R_mode, host_cols, partial)
+            parallel.reduce_partial_map(partial, "all")
+            d_band += partial[band.pix_lo:band.pix_hi]
+            del partial
+        canvas._dfull = None
+        stats["world_size"] = band.world_size
+        return stats
+
+    def _paint_rows(self, canvas, rows, R_mode, host_cols, d_map):
+        """Paint catalog rows `rows` (None = all) into the full-size device map d_map; returns stats dict."""
+        import torch
+        dev = d_map.device
+        halos = eng.DeviceHalos(canvas.catalog.data, canvas.R_times, dev, rows=rows)
+        nside = canvas.nside
+        d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        if self._interp_info() is not None:
             self._paint_python_table(self._interp_info(), halos, nside, rows, R_mode, host_cols, d_map, d_count)
             path = "python_table"
         else:
             hc = host_cols if rows is None else {k: v[rows] for k, v in host_cols.items()}
-            eng.spray_flat(halos, nside, tmpl, R_mode, hc, d_map, d_count)
-        if band_done is not None:      # paths that do not work band by band: the whole map at once
-            band_done(0, 0, d_map.numel())
+            eng.spray_flat(halos, nside, self.template, R_mode, hc, d_map, d_count)
+            path = "flat"
         return {"path": path, "n_halos": halos.n, "d_count": d_count}
 
     def _interp_info(self):
@@ -897,50 +1087,6 @@ class Painter:
         if info["sampling_method"] not in ("linspace", "logspace") or not (4 <= info["n_samples"] <= 32):
             return None
         return info
-
-    #: catalogs at least this large stream finished ring bands of the map to the host while the remaining
-    #: halos are still being integrated (only once the host copy has been read before)
-    PREFETCH_MIN_HALOS = 200000
-    PREFETCH_CHUNKS = 10     # ring bands of geometrically shrinking area (eng.BAND_RATIO): the exposed tail is the last one
-
-    def _paint_device_table(self, info, halos, nside, col, template_kwargs, d_map, d_count, prefetch=None,
-                            band_done=None):
-        """@interpolate(@LOS_integrate(profile_3D)) entirely on device (eng.table_spray: K1/K4/K3).
-
-        With `prefetch` (the Canvas whose pinned host buffer should receive the map) or `band_done` (the
-        multi-GPU reduce) the halos are processed ring band by ring band (eng.table_spray) and every
-        finished band is shipped on a second stream while the next band is in its QUADPACK phase.
-        """
-        import torch
-        assert info["kind"] in eng.LOS_KINDS
-        args = [col(a) for a in info["args"]]
-        args = [t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in args]
-        scale = None
-        if info["scale"] is not None:
-            sc = info["scale"]
-            cols = {a: col(a) for a in sc["args"]}
-            kw = {k: col(k, sc["kwonly"]) for k in sc["kwonly"]}
-            scale = sc["fn"](cols, kw)
-            scale = scale if scale.numel() == halos.n else scale.expand(halos.n)
-            scale = scale.contiguous()
-        n_bands = 1
-        if prefetch is not None:
-            canvas = prefetch
-            copy_stream = torch.cuda.Stream(device=d_map.device)
-
-            def band_done(k, p_lo, p_hi):  # noqa: F811
-                ev = torch.cuda.Event()
-                ev.record()
-                copy_stream.wait_event(ev)
-                with torch.cuda.stream(copy_stream):
-                    canvas._host_buf[p_lo:p_hi].copy_(d_map[p_lo:p_hi], non_blocking=True)
-            n_bands = self.PREFETCH_CHUNKS
-        elif band_done is not None:
-            n_bands = self.PREFETCH_CHUNKS
-        eng.table_spray(halos, nside, info["kind"], args, scale, info["n_samples"], info["sampling_method"], d_map,
-                        d_count, n_bands=n_bands, band_done=band_done)
-        if prefetch is not None:
-            prefetch._prefetch = (copy_stream, prefetch.npix)
 
     def _paint_python_table(self, info, halos, nside, rows, R_mode, host_cols, d_map, d_count):
         """A Python template wrapped in @interpolate: nodes, spline and painting on device; the

@@ -1,12 +1,16 @@
-"""Halo-sharded painting across the GPUs of one node.
+"""Multi-GPU painting: one process per GPU (torch.distributed, NCCL over NVLink 5), ring-band ownership.
 
-The reference's only parallelism is `np.array_split(range(N), n_cpus)` batches of halos painted
-by joblib threads into one shared array (paint_bucket.py:2402-2433).  Here each rank (one process
-per GPU, torch.distributed / NCCL over NVLink 5) paints its block of the catalog into a full-sky
-partial map in its own HBM and the partial maps are summed with NCCL all-reduces (fp64, npix values
-in total; ring band by ring band, overlapped with the next band's QUADPACK phase, for tabulated
-templates); the result is added to the canvas on every rank, so all ranks end with the same
-map the single-process path would have produced (up to fp64 summation order).
+The reference's only parallelism is `np.array_split(range(N), n_cpus)` batches of halos painted by joblib
+threads into one shared array (paint_bucket.py:2402-2433).  Here every rank OWNS one ring band of the map
+(_bands.Band: an equal share of the sphere's area, contiguous in RING order) and paints the halos whose disc
+touches it, clipped to its own rings -- no partial maps and no reduction.  The host copy
+of the map is one array shared by the ranks of the node (_bands.SharedHostMap); each rank copies its band into
+it over its own PCIe link.
+
+Under world_size > 1 the Canvas / Painter calls are SPMD-collective: every rank makes the same calls on the
+same catalog.  Templates that run on the host (arbitrary Python callables) keep the reference's halo batches:
+rank r paints rows np.array_split(range(N), world)[r] into a full-sky partial map, the partial maps are summed
+(NCCL all-reduce) and every rank adds its own band of the sum.
 """
 import numpy as np
 
@@ -23,7 +27,8 @@ def world():
 
 
 def shard_rows(n_halos, rank, world_size):
-    """Catalog rows painted by `rank`: contiguous blocks, as np.array_split(range(N), n) gives."""
+    """Catalog rows painted by `rank` on the host-template path: contiguous blocks, as
+    np.array_split(range(N), n) gives (paint_bucket.py:2414)."""
     return np.array_split(np.arange(n_halos), world_size)[rank]
 
 
@@ -37,30 +42,34 @@ def reduce_partial_map(partial, op="all"):
     return partial
 
 
-def spray_sharded(painter, canvas, R_mode, host_cols, template_kwargs, pinned=None):
-    import torch
+def all_agree(flag):
+    """True iff `flag` is true on every rank (one tiny all-reduce; the identity when not distributed)."""
     rank, ws = world()
     if ws == 1:
-        d_map = canvas.pixels_device
-        stats = painter._paint_rows(canvas, None, R_mode, host_cols, template_kwargs, d_map, pinned=pinned)
-        stats["world_size"] = 1
-        return stats
+        return bool(flag)
+    import torch
     import torch.distributed as dist
-    rows = shard_rows(canvas.catalog.size, rank, ws)
-    base = canvas.pixels_device
-    partial = torch.zeros_like(base)
-    works = []
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
 
-    def band_done(k, p_lo, p_hi):
-        # the band is final on this rank: sum it over the ranks on NCCL's stream while the next band of
-        # halos is still being integrated (table templates); other paths call this once for the whole map
-        if p_hi > p_lo:
-            works.append(dist.all_reduce(partial[p_lo:p_hi], op=dist.ReduceOp.SUM, async_op=True))
 
-    stats = painter._paint_rows(canvas, rows, R_mode, host_cols, template_kwargs, partial, pinned=pinned,
-                                band_done=band_done)
-    for w in works:
-        w.wait()
-    base += partial
-    stats["world_size"] = ws
-    return stats
+def barrier():
+    rank, ws = world()
+    if ws > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def gather_bands(d_band, band, dtype):
+    """Full map on every rank's device from the owners' bands: one broadcast per band over NVLink."""
+    import torch
+    import torch.distributed as dist
+    full = torch.empty(12 * band.nside * band.nside, dtype=dtype, device=d_band.device)
+    full[band.pix_lo:band.pix_hi].copy_(d_band)
+    for g in range(band.world_size):
+        lo, hi = band.pix_bounds[g], band.pix_bounds[g + 1]
+        if hi > lo:
+            dist.broadcast(full[lo:hi], src=g)
+    return full

@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """bench.py — painted halo-pixels/s of Painter.spray at nside 8192 (BASELINE.json's metric).
 
-Workload (N = 1 and every N): BASELINE config 3's shape — a Websky-shaped full-sky catalog painted
-with Battaglia16.kSZ_T (tau_2D_interp x v_r) at nside 8192, R_times 5.  Weak scaling: every rank
-(one process per GPU) paints its own --halos halos (seed 1 + rank) into a full-sky partial map and
-the partial maps are summed with one NCCL all-reduce inside the timed step.
+Workload (every N): BASELINE config 3 — ONE Websky-shaped full-sky catalog of --halos (1e7) halos painted with
+Battaglia16.kSZ_T (tau_2D_interp x v_r) at nside 8192, R_times 5.  Strong scaling: with N ranks (one process
+per GPU) each rank owns one ring band of the map (an equal share of the sphere's area) and paints the halos
+whose disc touches it; there is no partial map and no reduction (astropaint_b200/_bands.py, parallel.py).
 
-One JSON line on stdout (rank 0).  `value` is device-resident throughput (inputs in HBM), `e2e` the
-same metric through the public API (Painter.spray on a host catalog: pinned host->device copies of
-the catalog columns, device->host read-back of the map) — see the task contract for the keys.
+One JSON line on stdout (rank 0).  `value` is device-resident throughput (the rank's halo slice already in HBM,
+map band zeroed and painted inside the timed step); `e2e` is the same metric through the public API on a
+host catalog: Canvas.clean(); Painter.spray(canvas); canvas.pixels -- pinned host->device copies of each
+rank's catalog slice and device->host copies of every rank's band into the node's shared host map inside the
+timed region.
 
   python bench.py                                   # N=1, defaults finish in a few minutes
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
   python bench.py --impl reference                  # the CPU restatement of the reference loop
+  python bench.py --config C4 --steps 2 --warmup 1  # one of the other BASELINE configs alone (for ncu)
 """
 import argparse
 import json
@@ -31,6 +34,9 @@ NSIDE = 8192
 R_TIMES = 5
 METRIC = "painted halo-pixels/s for Painter.spray at nside 8192"
 UNIT = "halo-pixels/s"
+#: fp64 instructions per integrand evaluation in the hot loop of los_nodes_kernel<b16_tau> (SASS of qk15i_rm's
+#: four-evaluation trip, profiles/README.md): the ALGORITHMIC fp64 work of one QUADPACK function evaluation
+FP64_INSTR_PER_EVAL = 56
 
 
 def parse():
@@ -39,20 +45,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--halos", type=int, default=10_000_000, help="halos per GPU (BASELINE config 3: 1e7)")
+    ap.add_argument("--halos", type=int, default=10_000_000, help="halos of the WHOLE catalog (BASELINE config 3: 1e7)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-halos", type=int, default=400, help="halos of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short C1/C2/C4/C5 runs after the headline")
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="C3 = the headline workload; another value times only that BASELINE config (N=1)")
     return ap.parse_args()
 
 
 def config(args, n_gpus):
-    return {"workload": f"BASELINE config 3 shape: Websky-shaped synthetic full-sky catalog, {args.halos} halos per GPU, "
+    return {"workload": f"BASELINE config 3: Websky-shaped synthetic full-sky catalog, {args.halos} halos in total, "
                         f"Battaglia16.kSZ_T (tau_2D_interp x v_r), nside {NSIDE}, R_times {R_TIMES}",
-            "halos_per_gpu": args.halos, "nside": NSIDE, "R_times": R_TIMES,
-            "template": "Battaglia16.kSZ_T", "parallelism": f"halo-sharded x{n_gpus} + NCCL all-reduce of partial maps (per ring band, overlapped)",
-            "l2": "fp64 map of 6.44 GB and >1 GB of catalog columns per step: inputs larger than the 126 MB L2"}
+            "halos_total": args.halos, "nside": NSIDE, "R_times": R_TIMES, "template": "Battaglia16.kSZ_T",
+            "parallelism": f"ring-band ownership x{n_gpus}: each rank paints the halos touching its band of the map, "
+                           "no partial maps, no reduction; bands copied to one shared host map over each GPU's own PCIe link",
+            "catalog_staging": "Catalog.pin_memory(): columns page-locked in colatitude order, once per catalog, "
+                               "outside the timed region",
+            "l2": "fp64 map of 6.44 GB and >1 GB of catalog columns and tables per step: inputs larger than the 126 MB L2"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -81,7 +93,7 @@ def cpu_sample(n_halos, n_procs, seed=1):
     import astropaint_b200 as ap
     from astropaint_b200 import synthetic
     ap.paint_bucket.verbose = False
-    df = ap.Catalog(synthetic.websky_like(n_halos, seed=seed)).data
+    df = ap.Catalog(synthetic.websky_like(n_halos, seed=seed), device=False).data
     pixels = np.zeros(12 * NSIDE * NSIDE)
     bounds = np.linspace(0, n_halos, n_procs + 1).astype(int)
     jobs = [(df, bounds[i], bounds[i + 1]) for i in range(n_procs)]
@@ -119,7 +131,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     value = pairs / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"first {n} halos of the workload catalog per step ({pairs} halo-pixels), oracle "
@@ -177,11 +189,62 @@ class ClockSampler:
         return out
 
 
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except (OSError, ValueError, KeyError):
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def measure_fp64_peak(dev):
+    """thread-level fp64 instructions per second this GPU sustains (ap_fp64_peak, CUDA events, best of 3)"""
+    import ctypes as C
+    import torch
+    from astropaint_b200 import _capi
+    L = _capi.lib()
+    out = torch.zeros(1, dtype=torch.float64, device=dev)
+    n = C.c_uint64(0)
+    blocks = 148 * 8
+    _capi.check(L.ap_fp64_peak(2000, blocks, _capi.ptr(out), C.byref(n), None))
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _capi.check(L.ap_fp64_peak(40000, blocks, _capi.ptr(out), C.byref(n), _capi.c_ptr(torch.cuda.current_stream().cuda_stream)))
+        e1.record()
+        e1.synchronize()
+        best = max(best, n.value / (e0.elapsed_time(e1) / 1e3))
+    return best
+
+
+def mean_neval(dev, halos, cols, nodes, n_nodes, sample=200_000):
+    """QUADPACK's own evaluation count (scipy's `neval`) averaged over a sample of this rank's (halo, node)
+    quadratures: ap_b16_tau_eval returns it per quadrature."""
+    import torch
+    from astropaint_b200 import _capi
+    live = torch.nonzero(n_nodes > 0).squeeze(1)
+    if live.numel() == 0:
+        return 0.0
+    ns = nodes.shape[1]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    pick = live[torch.randint(0, live.numel(), (sample,), generator=g).to(dev)]
+    node = torch.randint(0, ns, (sample,), generator=g).to(dev)
+    R = nodes[pick, node].contiguous()
+    a = [cols[k][pick].contiguous() for k in ("R_200c", "M_200c", "redshift")]
+    res = torch.empty(sample, dtype=torch.float64, device=dev)
+    nev = torch.empty(sample, dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().ap_b16_tau_eval(sample, _capi.ptr(R), _capi.ptr(a[0]), _capi.ptr(a[1]), _capi.ptr(a[2]),
+                                            _capi.ptr(res), None, _capi.ptr(nev), None))
+    return float(nev.double().mean().item())
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import astropaint_b200 as ap
-    from astropaint_b200 import synthetic, _engine as eng, parallel
+    from astropaint_b200 import synthetic, _engine as eng, _bands
     from astropaint_b200.profiles import Battaglia16
 
     ap.paint_bucket.verbose = False
@@ -191,56 +254,60 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-
-    # ---- inputs: this rank's catalog, built on the host, then resident in HBM ------------------
-    cat = ap.Catalog(synthetic.websky_like(args.halos, seed=1 + rank))
-    halos = eng.DeviceHalos(cat.data, R_TIMES, dev)
-    cols = {k: halos.col(k) for k in ("R_200c", "M_200c", "redshift", "v_r")}
-    T_cmb, c_kms, ns = Battaglia16.T_cmb, Battaglia16.c, 15
-    npix = 12 * NSIDE * NSIDE
-    d_map = torch.zeros(npix, dtype=torch.float64, device=dev)
-    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
-    launches_per_step = 6
-    n_bands = 8 if world > 1 else 1   # ring bands: the all-reduce of band k overlaps band k+1's QUADPACK phase
-    args_t = [cols["R_200c"], cols["M_200c"], cols["redshift"]]
-
-    def step(timers=None):
-        """One spray of this rank's catalog into d_map through the engine's pipeline (the same function
-        Painter.spray drives), then the sum over ranks."""
-        scale = (-cols["v_r"] / c_kms * T_cmb * (1 + cols["redshift"])).contiguous()
-        works = []
-
-        def band_done(k, p_lo, p_hi):
-            if world > 1 and p_hi > p_lo:
-                works.append(dist.all_reduce(d_map[p_lo:p_hi], op=dist.ReduceOp.SUM, async_op=True))
-
-        eng.table_spray(halos, NSIDE, "b16_tau", args_t, scale, ns, "linspace", d_map, d_count, n_bands=n_bands,
-                        band_done=band_done, timers=timers)
-        if timers is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            timers.append(("allreduce_tail", ev))
-        for w in works:
-            w.wait()
-        if timers is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            timers.append(("end", ev))
+    if args.config != "C3":
+        assert world == 1, "the other BASELINE configs are single-GPU lines"
+        emit({"metric": METRIC, "unit": UNIT, "n_gpus": 1, "configs": run_configs(dev, [args.config], args.steps, args.warmup)})
+        return
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def over_ranks(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return [float(x) for x in t]
+
+    MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
+
+    # ---- inputs: ONE catalog (same seed on every rank), staged once; this rank's slice resident in HBM ----
+    t_stage = time.perf_counter()
+    cat = ap.Catalog(synthetic.websky_like(args.halos, seed=1))
+    cat.pin_memory()
+    stage_s = time.perf_counter() - t_stage
+    band = _bands.Band(NSIDE, rank, world)
+    order, theta_sorted, r_ang_max = cat.theta_order()
+    rmax = R_TIMES * float(ap.transform.arcmin2rad(r_ang_max))
+    plan = _bands.Plan(band, theta_sorted, rmax, n_chunks=1)
+    lo, hi = plan.halo_lo, plan.halo_hi
+    halos = eng.DeviceHalos(cat.data, R_TIMES, dev, rows=order[lo:hi], pinned=cat._pinned, pinned_range=(lo, hi))
+    cols = {k: halos.col(k) for k in ("R_200c", "M_200c", "redshift", "v_r")}
+    T_cmb, c_kms, ns = Battaglia16.T_cmb, Battaglia16.c, 15
+    npix = 12 * NSIDE * NSIDE
+    d_band = torch.zeros(band.npix, dtype=torch.float64, device=dev)
+    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    args_t = [cols["R_200c"], cols["M_200c"], cols["redshift"]]
+    launches_per_step = 6     # K1, nodes, QUADPACK, spline, K3, bypass (the zero-fill and the scale are torch kernels)
+
+    def step(timers=None):
+        """One spray of this rank's share into its band of the map through the engine's pipeline (the functions
+        Painter.spray drives): zero the band, then K1 / nodes / QUADPACK / spline / K3 / bypass."""
+        if timers is not None:
+            timers.tick("zero_fill")
+        d_band.zero_()
+        scale = (-cols["v_r"] / c_kms * T_cmb * (1 + cols["redshift"])).contiguous()
+        eng.run_chunks(plan, lambda a, e: eng.table_chunk(halos.view(a, e), NSIDE, "b16_tau", [t[a:e] for t in args_t],
+                                                          scale[a:e], ns, "linspace", d_band, d_count, timers))
+
     for _ in range(args.warmup):
         step()
     barrier()
     d_count.zero_()
-    timers = [[] for _ in range(args.steps)]
+    timers = [eng.Timers() for _ in range(args.steps)]
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
@@ -251,41 +318,28 @@ def run_b200(args):
     t1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
-    ms_total = t0.elapsed_time(t1)
-    pairs_per_step = int(d_count.item()) // args.steps
-    tt = torch.tensor([ms_total, float(pairs_per_step)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = tt.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_total, pairs_all = float(mx[0]), float(sm[1])
-    else:
-        pairs_all = float(pairs_per_step)
+    ms_rank = t0.elapsed_time(t1)
+    pairs_rank = int(d_count.item()) // args.steps
+    ms_total, = over_ranks([ms_rank], MAX)
+    pairs_all, halos_painted = over_ranks([float(pairs_rank), float(halos.n)], SUM)
     ms_step = ms_total / args.steps
     value = pairs_all / (ms_step / 1e3)
     phase_ms = {}
-    for tl in timers:   # consecutive ticks on the launching stream; every chunk adds to its phase
-        for (name, ev), (_, nxt) in zip(tl[:-1], tl[1:]):
-            if name != "end":
-                phase_ms[name] = phase_ms.get(name, 0.0) + ev.elapsed_time(nxt) / args.steps
+    for tm in timers:
+        tm.phase_ms(phase_ms, 1.0 / args.steps)
+    # the map itself: a checksum that must agree between N = 1 and any N (each pixel is painted by one rank)
+    csum = over_ranks([float(d_band.sum()), float(d_band.abs().sum()), float((d_band != 0).sum())], SUM)
+    checksum = {"sum": float(f"{csum[0]:.10e}"), "sum_abs": float(f"{csum[1]:.10e}"), "pixels_painted": int(csum[2])}
 
     # ---- roofline of the HBM-bound scatter kernel and of the dominant (fp64-bound) kernel -------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s"
-    n_pix, _, _, _ = eng.disc_count(halos, NSIDE)
+    hbm_peak, peak_src = load_peaks()
+    n_pix, _, rmin_t, rmax_t = eng.disc_count(halos, NSIDE, want_range=True)   # whole-disc counts of this rank's halos
+    nodes, n_nodes = eng.table_nodes(halos, n_pix, rmin_t, rmax_t, ns, "linspace")
     torch.cuda.synchronize()
-    big = n_pix >= ns
-    hp_table = int(n_pix[big].sum().item())
-    n_big = int(big.sum().item())
+    n_big = int((n_nodes > 0).sum().item())
     # 16 B per halo-pixel (fp64 read-modify-write) + 8*(7+n_params) B per halo (n_params = 4
-    # for kSZ) + 16*n_nodes B of table per halo
-    alg_bytes = 16.0 * hp_table + (8.0 * (7 + 4) + 16.0 * ns) * n_big
+    # for kSZ) + 16*n_nodes B of table per halo; the pixels are the ones THIS rank painted (its band)
+    alg_bytes = 16.0 * pairs_rank + (8.0 * (7 + 4) + 16.0 * ns) * n_big
     paint_gbs = alg_bytes / (phase_ms["paint_table"] / 1e3) / 1e9
     roofline = {"kernel": "paint_kernel<P_TABLE> (fused disc query + geometry + spline + fp64 RED scatter)",
                 "bound": "hbm", "achieved": paint_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -295,67 +349,78 @@ def run_b200(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("paint_table_bytes_per_launch")
+            tr = json.load(open(traffic_file))
+            if world == 1 and tr.get("halos") == args.halos:
+                roofline["traffic"] = tr.get("paint_table_bytes_per_launch")
         except (OSError, ValueError):
             pass
     dominant = max(phase_ms, key=phase_ms.get)
-    # the dominant kernel is the QUADPACK node kernel: fp64-pipe / issue bound (DRAM < 1% of peak), so an
-    # HBM or tensor roofline does not apply; report its rate and the ncu-measured pipe utilisation instead
+    # the dominant kernel is the QUADPACK node kernel: fp64-pipe bound (DRAM < 1% of peak), so its roofline is the
+    # fp64 instruction rate, measured here with a DFMA probe; its algorithmic work = QUADPACK's own number of
+    # integrand evaluations (measured on a sample with ap_b16_tau_eval) x the fp64 instructions of one evaluation
+    fp64_peak = measure_fp64_peak(dev)
+    nev = mean_neval(dev, halos, cols, nodes, n_nodes)
     n_quad = ns * n_big
+    fp64_instr = n_quad * nev * FP64_INSTR_PER_EVAL
+    fp64_rate = fp64_instr / (phase_ms["los_nodes"] / 1e3)
     roofline_dominant = {"kernel": "los_nodes_kernel<b16_tau> (QUADPACK dqagie per (halo, node))", "bound": "fp64-pipe",
-                         "achieved": n_quad / (phase_ms["los_nodes"] / 1e3), "unit": "quadratures/s",
-                         "launch_ms": phase_ms["los_nodes"], "share_of_step": phase_ms["los_nodes"] / ms_step,
-                         "fp64_pipe_active_pct_ncu": 63.0, "peak": None, "frac": None,
-                         "note": "profiles/r1c_ncu_final.csv: fp64 pipe 63.0% active; 165 integrand evaluations per "
-                                 "quadrature (scipy neval), ~142 warp instructions each; hot loop bound by dependent "
-                                 "fp64 chains (46% stall_wait), see DESIGN.md section 7"}
+                         "achieved": fp64_rate, "peak": fp64_peak, "unit": "fp64 thread-instructions/s",
+                         "frac": fp64_rate / fp64_peak, "launch_ms": phase_ms["los_nodes"],
+                         "share_of_step": phase_ms["los_nodes"] / ms_step, "quadratures_per_launch": n_quad,
+                         "mean_neval": nev, "fp64_instr_per_eval": FP64_INSTR_PER_EVAL,
+                         "peak_source": "ap_fp64_peak DFMA probe timed in this run (8 chains x 8 blocks x 256 threads per SM)",
+                         "peak_tflops_fp64": 2 * fp64_peak / 1e12}
+    del nodes, n_nodes, n_pix, rmin_t, rmax_t
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args, world),
-            "halo_pixels_per_step": pairs_all, "halos_per_s": args.halos * world / (ms_step / 1e3),
-            "phase_ms": phase_ms, "dominant_phase": dominant,
-            "gpu_launches": launches_per_step * n_bands * args.steps, "torch_elementwise_launches": 4 * args.steps,
+            "halo_pixels_per_step": pairs_all, "halos_per_s": args.halos / (ms_step / 1e3),
+            "halos_painted_all_ranks": halos_painted, "phase_ms": phase_ms, "dominant_phase": dominant,
+            "gpu_launches": launches_per_step * len(plan.chunks) * args.steps, "torch_elementwise_launches": 5 * args.steps,
+            "map_checksum": checksum, "catalog_stage_s": stage_s,
             "roofline": roofline, "roofline_dominant": roofline_dominant, "clocks": clocks}
 
     # ---- e2e: the public API on a host catalog --------------------------------------------------
     if not args.no_e2e:
-        del halos, cols
-        d_map = None
+        del halos, cols, args_t, d_band
         torch.cuda.empty_cache()
-        cat.pin_memory()
         canvas = ap.Canvas(cat, NSIDE, R_times=R_TIMES)
         painter = ap.Painter(Battaglia16.kSZ_T)
         h2d_cols = ["x", "y", "z", "theta", "phi", "D_a", "R_ang_200c", "R_200c", "M_200c", "redshift", "v_r"]
-        h2d = 8 * args.halos * len(h2d_cols)
-        d2h = 8 * npix if rank == 0 else 0
 
         def e2e_step():
             canvas.clean()
             painter.spray(canvas)
-            if rank == 0:
-                return canvas.pixels  # device -> pinned host
-            return None
+            return canvas.pixels  # every rank: its band device -> the node's shared pinned host map
 
-        for _ in range(3):   # W >= 3 warm-up steps (first one allocates the pinned read-back buffer)
-            e2e_step()
+        for _ in range(3):   # W >= 3 warm-up steps (the first one allocates the page-locked host map)
+            m = e2e_step()
+            del m
         barrier()
         t_start = time.perf_counter()
         for _ in range(args.e2e_steps):
-            e2e_step()
+            m = e2e_step()
+            del m            # nobody keeps the array: the next step may reuse the buffer
         barrier()
         dt = (time.perf_counter() - t_start) / args.e2e_steps
-        pairs = float(int(painter.last_spray["d_count"].item()))
-        tt = torch.tensor([dt, pairs], dtype=torch.float64, device=dev)
-        if world > 1:
-            mx = tt.clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sm = tt.clone()
-            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            dt, pairs = float(mx[0]), float(sm[1])
-        line["e2e"] = {"value": pairs / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-                       "api": "Catalog.pin_memory(); Canvas.clean(); Painter(Battaglia16.kSZ_T).spray(canvas); canvas.pixels"}
+        dt, = over_ranks([dt], MAX)
+        pairs, n_h2d = over_ranks([float(int(painter.last_spray["d_count"].item())), float(painter.last_spray["n_halos"])], SUM)
+        m = canvas.pixels
+        e2e_sum = float(f"{float(m.sum()):.10e}") if rank == 0 else None
+        del m
+        line["e2e"] = {"value": pairs / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_h2d * len(h2d_cols)),
+                       "d2h_bytes_per_step": 8 * npix, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+                       "path": painter.last_spray["path"], "chunks": painter.last_spray["chunks"], "map_sum": e2e_sum,
+                       "api": "Catalog.pin_memory(); Canvas.clean(); Painter(Battaglia16.kSZ_T).spray(canvas); canvas.pixels "
+                              "(all ranks; each copies its band into the node's shared host map)"}
+        del canvas, painter
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, short (N = 1 only) ------------------------------------------
+    if world == 1 and not args.no_configs:
+        del cat
+        line["configs"] = run_configs(dev, ["C1", "C2", "C4", "C5"], 3, 2)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -367,6 +432,77 @@ def run_b200(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs 1, 2, 4, 5 (single GPU, short): device time of Painter.spray / stack_cutouts on a staged catalog
+# ---------------------------------------------------------------------------------------------
+def run_configs(dev, which, steps, warmup):
+    import torch
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    from astropaint_b200.profiles import spherical, NFW, Battaglia16
+    hbm_peak, _ = load_peaks()
+    out = {}
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def spray_config(cat, nside, tmpl, bytes_per_halo, label):
+        cat.pin_memory()
+        canvas = ap.Canvas(cat, nside, R_times=R_TIMES)
+        p = ap.Painter(tmpl)
+
+        def one():
+            canvas.clean()
+            p.spray(canvas)
+        ms = timed(one)
+        pairs = int(p.last_spray["d_count"].item())
+        alg = 16.0 * pairs + bytes_per_halo * cat.size
+        return canvas, {"workload": label, "halo_pixels": pairs, "ms": ms, "value": pairs / (ms / 1e3), "unit": UNIT,
+                        "path": p.last_spray["path"], "algorithmic_bytes": alg,
+                        "roofline_frac": alg / (ms / 1e3) / 1e9 / hbm_peak,
+                        "timed": "CUDA events around Canvas.clean() + Painter.spray (zero-fill of the map, pinned H2D of "
+                                 "the catalog columns and every kernel of the spray)"}
+
+    cat6 = None
+    if "C1" in which:
+        cat = ap.Catalog(synthetic.random_box(1000, seed=0))
+        _, out["C1"] = spray_config(cat, 512, spherical.gaussian_2D, 8.0 * (7 + 4),
+                                    "1e3 random-box halos, README Gaussian, nside 512, R_times 5")
+    if "C2" in which or "C4" in which or "C5" in which:
+        cat6 = ap.Catalog(synthetic.websky_like(1_000_000, seed=1))
+    if "C2" in which:
+        _, out["C2"] = spray_config(cat6, 4096, Battaglia16.tau_2D_interp, 8.0 * (7 + 3) + 16.0 * 15,
+                                    "1e6 Websky-shaped halos, Battaglia16.tau_2D_interp, nside 4096, R_times 5")
+    canvas = None
+    if "C4" in which or "C5" in which:
+        canvas, res = spray_config(cat6, NSIDE, NFW.BG, 8.0 * (7 + 8),
+                                   "1e6 Websky-shaped halos, NFW.BG (R_vec), nside 8192, R_times 5")
+        if "C4" in which:
+            out["C4"] = res
+    if "C5" in which:
+        halo_list = np.arange(100_000)
+
+        def stack():
+            canvas.stack_cutouts(halo_list, lon_range=[-0.2, 0.2], lat_range=[-0.2, 0.2], xpix=200)
+        ms = timed(stack)
+        samples = 100_000 * 200 * 200
+        out["C5"] = {"workload": "stack_cutouts of 1e5 halos, 0.4 x 0.4 deg, 200 x 200, from the C4 map (nside 8192)",
+                     "samples": samples, "ms": ms, "value": 1e5 / (ms / 1e3), "unit": "cutouts/s",
+                     "algorithmic_bytes": 8.0 * samples, "roofline_frac": 8.0 * samples / (ms / 1e3) / 1e9 / hbm_peak,
+                     "timed": "CUDA events around Canvas.stack_cutouts (H2D of lon/lat, fused project + gather + "
+                              "accumulate kernel, D2H of the 200 x 200 stack)"}
+    return out
 
 
 _JSON_OUT = None

@@ -98,6 +98,25 @@ int ap_disc_radius(int64_t n, const double* d_R_ang_200c, double R_times, double
 int ap_disc_count(int64_t nside, const ap_halos* halos, int inclusive, int64_t* d_n_pix,
                   int32_t* d_n_rings, double* d_rmin, double* d_rmax, void* stream);
 
+/* Ring-band ownership of the map (the multi-GPU form of the reference's shared accumulator, paint_bucket.py:
+ * 2414-2433: joblib threads adding into ONE array).  After ap_band_clip(ring_lo, ring_hi) every painting entry
+ * point called by this thread (ap_paint_profile, ap_paint_table, ap_paint_los_items and their _f32 forms) paints
+ * only rings ring_lo <= iz < ring_hi (1-based HEALPix ring numbers) and treats d_map as the address of the first
+ * pixel of ring ring_lo, i.e. of a buffer holding just that band; ap_disc_count keeps whole-disc counts but
+ * reports 0 pixels for a halo whose disc misses the band.  A halo that straddles a boundary is painted by both
+ * owners, each keeping its own rings, so the bands of all ranks tile the map with no reduction.
+ * ap_band_clip(0, 0) restores the whole map.                                                     */
+int ap_band_clip(int64_t ring_lo, int64_t ring_hi);
+
+/* ap_disc_count that also builds the work list of the `len(R) < n_samples` bypass of utils.interpolate
+ * (lib/utils.py:510-511) on the device: every halo with 0 < n_pix < n_samples appends one item
+ * (halo * 32 + pixel ordinal, 0 <= ordinal < n_pix, ring by ring) per pixel at
+ * d_items[atomicAdd(d_item_count, n_pix) ...]; items beyond item_cap are dropped (size the list
+ * n * (n_samples - 1) to make that impossible).  *d_item_count must be zeroed by the caller.   */
+int ap_disc_count_items(int64_t nside, const ap_halos* halos, int64_t* d_n_pix, double* d_rmin, double* d_rmax,
+                        int32_t n_samples, int64_t* d_items, int64_t item_cap, unsigned long long* d_item_count,
+                        void* stream);
+
 /* Flat (halo, pixel) work list: pixel ids of halo h in ascending order at
  * d_pix[d_pix_off[h] .. d_pix_off[h+1]) — identical to np.concatenate of gen_pixel_index().
  * Optional outputs (NULL to skip): d_R[total] = gen_cent2pix_mpc (:1266-1273),
@@ -125,15 +144,11 @@ int ap_paint_profile(int profile, int64_t nside, const ap_halos* halos, const do
 int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d_rmin, const double* d_rmax,
                    int32_t n_samples, int32_t method, double* d_nodes, int32_t* d_n_nodes, void* stream);
 
-/* Battaglia16.tau_2D at the nodes: one QUADPACK qagie(epsabs=0, epsrel=1e-2) per (halo, node)
- * (lib/utils.py:445-448 through Battaglia16.py:132-155, :221-239).                           */
-int ap_b16_tau_nodes(int64_t n, const double* d_R_200c, const double* d_M_200c, const double* d_redshift,
-                     int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes,
-                     double* d_values, void* stream);
-
-/* The same for any ap_los_kind: d_p0, d_p1, d_p2 are the 3-D profile's per-halo arguments in reference
- * order (R_200c, M_200c, redshift | rho_s, r_s, NULL).  Serves Battaglia16.ne_2D (interpolate(n=20) of
- * LOS_integrate(ne_3D), :201-218) and NFW.rho_2D_interp (n=20, logspace; NFW.py:96-108).            */
+/* @LOS_integrate at the nodes: one QUADPACK qagie(epsabs=0, epsrel=1e-2) per (halo, node)
+ * (lib/utils.py:445-448).  d_p0, d_p1, d_p2 are the 3-D profile's per-halo arguments in reference
+ * order (R_200c, M_200c, redshift | rho_s, r_s, NULL).  Serves Battaglia16.tau_2D_interp / kSZ_T (n=15,
+ * :242-271), Battaglia16.ne_2D (interpolate(n=20) of LOS_integrate(ne_3D), :201-218) and
+ * NFW.rho_2D_interp (n=20, logspace; NFW.py:96-108).                                           */
 int ap_los_nodes(int kind, int64_t n, const double* d_p0, const double* d_p1, const double* d_p2, int32_t n_samples,
                  const double* d_nodes, const int32_t* d_n_nodes, double* d_values, void* stream);
 
@@ -155,31 +170,24 @@ int ap_spline_build_uniform(int64_t n, int32_t n_samples, const double* d_nodes,
 
 /* Painter.spray for a tabulated template: value = spline_h(R) * d_scale[h] (d_scale optional).
  * uniform_nodes = 1 when the nodes are linspace (method 0 of ap_table_nodes).
- * Halos with d_n_nodes[h] == 0 are skipped (bypass halos are painted by ap_paint_b16_small or
+* Halos with d_n_nodes[h] == 0 are skipped (bypass halos are painted by ap_paint_los_items or
  * through the flat work list).                                                               */
 int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
                    const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes, const double* d_scale,
                    double* d_map, unsigned long long* d_n_painted, void* stream);
 
-/* The `len(R) < n_samples` branch of Battaglia16.tau_2D_interp / kSZ_T: halos with
- * 0 < n_pix < n_samples get tau_2D (QUADPACK) evaluated at every pixel (lib/utils.py:510-511). */
-int ap_paint_b16_small(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
-                       const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
-                       int32_t n_samples, double* d_map, unsigned long long* d_n_painted, void* stream);
-
-int ap_paint_los_small(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
-                       const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
-                       double* d_map, unsigned long long* d_n_painted, void* stream);
-
-/* The same bypass from a compacted work list: item t paints the d_item_ord[t]-th pixel (ring by ring, 0 <= ord <
- * n_pix) of halo d_item_halo[t].  Every lane of a warp runs its own quadrature; the
- * caller builds the list from ap_disc_count's d_n_pix (astropaint_b200/_engine.py::paint_los_small). */
+/* The `len(R) < n_samples` branch of utils.interpolate (lib/utils.py:510-511) for the @LOS_integrate kinds:
+ * item t of the list ap_disc_count_items built paints the (d_items[t] & 31)-th pixel (ring by ring) of halo
+ * d_items[t] >> 5 with the projected profile (one QUADPACK quadrature) times d_scale[halo].  The number of items
+ * is read on the device (*d_n_items, clamped to item_cap): no host synchronisation.            */
 int ap_paint_los_items(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
-                       const double* d_p2, const double* d_scale, int64_t n_items, const int64_t* d_item_halo,
-                       const int32_t* d_item_ord, double* d_map, void* stream);
+                       const double* d_p2, const double* d_scale, const unsigned long long* d_n_items,
+                       int64_t item_cap, const int64_t* d_items, double* d_map, unsigned long long* d_n_painted,
+                       void* stream);
 
 /* Canvas.cutouts / stack_cutouts (paint_bucket.py:1601-1743, 1745-1941): healpy
- * CartesianProj(lonra, latra, xsize, ysize).projmap(map, rot=(lon, lat), vec2pix) per halo.
+ * CartesianProj(lonra, latra, xsize, ysize).projmap(map, rot=(lon, lat), vec2pix) per halo; the image
+ * grid is healpy's endpoint-inclusive one (ij2xy: x_j = -lon1 + j (lon1 - lon0) / (xsize - 1), astro flip).
  * d_lon_deg/d_lat_deg[n_sel] are the catalog lon/lat (degrees) of the selected halos.
  * ap_cutouts writes d_out[n_sel*ysize*xsize]; ap_stack_cutouts accumulates
  * d_stack[ysize*xsize] += sum_h weight_h * cutout_h (d_weight optional).                    */
@@ -199,15 +207,10 @@ int ap_paint_profile_f32(int profile, int64_t nside, const ap_halos* halos, cons
 int ap_paint_table_f32(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,
                        const double* d_nodes, const double* d_coef, const int32_t* d_n_nodes, const double* d_scale,
                        float* d_map, unsigned long long* d_n_painted, void* stream);
-int ap_paint_los_small_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
-                           const double* d_p2, const double* d_scale, const int64_t* d_n_pix, int32_t n_samples,
-                           float* d_map, unsigned long long* d_n_painted, void* stream);
 int ap_paint_los_items_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
-                           const double* d_p2, const double* d_scale, int64_t n_items, const int64_t* d_item_halo,
-                           const int32_t* d_item_ord, float* d_map, void* stream);
-int ap_paint_b16_small_f32(int64_t nside, const ap_halos* halos, const double* d_R_200c, const double* d_M_200c,
-                           const double* d_redshift, const double* d_scale, const int64_t* d_n_pix,
-                           int32_t n_samples, float* d_map, unsigned long long* d_n_painted, void* stream);
+                           const double* d_p2, const double* d_scale, const unsigned long long* d_n_items,
+                           int64_t item_cap, const int64_t* d_items, float* d_map, unsigned long long* d_n_painted,
+                           void* stream);
 
 /* Host-buffer convenience entry (what bench.py's e2e leg and INTEGRATION.md's stub call):
  * copies the halo columns and parameters host->device, paints into a device map initialised
@@ -216,6 +219,20 @@ int ap_spray_host(int profile, int64_t nside, int64_t n, const double* h_x, cons
                   const double* h_z, const double* h_radius, const double* h_theta, const double* h_phi,
                   const double* h_D_a, const double* const* h_params, const int32_t* h_strides,
                   int32_t n_params, double* h_map, uint64_t* h_n_painted);
+
+/* Host side of the map (Canvas.pixels is a host ndarray in the reference, paint_bucket.py:798, 858-869): the
+ * ranks of one node write their bands into ONE host array.  ap_host_register page-locks a caller-owned host
+ * range (e.g. the rank's band of a shared mapping) so that ap_copy_d2h_async / ap_copy_h2d_async on it are
+ * asynchronous DMA on `stream`; ap_host_unregister undoes it.                                              */
+int ap_host_register(void* h_ptr, uint64_t bytes);
+int ap_host_unregister(void* h_ptr);
+int ap_copy_d2h_async(void* h_dst, const void* d_src, uint64_t bytes, void* stream);
+int ap_copy_h2d_async(void* d_dst, const void* h_src, uint64_t bytes, void* stream);
+
+/* Measurement aid (bench.py): launches `blocks` x 256 threads each issuing 8 x iters dependent-chain DFMAs from
+ * registers; *h_n_dfma receives the number of thread-level DFMAs.  Timed with CUDA events it gives the fp64
+ * instruction rate this GPU sustains -- the roofline of the QUADPACK node kernel.                           */
+int ap_fp64_peak(int32_t iters, int32_t blocks, double* d_out, uint64_t* h_n_dfma, void* stream);
 
 /* ---- per-cutout operators: Canvas.cutouts / stack_cutouts `apply_func` (paint_bucket.py:1729-1742) on a batch
  * of device-resident cutouts d_patches[n][ysize][xsize] (what ap_cutouts writes).                          */

@@ -571,11 +571,17 @@ def cartesian_projmap(hpx, healpix_map, lon_deg, lat_deg, lonra, latra, xsize, y
     if ysize is None:
         ratio = (lat1 - lat0) / (lon1 - lon0)
         ysize = int(round(xsize * ratio))
-    # ij2xy: pixel centres
+    # CartesianProj.ij2xy (healpy/projector.py), as recalled by two independent restatements (round-1 advisor and
+    # round-2 builder; SURVEY A.6's half-pixel-centre form was a third recollection and is NOT what healpy does):
+    #     lonra = flip * np.float64(lonra)[::flip]            # 'astro' flip = -1  ->  [-lonra[1], -lonra[0]]
+    #     y = (latra[1] - latra[0]) / (ysize - 1.) * idx_i + latra[0]
+    #     x = (lonra[1] - lonra[0]) / (xsize - 1.) * idx_j + lonra[0]
+    # i.e. an ENDPOINT-INCLUSIVE grid; healpy is not installed here, so this stays "unpinned" (DESIGN.md section 5).
     j = np.arange(xsize, dtype=np.float64)
     i = np.arange(ysize, dtype=np.float64)
-    x = lon0 + (j + 0.5) * ((lon1 - lon0) / xsize)
-    y = lat0 + (i + 0.5) * ((lat1 - lat0) / ysize)
+    fl0, fl1 = -lon1, -lon0
+    x = ((fl1 - fl0) / (xsize - 1.0)) * j + fl0 if xsize > 1 else np.full(1, fl0)
+    y = ((lat1 - lat0) / (ysize - 1.0)) * i + lat0 if ysize > 1 else np.full(1, lat0)
     X, Y = np.meshgrid(x, y)  # shape (ysize, xsize)
     # xy2vec: flip = -1 ('astro'); theta = pi/2 - y, phi = flip * x
     theta = HALFPI - np.radians(Y)

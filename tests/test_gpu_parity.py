@@ -623,9 +623,9 @@ def test_los_projected_templates_on_device(kind, nside, n, m_min):
 
 
 def test_prefetch_pipeline_matches_plain_spray(monkeypatch):
-    """ring-band ordered chunks with device->host streaming of finished bands == the plain path"""
+    """colatitude-ordered chunks with device->host streaming of the finished rings == the plain path"""
     import astropaint_b200 as ap
-    from astropaint_b200 import synthetic
+    from astropaint_b200 import synthetic, _bands
     from astropaint_b200.profiles import Battaglia16
     cat = ap.Catalog(synthetic.websky_like(4000, seed=17, m_min=5e13))
     canvas = ap.Canvas(cat, 2048, R_times=5)
@@ -635,9 +635,10 @@ def test_prefetch_pipeline_matches_plain_spray(monkeypatch):
     plain = canvas.pixels.copy()              # first read allocates the pinned host buffer
     n_plain = int(p.last_spray["d_count"].item())
     monkeypatch.setattr(ap.Painter, "PREFETCH_MIN_HALOS", 0)
+    monkeypatch.setattr(_bands, "MIN_CHUNK_HALOS", 500)
     canvas.clean()
     p.spray(canvas)
-    assert p.last_spray["path"] == "device_table+prefetch"
+    assert p.last_spray["path"] == "device_table+stream" and p.last_spray["chunks"] == 8
     assert int(p.last_spray["d_count"].item()) == n_plain
     got = canvas.pixels
     map_close(got, plain, 1e-12)

@@ -172,35 +172,49 @@ def test_shard_rows_is_array_split():
         assert all(np.array_equal(a, b) for a, b in zip(parts, want))
 
 
-def test_ring_band_layout_is_safe_for_streaming():
-    """The banded pipeline ships band k once the halos of bands <= k are painted.  That is only correct
-    if no halo assigned to band b touches a pixel below pix_bounds[b]: check it against the oracle's
-    pixel sets (CPU tensors stand in for the device columns)."""
-    import torch
-    from astropaint_b200 import _engine as eng
+def test_band_plan_ownership_and_streaming_are_safe():
+    """Ring-band ownership (_bands.Plan): (a) the bands of all ranks tile the map; (b) every halo whose disc
+    touches a rank's band lies inside the contiguous slice of the colatitude order that rank paints; (c) after
+    chunk c of a rank's schedule no LATER halo touches a ring the chunk declared final.  Checked against the
+    oracle's pixel sets, including polar, sky-sized and inclusive-sized discs."""
+    from astropaint_b200 import _bands
     from oracle import healpix_np as H
 
-    class FakeHalos:
-        def __init__(self, theta, radius):
-            self.cols = {"theta": torch.from_numpy(theta), "__radius__": torch.from_numpy(radius)}
-
-        def col(self, k):
-            return self.cols[k]
-
     rng = np.random.default_rng(0)
-    for nside, K in [(16, 8), (64, 8), (256, 5), (64, 1)]:
+    for nside, ws, n_chunks in [(16, 1, 5), (16, 3, 2), (64, 8, 3), (64, 2, 6), (128, 5, 4)]:
         hp = H.HealpixRing(nside)
-        rings, pix = eng.band_layout(nside, K)
-        assert rings[0] == 1 and pix[0] == 0 and pix[-1] == hp.npix and all(np.diff(pix) >= 0)
-        n = 400
+        bands = [_bands.Band(nside, r, ws) for r in range(ws)]
+        assert bands[0].pix_lo == 0 and bands[-1].pix_hi == hp.npix
+        assert all(bands[r].pix_hi == bands[r + 1].pix_lo for r in range(ws - 1))
+        assert all(b.pix_lo == _bands.ring_start(nside, b.ring_lo) for b in bands)
+        n = 300
         theta = np.arccos(rng.uniform(-1, 1, n))
-        theta[:20] = [0.0, np.pi, 1e-9, np.pi - 1e-9] * 5
+        theta[:12] = [0.0, np.pi, 1e-9, np.pi - 1e-9] * 3
         phi = rng.uniform(0, 2 * np.pi, n)
-        radius = rng.choice([1.0, 0.1, 3.0], n) * rng.uniform(0, 4.0 / nside, n) + (rng.uniform(0, 1, n) < 0.02) * 1.0
-        tr = eng.top_ring(FakeHalos(theta, radius), nside).numpy()
-        band = np.searchsorted(np.asarray(rings[1:-1]), tr, side="right")
+        radius = rng.choice([1.0, 0.1, 3.0], n) * rng.uniform(0, 4.0 / nside, n) + (rng.uniform(0, 1, n) < 0.02) * 0.7
+        order = np.argsort(theta, kind="stable")
+        ts, rs = theta[order], radius[order]
+        pix_sets = []
         for i in range(n):
-            v = (np.sin(theta[i]) * np.cos(phi[i]), np.sin(theta[i]) * np.sin(phi[i]), np.cos(theta[i]))
-            q = hp.query_disc(v, radius[i])
-            if len(q):
-                assert q.min() >= pix[band[i]], (nside, K, i, q.min(), pix[band[i]], band[i])
+            v = (np.sin(ts[i]) * np.cos(phi[order[i]]), np.sin(ts[i]) * np.sin(phi[order[i]]), np.cos(ts[i]))
+            pix_sets.append(hp.query_disc(v, rs[i]))
+        ring_starts = np.array([_bands.ring_start(nside, r) for r in range(1, 4 * nside + 1)])
+        for b in bands:
+            plan = _bands.Plan(b, ts, float(rs.max()), n_chunks=n_chunks)
+            assert plan.chunks[0][0] == plan.halo_lo and plan.chunks[-1][1] == plan.halo_hi
+            assert plan.chunks[-1][2] == b.ring_hi
+            for i, q in enumerate(pix_sets):
+                touches = len(q) and q.max() >= b.pix_lo and q.min() < b.pix_hi
+                if touches:
+                    assert plan.halo_lo <= i < plan.halo_hi, (nside, ws, b.rank, i)
+            for (a, e, done) in plan.chunks:
+                done_pix = _bands.ring_start(nside, done)
+                for i in range(e, plan.halo_hi):
+                    q = pix_sets[i]
+                    q = q[(q >= b.pix_lo) & (q < b.pix_hi)]
+                    if len(q):
+                        assert q.min() >= done_pix, (nside, ws, b.rank, e, i, q.min(), done_pix)
+        # ring helpers agree with the oracle's ring scheme
+        for r in (1, nside - 1, nside, 2 * nside, 3 * nside, 3 * nside + 1, 4 * nside - 1):
+            assert _bands.ring_start(nside, r) == hp.ring_info(r)[0]
+            assert abs(_bands.ring_z(nside, r) - hp.ring2z(r)) < 1e-15
