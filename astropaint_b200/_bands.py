@@ -97,24 +97,33 @@ class Band:
 CHUNK_RATIO = 0.75
 MAX_CHUNKS = 10
 MIN_CHUNK_HALOS = 50_000
+#: share of the first chunk when there are three or more: the halo columns go host->device chunk by chunk on
+#: their own stream, so painting starts as soon as this small lead chunk has arrived and every later upload hides
+#: behind the previous chunk's kernels
+LEAD_FRACTION = 0.04
 
 
 class Plan:
-    """Host-side schedule of one rank's share of a spray (no device work, no synchronisation)."""
+    """Host-side schedule of one rank's share of a spray (no device work, no synchronisation).
 
-    def __init__(self, band, theta_sorted, rmax, n_chunks=None, ratio=None):
+    reach = (north, south) from Catalog.disc_reach: for the halos in colatitude order, north[i] is the smallest
+    colatitude reached by any disc of halos i.. and south[i] the largest reached by any disc of halos ..i."""
+
+    def __init__(self, band, reach, n_chunks=None, ratio=None):
         nside = band.nside
         self.band = band
-        margin = rmax + 4.0 / nside        # largest disc radius + more than two ring spacings
-        n = len(theta_sorted)
+        north, south = reach
+        margin = 4.0 / nside               # more than two ring spacings: rounding of ring boundaries, centre from (x, y, z)
+        n = len(north)
         if band.whole:
             lo, hi = 0, n
         else:
-            # colatitudes of the band's first and last ring; halos farther away than `margin` cannot touch it
+            # colatitudes of the band's first and last ring; a halo whose disc stays `margin` clear of them cannot touch it
             t_top = math.acos(max(-1.0, min(1.0, ring_z(nside, band.ring_lo))))
             t_bot = math.acos(max(-1.0, min(1.0, ring_z(nside, max(band.ring_hi - 1, band.ring_lo)))))
-            lo = int(np.searchsorted(theta_sorted, t_top - margin, side="left")) if band.rank > 0 else 0
-            hi = int(np.searchsorted(theta_sorted, t_bot + margin, side="right")) if band.rank < band.world_size - 1 else n
+            lo = int(np.searchsorted(south, t_top - margin, side="left")) if band.rank > 0 else 0
+            hi = int(np.searchsorted(north, t_bot + margin, side="right")) if band.rank < band.world_size - 1 else n
+            hi = max(hi, lo)
             if band.npix == 0:
                 hi = lo
         self.halo_lo, self.halo_hi = lo, hi
@@ -122,7 +131,11 @@ class Plan:
         if n_chunks is None:
             n_chunks = max(1, min(MAX_CHUNKS, m // MIN_CHUNK_HALOS))
         ratio = CHUNK_RATIO if ratio is None else ratio
-        f = np.power(float(ratio), np.arange(n_chunks))
+        if n_chunks >= 3:
+            f = np.power(float(ratio), np.arange(n_chunks - 1))
+            f = np.concatenate([[LEAD_FRACTION], (1.0 - LEAD_FRACTION) * f / f.sum()])
+        else:
+            f = np.power(float(ratio), np.arange(n_chunks))
         cuts = lo + np.round(np.cumsum(f / f.sum()) * m).astype(np.int64)
         cuts[-1] = hi
         #: (halo_lo, halo_hi, done_ring): after the chunk's kernels, rings [ring_lo, done_ring) are final
@@ -133,8 +146,8 @@ class Plan:
             if e >= hi:
                 done = band.ring_hi
             else:
-                z = math.cos(min(math.pi, max(0.0, float(theta_sorted[e]) - margin)))
-                done = ring_above(nside, z) if theta_sorted[e] - margin > 0.0 else band.ring_lo
+                top = float(north[e]) - margin        # no halo from e on reaches farther north than this
+                done = ring_above(nside, math.cos(min(math.pi, top))) if top > 0.0 else band.ring_lo
                 done = min(max(done, band.ring_lo), band.ring_hi)
             if self.chunks and done < self.chunks[-1][2]:
                 done = self.chunks[-1][2]

@@ -53,19 +53,23 @@ class DeviceHalos:
     radius rounds identically.
     """
 
-    def __init__(self, data, R_times, device, rows=None, pinned=None, pinned_range=None):
+    def __init__(self, data, R_times, device, rows=None, pinned=None, pinned_range=None, lazy=False):
         """rows: catalog row labels of the halos held, in this object's order (None = every row, catalog order).
         pinned: {column: page-locked host tensor}.  With pinned_range = (lo, hi) the tensors are in the
         catalog's colatitude order (Catalog.pin_memory) and [lo:hi] of them ARE the rows (one contiguous DMA
-        per column); otherwise they are in catalog order and `rows` is gathered from them."""
+        per column); otherwise they are in catalog order and `rows` is gathered from them.
+        lazy: upload nothing yet -- the caller stages the columns piecewise with upload_pieces()."""
         self.device = device
         self._data = data
         self._rows = rows
         self._pinned = pinned or {}
         self._pinned_range = pinned_range
+        self._R_times = float(R_times)
         self.cols = {}
         self._n_all = len(data)
         self.n = self._n_all if rows is None else len(rows)
+        if lazy:
+            return
         # disc radius = R_times * arcmin2rad(R_ang_200c) = R_times * ((R_ang / 60) * (pi / 180))
         # (paint_bucket.py:1226-1227, lib/transform.py:148-150).  Formed on the device from the uploaded
         # column with the same three IEEE operations numpy performs (ap_disc_radius; torch's own
@@ -77,6 +81,44 @@ class DeviceHalos:
         self.cols["__radius__"] = radius
         for k in GEOMETRY_COLUMNS:
             self.col(k)
+
+    def upload_pieces(self, names, pieces, stream):
+        """Stage the geometry columns and `names` piece by piece: piece k = halos [a_k, e_k) of this object goes
+        host -> device on `stream` (one DMA per column and piece, straight out of the page-locked colatitude-ordered
+        staging of Catalog.pin_memory); returns one event per piece.  The painting stream waits for piece k's event,
+        calls radius_piece(a_k, e_k) and paints it while the later pieces are still in flight."""
+        assert self._pinned_range is not None
+        lo = self._pinned_range[0]
+        names = list(dict.fromkeys(list(GEOMETRY_COLUMNS) + ["R_ang_200c"] + list(names)))
+        L = _capi.lib()
+        piecewise = []
+        for name in names:
+            if name in self.cols:
+                continue
+            if name in self._pinned:
+                self.cols[name] = torch.empty(self.n, dtype=torch.float64, device=self.device)
+                piecewise.append(name)
+            else:
+                self.col(name)                # not staged: whole column now, on the painting stream
+        self.cols["__radius__"] = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        stream.wait_stream(torch.cuda.current_stream())   # the fresh buffers may be recycled blocks still in use
+        sp = c_ptr(stream.cuda_stream)
+        events = []
+        for (a, e) in pieces:
+            for name in piecewise:
+                src = self._pinned[name]
+                check(L.ap_copy_h2d_async(c_ptr(self.cols[name].data_ptr() + 8 * a), c_ptr(src.data_ptr() + 8 * (lo + a)),
+                                          8 * (e - a), sp))
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            events.append(ev)
+        return events
+
+    def radius_piece(self, a, e):
+        """disc radius of halos [a, e) on the painting stream (their R_ang_200c has arrived)"""
+        if e > a:
+            check(_capi.lib().ap_disc_radius(e - a, c_ptr(self.cols["R_ang_200c"].data_ptr() + 8 * a), self._R_times,
+                                             c_ptr(self.cols["__radius__"].data_ptr() + 8 * a), stream_ptr()))
 
     @property
     def index(self):
@@ -219,9 +261,9 @@ def run_chunks(plan, paint_chunk, chunk_done=None):
     band = plan.band
     prev = band.ring_lo
     with band_clip(band):
-        for (a, e, done) in plan.chunks:
+        for k, (a, e, done) in enumerate(plan.chunks):
             if e > a:
-                paint_chunk(a - plan.halo_lo, e - plan.halo_lo)
+                paint_chunk(a - plan.halo_lo, e - plan.halo_lo, k)
             if chunk_done is not None and done > prev:
                 chunk_done(ring_start(band.nside, prev) - band.pix_lo, ring_start(band.nside, done) - band.pix_lo)
                 prev = done

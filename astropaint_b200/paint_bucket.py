@@ -84,7 +84,22 @@ class Catalog:
             order = np.argsort(key, kind="stable")
             r_ang_max = float(np.nanmax(d["R_ang_200c"].values)) if len(d) else 0.0
             self._order = (order, key[order], r_ang_max)
+            self._reach = {}
         return self._order
+
+    def disc_reach(self, R_times, extra=0.0):
+        """(north, south) for the discs of radius R_times * R_ang_200c (+ extra [rad]) in colatitude order:
+        north[i] = the smallest colatitude any disc of halos i, i+1, ... reaches, south[i] = the largest colatitude
+        any disc of halos 0 .. i reaches.  Both are non-decreasing, so the halos that can touch a ring band, and the
+        rings no later halo can touch, come out of binary searches (astropaint_b200/_bands.py).  Cached."""
+        order, theta_sorted, _ = self.theta_order()
+        key = (float(R_times), float(extra))
+        if key not in self._reach:
+            r = float(R_times) * transform.arcmin2rad(np.nan_to_num(self._data["R_ang_200c"].values[order])) + float(extra)
+            north = np.minimum.accumulate((theta_sorted - r)[::-1])[::-1]
+            south = np.maximum.accumulate(theta_sorted + r)
+            self._reach = {key: (np.ascontiguousarray(north), south)}      # one entry: a catalog is sprayed with one R_times
+        return self._reach[key]
 
     def pin_memory(self):
         """Stage every numeric column in page-locked host memory (torch pinned tensors), rows in colatitude
@@ -834,6 +849,9 @@ class Canvas:
 class Painter:
     """Sprays a template (radial profile) over a Canvas."""
 
+    #: True: every device spray records CUDA events (chunk ends, uploads, read-back copies) in last_spray["trace"]
+    trace = False
+
     def __init__(self, template):
         self.template = template
 
@@ -967,23 +985,42 @@ class Painter:
         band = canvas._band()
         cat = canvas.catalog
         nside = canvas.nside
-        order, theta_sorted, r_ang_max = cat.theta_order()
-        rmax = float(canvas.R_times) * float(transform.arcmin2rad(r_ang_max))
-        if canvas.inclusive:
-            rmax += 4.0 / nside          # the inclusive query widens every disc by about one pixel radius
+        order = cat.theta_order()[0]
+        # the inclusive query widens every disc by about one pixel radius
+        reach = cat.disc_reach(canvas.R_times, 4.0 / nside if canvas.inclusive else 0.0)
         d_band = canvas._device_band()
         dev = d_band.device
         # the decision to stream must be the same on every rank: it depends on the catalog size only
         host = None
         if cat.size // band.world_size >= self.PREFETCH_MIN_HALOS:
             host = canvas._reusable_host()
-        plan = _bands.Plan(band, theta_sorted, rmax, n_chunks=None if host is not None else 1)
+        plan = _bands.Plan(band, reach, n_chunks=None if host is not None else 1)
         lo, hi = plan.halo_lo, plan.halo_hi
         rows = order[lo:hi]
         pinned = getattr(cat, "_pinned", None)
+        # a page-locked catalog painted in several chunks is uploaded chunk by chunk on its own stream
+        piecewise = bool(pinned) and len(plan.chunks) > 1
         halos = eng.DeviceHalos(cat.data, canvas.R_times, dev, rows=rows, pinned=pinned,
-                                pinned_range=(lo, hi) if pinned else None)
+                                pinned_range=(lo, hi) if pinned else None, lazy=piecewise)
         d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        trace = {"main": [], "upload": [], "copy": []} if self.trace else None
+
+        def mark(lane, name, stream=None):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream) if stream is not None else ev.record()
+                trace[lane].append((name, ev))
+
+        mark("main", "start")
+        arrived = None
+        if piecewise:
+            wanted = list(info["args"]) + list(info.get("kwonly", {}))
+            if info.get("scale"):
+                wanted += list(info["scale"]["args"]) + list(info["scale"]["kwonly"])
+            wanted = [a for a in wanted if a in host_cols and a in self._catalog_cols]
+            up_stream = torch.cuda.Stream(device=dev)
+            arrived = halos.upload_pieces(wanted, [(a - lo, e - lo) for (a, e, _) in plan.chunks], up_stream)
+            mark("upload", "all uploads", up_stream)
 
         def col(name, defaults=None):
             """device tensor of a template argument: spray kwarg > catalog column > kw-only default"""
@@ -998,28 +1035,37 @@ class Painter:
         def cut(t, a, e):
             return t if t.numel() == 1 else t[a:e]
 
+        def ready(a, e, k):
+            if arrived is not None:       # this chunk's columns: wait for their DMA, then form the disc radii
+                torch.cuda.current_stream().wait_event(arrived[k])
+                halos.radius_piece(a, e)
+
         if kind == "profile":
             params = [col(a) for a in info["args"]] + [col(k, info["kwonly"]) for k in info["kwonly"]]
 
-            def paint_chunk(a, e):
+            def paint_chunk(a, e, k):
+                ready(a, e, k)
                 eng.paint_profile(halos.view(a, e), nside, info["id"], [cut(t, a, e) for t in params], d_band, d_count)
+                mark("main", f"chunk {k}")
             path = "device_profile"
         else:
             assert info["kind"] in eng.LOS_KINDS
             args = [col(a) for a in info["args"]]
             args = [t if t.numel() == halos.n else t.expand(halos.n).contiguous() for t in args]
-            scale = None
-            if info["scale"] is not None:
-                sc = info["scale"]
-                cols = {a: col(a) for a in sc["args"]}
-                kw = {k: col(k, sc["kwonly"]) for k in sc["kwonly"]}
-                scale = sc["fn"](cols, kw)
-                scale = (scale if scale.numel() == halos.n else scale.expand(halos.n)).contiguous()
+            sc = info["scale"]
+            if sc is not None:
+                sc_cols = {a: col(a) for a in sc["args"]}
+                sc_kw = {k: col(k, sc["kwonly"]) for k in sc["kwonly"]}
 
-            def paint_chunk(a, e):
-                eng.table_chunk(halos.view(a, e), nside, info["kind"], [t[a:e] for t in args],
-                                scale[a:e] if scale is not None else None, info["n_samples"],
+            def paint_chunk(a, e, k):
+                ready(a, e, k)
+                scale = None
+                if sc is not None:     # per-halo multiplier (kSZ: -v_r / c T_cmb (1 + z)), formed chunk by chunk
+                    scale = sc["fn"]({n_: cut(t, a, e) for n_, t in sc_cols.items()}, sc_kw)
+                    scale = (scale if scale.numel() == e - a else scale.expand(e - a)).contiguous()
+                eng.table_chunk(halos.view(a, e), nside, info["kind"], [t[a:e] for t in args], scale, info["n_samples"],
                                 info["sampling_method"], d_band, d_count, timers)
+                mark("main", f"chunk {k}")
             path = "device_table"
 
         chunk_done = None
@@ -1031,13 +1077,14 @@ class Painter:
                 ev.record()
                 copy_stream.wait_event(ev)
                 eng.copy_d2h(host.band_view(rel_lo, rel_hi), d_band[rel_lo:rel_hi], stream=copy_stream)
+                mark("copy", f"pixels {rel_lo}:{rel_hi}", copy_stream)
             path += "+stream"
         eng.run_chunks(plan, paint_chunk, chunk_done)
         if host is not None:
             canvas._prefetch = (copy_stream, band.npix)
         canvas._dfull = None
         return {"path": path, "n_halos": halos.n, "d_count": d_count, "world_size": band.world_size,
-                "chunks": len(plan.chunks), "band": (band.ring_lo, band.ring_hi)}
+                "chunks": len(plan.chunks), "band": (band.ring_lo, band.ring_hi), "trace": trace}
 
     # ------------------------ host templates: the reference's halo batches ------------------------
     def _spray_host_template(self, canvas, R_mode, host_cols, template_kwargs):

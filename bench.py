@@ -280,9 +280,8 @@ def run_b200(args):
     cat.pin_memory()
     stage_s = time.perf_counter() - t_stage
     band = _bands.Band(NSIDE, rank, world)
-    order, theta_sorted, r_ang_max = cat.theta_order()
-    rmax = R_TIMES * float(ap.transform.arcmin2rad(r_ang_max))
-    plan = _bands.Plan(band, theta_sorted, rmax, n_chunks=1)
+    order = cat.theta_order()[0]
+    plan = _bands.Plan(band, cat.disc_reach(R_TIMES), n_chunks=1)
     lo, hi = plan.halo_lo, plan.halo_hi
     halos = eng.DeviceHalos(cat.data, R_TIMES, dev, rows=order[lo:hi], pinned=cat._pinned, pinned_range=(lo, hi))
     cols = {k: halos.col(k) for k in ("R_200c", "M_200c", "redshift", "v_r")}
@@ -300,7 +299,7 @@ def run_b200(args):
             timers.tick("zero_fill")
         d_band.zero_()
         scale = (-cols["v_r"] / c_kms * T_cmb * (1 + cols["redshift"])).contiguous()
-        eng.run_chunks(plan, lambda a, e: eng.table_chunk(halos.view(a, e), NSIDE, "b16_tau", [t[a:e] for t in args_t],
+        eng.run_chunks(plan, lambda a, e, k: eng.table_chunk(halos.view(a, e), NSIDE, "b16_tau", [t[a:e] for t in args_t],
                                                           scale[a:e], ns, "linspace", d_band, d_count, timers))
 
     for _ in range(args.warmup):

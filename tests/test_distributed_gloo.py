@@ -59,7 +59,6 @@ def _band_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     import astropaint_b200 as ap
     from astropaint_b200 import parallel, synthetic, _bands
-    from astropaint_b200.lib import transform
     from oracle import reference_loop as ref, profiles_np as oprof
     ap.paint_bucket.verbose = False
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -68,8 +67,8 @@ def _band_worker(rank, world, port, out_dir):
     nside, R_times = 32, 3
     cat = ap.Catalog(synthetic.random_box(41, seed=7))
     band = _bands.Band(nside, rank, world)
-    order, theta_sorted, r_ang_max = cat.theta_order()
-    plan = _bands.Plan(band, theta_sorted, R_times * float(transform.arcmin2rad(r_ang_max)), n_chunks=2)
+    order = cat.theta_order()[0]
+    plan = _bands.Plan(band, cat.disc_reach(R_times), n_chunks=2)
     rows = order[plan.halo_lo:plan.halo_hi]
     full = np.zeros(12 * nside * nside)
     ref.spray(full, cat.data, nside, oprof.gaussian_readme, R_times=R_times, halo_list=rows)

@@ -200,7 +200,8 @@ def test_band_plan_ownership_and_streaming_are_safe():
             pix_sets.append(hp.query_disc(v, rs[i]))
         ring_starts = np.array([_bands.ring_start(nside, r) for r in range(1, 4 * nside + 1)])
         for b in bands:
-            plan = _bands.Plan(b, ts, float(rs.max()), n_chunks=n_chunks)
+            reach = (np.minimum.accumulate((ts - rs)[::-1])[::-1], np.maximum.accumulate(ts + rs))
+            plan = _bands.Plan(b, reach, n_chunks=n_chunks)
             assert plan.chunks[0][0] == plan.halo_lo and plan.chunks[-1][1] == plan.halo_hi
             assert plan.chunks[-1][2] == b.ring_hi
             for i, q in enumerate(pix_sets):
