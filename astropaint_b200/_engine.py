@@ -1,7 +1,7 @@
 """Device-side plumbing of the painting path: catalog columns in HBM and kernel launches.
 
 PyTorch is used for device memory, streams and (in `parallel.py`) torch.distributed; every
-compute step is a call into libastropaint_b200.so (csrc/kernels.cu) through `_capi`.
+compute step is a call into libastropaint_b200.so (csrc/k_*.cu) through `_capi`.
 """
 import ctypes as C
 

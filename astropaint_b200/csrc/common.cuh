@@ -11,10 +11,10 @@
 
 #if defined(__CUDACC__)
 #define AP_HD __host__ __device__ __forceinline__
-#define AP_HD_NOINLINE __host__ __device__
+#define AP_HD_NOINLINE inline __host__ __device__
 #else
 #define AP_HD inline
-#define AP_HD_NOINLINE
+#define AP_HD_NOINLINE inline
 #endif
 
 // Round-to-nearest multiply/add/sub that the compiler may NOT contract into an FMA.  The

@@ -1,0 +1,346 @@
+// astropaint_b200 — translation unit 4 of 4: K4 (@interpolate tables: nodes, QUADPACK node values, splines) and
+// the `len(R) < n_samples` bypass.
+#include "internal.cuh"
+
+AP_TU_BOUNDS_GETTER(ap_bounds_los)
+
+// ------------------------------------------------------------------------------------------
+// K4: @interpolate tables
+// ------------------------------------------------------------------------------------------
+__global__ void table_nodes_kernel(int64_t n, const int64_t* n_pix, const double* rmin, const double* rmax,
+                                   int32_t ns, int32_t method, double* nodes, int32_t* n_nodes) {
+  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n) return;
+  if (n_pix[h] < ns) {  // len(R) < n_samples -> direct evaluation (utils.py:510-511)
+    n_nodes[h] = 0;
+    for (int i = 0; i < ns; ++i) nodes[h * ns + i] = 0.0;
+    return;
+  }
+  n_nodes[h] = ns;
+  double a = rmin[h], b = rmax[h];
+  if (method == 1) {  // logspace: sample_array clamps the minimum to eps = 1e-3 (utils.py:417-421)
+    if (a < 1.0e-3) a = 1.0e-3;
+    a = log10(a);
+    b = log10(b);
+  }
+  // np.linspace: step = (b - a) / (n - 1); y_i = i * step + a; y_{n-1} = b
+  double step = AP_SUB(b, a) / (double)(ns - 1);
+  for (int i = 0; i < ns; ++i) {
+    double v = (i == ns - 1) ? b : AP_ADD(AP_MUL((double)i, step), a);
+    if (method == 1) v = pow(10.0, v);
+    nodes[h * ns + i] = v;
+  }
+}
+
+extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d_rmin, const double* d_rmax,
+                              int32_t n_samples, int32_t method, double* d_nodes, int32_t* d_n_nodes, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n_samples < 2 || n_samples > kMaxNodes) return fail("n_samples must be in [2, 32]");
+  if (method != 0 && method != 1) return fail("method must be 0 (linspace) or 1 (logspace)");
+  if (n == 0) return 0;
+  if (!d_n_pix || !d_rmin || !d_rmax || !d_nodes || !d_n_nodes) return fail("table_nodes: NULL pointer");
+  int threads = 128;
+  table_nodes_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n, d_n_pix, d_rmin, d_rmax, n_samples, method, d_nodes, d_n_nodes);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// 6 blocks of 128 threads per SM (80 registers): measured 176.1 / 173.5 / 180.9 / 182.9 ms
+// per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers); the kernel is fp64-pipe bound
+// (66% of the DFMA issue rate, profiles/), not occupancy bound
+#ifndef AP_QAGI_THREADS
+#define AP_QAGI_THREADS 128
+#endif
+#ifndef AP_QAGI_MINBLOCKS
+#define AP_QAGI_MINBLOCKS 6
+#endif
+template <int KIND, int FAST>
+__global__ void __launch_bounds__(AP_QAGI_THREADS, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64_t n, const double* p0, const double* p1,
+                                                                           const double* p2, int32_t ns, const double* nodes,
+                                                                           const int32_t* n_nodes, double* values) {
+  fm_smem_init();
+  // one thread per (halo, node).  A persistent grid-stride form (each resident thread reusing ONE local-memory
+  // frame, which removes the ~138 GB of dead local-memory write-back per 1e7 halos) measured 191 ms against
+  // 170 ms: resident warps then run in lockstep through the fp64-heavy and the bookkeeping phases.
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ns) return;
+  int64_t h = t / ns;
+  if (n_nodes[h] == 0) {
+    values[t] = 0.0;
+    return;
+  }
+  double ctx[kCtx];
+  los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+  values[t] = los_eval<KIND, FAST>(ctx, nodes[t]);
+}
+
+extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const double* d_p1, const double* d_p2,
+                            int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes, double* d_values,
+                            void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
+  if (n == 0) return 0;
+  if (!d_p0 || !d_p1 || (kind != LOS_NFW_RHO && !d_p2) || !d_nodes || !d_n_nodes || !d_values)
+    return fail("los_nodes: NULL pointer");
+  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
+  int threads = AP_QAGI_THREADS;
+  int64_t total = n * n_samples;
+  unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  cudaStream_t st = (cudaStream_t)stream;
+#define AP_LOS_NODES(K)                                                                                                  \
+  if (quad_fast_enabled())                                                                                                     \
+    los_nodes_kernel<K, 1><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values);    \
+  else                                                                                                                   \
+    los_nodes_kernel<K, 0><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values)
+  switch (kind) {
+    case LOS_B16_TAU: AP_LOS_NODES(LOS_B16_TAU); break;
+    case LOS_B16_NE: AP_LOS_NODES(LOS_B16_NE); break;
+    case LOS_B16_RHO_GAS: AP_LOS_NODES(LOS_B16_RHO_GAS); break;
+    case LOS_NFW_RHO: AP_LOS_NODES(LOS_NFW_RHO); break;
+  }
+#undef AP_LOS_NODES
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// diagnostic: tau_2D(R) with QUADPACK's own error estimate and evaluation count
+__global__ void __launch_bounds__(128) b16_tau_eval_kernel(int64_t n, const double* R, const double* R200,
+                                                           const double* M200, const double* zred, double* result,
+                                                           double* abserr, int32_t* neval) {
+  fm_smem_init();
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double ctx[kCtx];
+  b16_setup(R200[t], M200[t], zred[t], ctx);
+  QagiResult q;
+  result[t] = b16_tau_2D(ctx, R[t], &q);
+  if (abserr) abserr[t] = q.abserr;
+  if (neval) neval[t] = q.neval;
+}
+
+extern "C" int ap_b16_tau_eval(int64_t n, const double* d_R, const double* d_R_200c, const double* d_M_200c,
+                               const double* d_redshift, double* d_result, double* d_abserr, int32_t* d_neval,
+                               void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n == 0) return 0;
+  if (!d_R || !d_R_200c || !d_M_200c || !d_redshift || !d_result) return fail("b16_tau_eval: NULL pointer");
+  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
+  int threads = 128;
+  b16_tau_eval_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n, d_R, d_R_200c, d_M_200c, d_redshift, d_result, d_abserr, d_neval);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(128) spline_build_kernel(int64_t n, int32_t ns, const double* nodes,
+                                                           const double* values, const int32_t* n_nodes, double* coef) {
+  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n) return;
+  double* c = coef + h * (int64_t)(ns - 1) * 4;
+  if (n_nodes[h] == 0) {
+    for (int i = 0; i < (ns - 1) * 4; ++i) c[i] = 0.0;
+    return;
+  }
+  double x[kMaxNodes], y[kMaxNodes], cc[(kMaxNodes - 1) * 4];
+  for (int i = 0; i < ns; ++i) {
+    x[i] = nodes[h * ns + i];
+    y[i] = values[h * ns + i];
+  }
+  spline_build_nak(ns, x, y, cc);
+  for (int i = 0; i < (ns - 1) * 4; ++i) c[i] = cc[i];
+}
+
+// Uniform (np.linspace) nodes: the not-a-knot system has constant coefficients, so with NS a
+// compile-time constant the Thomas multipliers fold to literals and every array lives in registers.
+// A block builds 64 consecutive halos: node values are staged through shared memory (coalesced
+// 120 B rows in, 448 B rows out) instead of 8 B accesses strided by the row length.
+template <int NS>
+__global__ void __launch_bounds__(64) spline_build_uniform_kernel(int64_t n, const double* __restrict__ nodes,
+                                                                  const double* __restrict__ values,
+                                                                  const int32_t* __restrict__ n_nodes,
+                                                                  double* __restrict__ coef) {
+  constexpr int NC = (NS - 1) * 4;
+  __shared__ double sm[64 * NC];
+  const int tid = threadIdx.x;
+  const int64_t h0 = (int64_t)blockIdx.x * 64;
+  const int nh = (int)min((int64_t)64, n - h0);
+  for (int i = tid; i < nh * NS; i += 64) sm[i] = values[h0 * NS + i];
+  __syncthreads();
+  double y[NS], s[NS];
+  const bool active = tid < nh && n_nodes[h0 + tid] != 0;
+  double hstep = 1.0;
+  if (tid < nh) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) y[i] = sm[tid * NS + i];
+    if (active) hstep = (nodes[(h0 + tid) * NS + NS - 1] - nodes[(h0 + tid) * NS]) / (double)(NS - 1);
+  }
+  __syncthreads();
+  if (tid < nh) {
+    const double ih = 1.0 / hstep;
+    double dl[NS - 1];
+#pragma unroll
+    for (int i = 0; i < NS - 1; ++i) dl[i] = (y[i + 1] - y[i]) * ih;
+    // rows scaled by 1/h: [1 2 | (5 d0 + d1)/2], [1 4 1 | 3 (d_{i-1} + d_i)], [2 1 | (d_{n-3} + 5 d_{n-2})/2]
+    double diag[NS], up[NS];
+    s[0] = 0.5 * (5.0 * dl[0] + dl[1]);
+    diag[0] = 1.0;
+    up[0] = 2.0;
+#pragma unroll
+    for (int i = 1; i < NS - 1; ++i) {
+      const double m = 1.0 / diag[i - 1];  // lower = 1
+      diag[i] = 4.0 - m * up[i - 1];
+      up[i] = 1.0;
+      s[i] = 3.0 * (dl[i - 1] + dl[i]) - m * s[i - 1];
+    }
+    {
+      const double m = 2.0 / diag[NS - 2];
+      diag[NS - 1] = 1.0 - m * up[NS - 2];
+      s[NS - 1] = 0.5 * (dl[NS - 3] + 5.0 * dl[NS - 2]) - m * s[NS - 2];
+    }
+    s[NS - 1] = s[NS - 1] / diag[NS - 1];
+#pragma unroll
+    for (int i = NS - 2; i >= 0; --i) s[i] = (s[i] - up[i] * s[i + 1]) / diag[i];
+    double* out = sm + tid * NC;
+#pragma unroll
+    for (int i = 0; i < NS - 1; ++i) {
+      out[4 * i + 0] = active ? y[i] : 0.0;
+      out[4 * i + 1] = active ? s[i] : 0.0;
+      out[4 * i + 2] = active ? (3.0 * dl[i] - 2.0 * s[i] - s[i + 1]) * ih : 0.0;
+      out[4 * i + 3] = active ? (s[i] + s[i + 1] - 2.0 * dl[i]) * ih * ih : 0.0;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nh * NC; i += 64) coef[h0 * NC + i] = sm[i];
+}
+
+extern "C" int ap_spline_build_uniform(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,
+                                       const int32_t* d_n_nodes, double* d_coef, void* stream);
+
+extern "C" int ap_spline_build(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,
+                               const int32_t* d_n_nodes, double* d_coef, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n_samples < 4 || n_samples > kMaxNodes) return fail("n_samples must be in [4, 32]");
+  if (n == 0) return 0;
+  if (!d_nodes || !d_values || !d_n_nodes || !d_coef) return fail("spline_build: NULL pointer");
+  int threads = 128;
+  spline_build_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      n, n_samples, d_nodes, d_values, d_n_nodes, d_coef);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ap_spline_build_uniform(int64_t n, int32_t n_samples, const double* d_nodes, const double* d_values,
+                                       const int32_t* d_n_nodes, double* d_coef, void* stream) {
+  if (n < 0) return fail("n < 0");
+  if (n == 0) return 0;
+  if (!d_nodes || !d_values || !d_n_nodes || !d_coef) return fail("spline_build_uniform: NULL pointer");
+  unsigned blocks = (unsigned)((n + 63) / 64);
+  if (n_samples == 15)
+    spline_build_uniform_kernel<15><<<blocks, 64, 0, (cudaStream_t)stream>>>(n, d_nodes, d_values, d_n_nodes, d_coef);
+  else if (n_samples == 20)
+    spline_build_uniform_kernel<20><<<blocks, 64, 0, (cudaStream_t)stream>>>(n, d_nodes, d_values, d_n_nodes, d_coef);
+  else
+    return ap_spline_build(n, n_samples, d_nodes, d_values, d_n_nodes, d_coef, stream);  // generic solver
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// The `len(R) < n_samples` bypass of @interpolate (lib/utils.py:510-511): halos with 1 .. n_samples-1 pixels
+// get the projected profile (one QUADPACK quadrature) at every pixel.  Work items come from K1
+// (ap_disc_count_items: halo * 32 + pixel ordinal, appended on the device, their number in *n_items), so the
+// host never reads a count back; the grid is sized for the SMs and strides over the list, one quadrature per
+// lane.  Pixels outside the calling rank's ring band (ap_band_clip) belong to another rank and are skipped.
+template <int KIND, class MapT>
+__global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev H, const double* p0, const double* p1,
+                                                              const double* p2, const double* scale,
+                                                              const unsigned long long* n_items, int64_t item_cap,
+                                                              const int64_t* items, MapT* map,
+                                                              unsigned long long* n_painted) {
+  fm_smem_init();
+  const int64_t total = min((int64_t)*n_items, item_cap);
+  unsigned painted = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t h = items[t] >> 5;
+    const int32_t want = (int32_t)(items[t] & 31);
+    if (!AP_BOUNDS_OK(h >= 0 && h < H.n)) continue;
+    DiscHeader d = disc_header(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+    HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], false);
+    int32_t run = 0;
+    for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+      RingSpan s = ring_span(hpx, d, iz);
+      if (s.len <= 0) continue;
+      if (want < run + s.len) {
+        if (iz < hpx.clip_lo || iz >= hpx.clip_hi) break;  // another rank's ring
+        RingGeom g = ring_geom(hpx, iz, s, c);
+        int32_t js = want - run;
+        int32_t ip = s.ip_lo + js;
+        double R = c.D_a * pixel_sep(g, js);
+        double ctx[kCtx];
+        los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+        double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
+        const int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
+        if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && pix >= hpx.clip_pix0 && pix < hpx.npix)) {
+          atomicAdd(&map[pix - hpx.clip_pix0], (MapT)val);
+          ++painted;
+        }
+        break;
+      }
+      run += s.len;
+    }
+  }
+  painted = __reduce_add_sync(0xffffffffu, painted);
+  if (n_painted && painted && (threadIdx.x & 31) == 0) atomicAdd(n_painted, (unsigned long long)painted);
+}
+
+template <int KIND>
+static void launch_los_items(bool f32, unsigned blocks, cudaStream_t st, Hpx hpx, HalosDev H, const double* p0,
+                             const double* p1, const double* p2, const double* scale, const unsigned long long* n_items,
+                             int64_t item_cap, const int64_t* items, void* map, unsigned long long* n_painted) {
+  if (f32)
+    paint_los_items_kernel<KIND, float><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (float*)map, n_painted);
+  else
+    paint_los_items_kernel<KIND, double><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (double*)map, n_painted);
+}
+
+static int paint_los_items_impl(int kind, int64_t nside, const ap_halos* halos, const double* p0, const double* p1,
+                                const double* p2, const double* scale, const unsigned long long* d_n_items,
+                                int64_t item_cap, const int64_t* d_items, void* d_map, bool f32,
+                                unsigned long long* d_n_painted, void* stream) {
+  if (check_nside(nside)) return 1;
+  if (check_halos(halos, true)) return 1;
+  if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
+  if (item_cap < 0) return fail("item_cap < 0");
+  if (item_cap == 0 || halos->n == 0) return 0;
+  if (!p0 || !p1 || (kind != LOS_NFW_RHO && !p2) || !d_n_items || !d_items || !d_map)
+    return fail("paint_los_items: NULL pointer");
+  if (rm_ensure_tables(stream)) return fail("could not initialise the quadrature tables");
+  int64_t nb = (item_cap + 127) / 128;
+  if (nb > 148 * 12) nb = 148 * 12;  // 12 resident blocks of 128 threads per SM: the list is walked grid-stride
+  unsigned blocks = (unsigned)nb;
+  Hpx hpx = disc_hpx(nside);
+  HalosDev H = to_dev(halos);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case LOS_B16_TAU: launch_los_items<LOS_B16_TAU>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
+    case LOS_B16_NE: launch_los_items<LOS_B16_NE>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
+    case LOS_B16_RHO_GAS: launch_los_items<LOS_B16_RHO_GAS>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
+    case LOS_NFW_RHO: launch_los_items<LOS_NFW_RHO>(f32, blocks, st, hpx, H, p0, p1, p2, scale, d_n_items, item_cap, d_items, d_map, d_n_painted); break;
+  }
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ap_paint_los_items(int kind, int64_t nside, const ap_halos* halos, const double* d_p0, const double* d_p1,
+                                  const double* d_p2, const double* d_scale, const unsigned long long* d_n_items,
+                                  int64_t item_cap, const int64_t* d_items, double* d_map,
+                                  unsigned long long* d_n_painted, void* stream) {
+  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_items, item_cap, d_items, d_map, false,
+                              d_n_painted, stream);
+}
+extern "C" int ap_paint_los_items_f32(int kind, int64_t nside, const ap_halos* halos, const double* d_p0,
+                                      const double* d_p1, const double* d_p2, const double* d_scale,
+                                      const unsigned long long* d_n_items, int64_t item_cap, const int64_t* d_items,
+                                      float* d_map, unsigned long long* d_n_painted, void* stream) {
+  return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_items, item_cap, d_items, d_map, true,
+                              d_n_painted, stream);
+}

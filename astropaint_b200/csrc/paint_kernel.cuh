@@ -1,0 +1,406 @@
+// K3 / K1: the fused painter kernel template and its launcher (instantiated by k_paint.cu and k_paint_los.cu).
+#pragma once
+#include "internal.cuh"
+
+// ------------------------------------------------------------------------------------------
+// K3: fused painter
+// ------------------------------------------------------------------------------------------
+constexpr int kPaintThreads = 256;
+constexpr int kMaxHalosPerBlock = 112;
+// templates that run a quadrature per PIXEL also hold the log/exp tables in shared memory (fastmath.cuh):
+// fewer halos per block keep them inside the 48 KB static limit; their time is all quadrature anyway
+template <int P>
+constexpr int max_halos_per_block() {
+  return (P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) ? 48 : kMaxHalosPerBlock;
+}
+constexpr int kHintMax = 256;     // warp-group hints cover chunks up to 8 Ki pixels
+constexpr int kPixMapMax = 4096;  // pixel -> ring-item byte map for the first 4 Ki pixels of a chunk
+constexpr int kStageHalos = 28;   // spline coefficients staged in shared memory per chunk (P_TABLE)
+constexpr int kStageMaxNodes = 15;
+constexpr int P_TABLE = 100;   // tabulated template (spline of per-halo nodes)
+constexpr int P_STATS = 101;   // no painting: per-halo pixel count and R range (K1)
+
+struct ParamPtrs {
+  const double* p[kMaxParams];
+  int32_t stride[kMaxParams];
+  int32_t n;
+};
+
+struct TableArgs {
+  const double* nodes;
+  const double* coef;
+  const int32_t* n_nodes;
+  const double* scale;
+  int32_t n_samples;
+  int32_t uniform;  // nodes are linspace: interval index by multiplication
+};
+
+struct StatsArgs {
+  int64_t* n_pix;
+  int32_t* n_rings;
+  double* rmin;
+  double* rmax;
+  // optional work list of the `len(R) < n_samples` bypass: halos with 0 < n_pix < item_ns append one packed
+  // item (halo * 32 + pixel ordinal) per pixel at items[atomicAdd(item_count, n_pix) ...] (capacity item_cap)
+  unsigned long long* item_count;
+  int64_t* items;
+  int64_t item_cap;
+  int32_t item_ns;
+};
+
+struct HaloHdr {  // DiscHeader with 32-bit ring numbers (nside <= 2^18)
+  double phi, z0, xa, cosr, cosrs;
+  int32_t irmin, irmax, ir_first, ir_last;
+};
+
+struct RingItem {
+  int64_t startpix;
+  int32_t nr, ip_lo, len, hl;
+  double A, B, phi_step, d0;
+};
+struct RingItemVec {  // extra per-ring data of R_vec templates
+  double phi0, z, sth;
+};
+
+template <int P>
+struct PaintShared {
+  static constexpr int MAXH = max_halos_per_block<P>();
+  static constexpr bool VEC = (P == P_NFW_BG);
+  static constexpr int NCTX = (P == P_TABLE) ? 4 : ((P == P_STATS) ? 1 : kCtx);
+  HaloHdr hdr[MAXH];
+  double cen_cos[MAXH], cen_phi[MAXH], cen_sin[MAXH],
+      cen_Da[MAXH];
+  double cen_vec[VEC ? MAXH : 1][3];
+  double ctx[MAXH][NCTX];
+  int32_t ring_off[MAXH + 1];
+  RingItem item[kPaintThreads];
+  RingItemVec itemv[VEC ? kPaintThreads : 1];
+  int32_t pix_off[kPaintThreads + 1];
+  int32_t warp_sum[kPaintThreads / 32];
+  int32_t hint[kHintMax];  // hint[g] = ring item holding pixel 32 g of the current chunk
+  uint8_t pixmap[P == P_STATS ? 1 : kPixMapMax];  // ring item of each of the first 4 Ki pixels
+  double stage[P == P_TABLE ? kStageHalos * (kStageMaxNodes - 1) * 4 : 1];
+  // P_STATS accumulators
+  unsigned long long cnt[P == P_STATS ? MAXH : 1];
+  unsigned long long hmin[P == P_STATS ? MAXH : 1], hmax[P == P_STATS ? MAXH : 1];
+};
+
+// One block paints `halos_per_block` consecutive halos.  Phase 0: per-halo disc header, centre and
+// template constants (one thread per halo).  Then, 256 ring items at a time: phase 1 computes one
+// ring span per thread (query_disc's per-ring work) and its ring-constant geometry, a block scan of
+// the span lengths gives the flat pixel numbering; phase 2 walks the pixels with consecutive lanes
+// on consecutive pixels of a ring (sector-coalesced fp64 RED traffic), evaluates separation,
+// template and accumulates.  No work list ever touches HBM.
+template <int P, class MapT, bool INCL>
+__global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
+                                                               StatsArgs st, int halos_per_block,
+                                                               MapT* __restrict__ map,
+                                                               unsigned long long* n_painted) {
+  constexpr bool VEC = (P == P_NFW_BG);
+  constexpr bool STATS = (P == P_STATS);
+  __shared__ PaintShared<P> sm;
+  if (P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) fm_smem_init();
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int64_t h0 = (int64_t)blockIdx.x * halos_per_block;
+  const int G = (int)min((int64_t)halos_per_block, H.n - h0);
+
+  // phase 0
+  if (tid < G) {
+    int64_t h = h0 + tid;
+    DiscHeader d = disc_header_t<INCL>(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+    if (P == P_TABLE && tab.n_nodes[h] == 0) {  // bypass halo: painted elsewhere
+      d.ir_first = 1;
+      d.ir_last = 0;
+    }
+    if (STATS) {  // counts stay those of the WHOLE disc; a disc that misses the rank's band reports 0 pixels
+      if (d.ir_last < hpx.clip_lo || d.ir_first >= hpx.clip_hi) {
+        d.ir_first = 1;
+        d.ir_last = 0;
+      }
+    } else {      // paint the rings of the rank's own band only
+      if (d.ir_first < hpx.clip_lo) d.ir_first = hpx.clip_lo;
+      if (d.ir_last >= hpx.clip_hi) d.ir_last = hpx.clip_hi - 1;
+    }
+    HaloHdr hh;
+    hh.phi = d.phi; hh.z0 = d.z0; hh.xa = d.xa; hh.cosr = d.cosr; hh.cosrs = d.cosrs;
+    hh.irmin = (int32_t)d.irmin; hh.irmax = (int32_t)d.irmax;
+    hh.ir_first = (int32_t)d.ir_first; hh.ir_last = (int32_t)d.ir_last;
+    sm.hdr[tid] = hh;
+    if (!STATS || st.rmin) {
+      HaloCenter c = make_center(H.theta[h], H.phi[h], H.D_a[h], VEC);
+      sm.cen_cos[tid] = c.cos_t; sm.cen_phi[tid] = c.phi; sm.cen_sin[tid] = c.sin_t; sm.cen_Da[tid] = c.D_a;
+      if (VEC) { sm.cen_vec[tid][0] = c.cx; sm.cen_vec[tid][1] = c.cy; sm.cen_vec[tid][2] = c.cz; }
+    }
+    if (STATS) {
+      sm.cnt[tid] = 0ull;
+      sm.hmin[tid] = 0x7ff0000000000000ull;  // +inf
+      sm.hmax[tid] = 0ull;                   // haversines are >= 0: their bit patterns order like uint64
+    } else if (P == P_TABLE) {
+      const double* x = tab.nodes + h * tab.n_samples;
+      sm.ctx[tid][0] = tab.scale ? tab.scale[h] : 1.0;
+      sm.ctx[tid][1] = x[0];
+      sm.ctx[tid][3] = (x[tab.n_samples - 1] - x[0]) / (double)(tab.n_samples - 1);
+      sm.ctx[tid][2] = 1.0 / sm.ctx[tid][3];
+    } else {
+      double p[kMaxParams];
+#pragma unroll
+      for (int i = 0; i < kMaxParams; ++i)
+        if (i < pp.n) p[i] = pp.p[i][h * pp.stride[i]];
+      profile_setup<P>(p, sm.ctx[tid]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int32_t run = 0;
+    for (int i = 0; i < G; ++i) {
+      sm.ring_off[i] = run;
+      int32_t n = sm.hdr[i].ir_last - sm.hdr[i].ir_first + 1;
+      run += n > 0 ? n : 0;
+    }
+    sm.ring_off[G] = run;
+  }
+  __syncthreads();
+  const int32_t T = sm.ring_off[G];
+  unsigned long long painted = 0;
+
+  for (int32_t base = 0; base < T; base += kPaintThreads) {
+    // P_TABLE: the spline coefficients of the halos this chunk touches are one contiguous run in HBM;
+    // start streaming the first kStageHalos of them now (coalesced), park them in shared memory after
+    // phase 1 so that phase 2 never waits on a dependent global load
+    constexpr int kStageRegs = (P == P_TABLE) ? (kStageHalos * (kStageMaxNodes - 1) * 4 + kPaintThreads - 1) / kPaintThreads : 1;
+    double stage_reg[kStageRegs];
+    int stage_lo = 0, stage_n = 0;
+    const bool do_stage = (P == P_TABLE) && tab.n_samples <= kStageMaxNodes;
+    if (do_stage) {
+      int lo = 0, hi = G;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (sm.ring_off[mid] <= base) lo = mid; else hi = mid;
+      }
+      stage_lo = lo;
+      const int nc = (tab.n_samples - 1) * 4;
+      stage_n = min(kStageHalos, G - lo) * nc;
+      const double* src = tab.coef + (h0 + lo) * (int64_t)nc;
+#pragma unroll
+      for (int q = 0; q < kStageRegs; ++q) {
+        int e = tid + q * kPaintThreads;
+        stage_reg[q] = (e < stage_n) ? __ldg(src + e) : 0.0;
+      }
+    }
+
+    // phase 1: one ring item per thread
+    int32_t it = base + tid;
+    int32_t len = 0;
+    if (it < T) {
+      int lo = 0, hi = G;  // largest hl with ring_off[hl] <= it
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (sm.ring_off[mid] <= it) lo = mid; else hi = mid;
+      }
+      const HaloHdr& hh = sm.hdr[lo];
+      DiscHeader d;
+      d.phi = hh.phi; d.z0 = hh.z0; d.xa = hh.xa; d.cosr = hh.cosr; d.cosrs = hh.cosrs;
+      d.irmin = hh.irmin; d.irmax = hh.irmax; d.ir_first = hh.ir_first; d.ir_last = hh.ir_last;
+      int64_t iz = d.ir_first + (it - sm.ring_off[lo]);
+      RingSpan s = ring_span_t<INCL>(hpx, d, iz);
+      len = s.len;
+      RingItem& r = sm.item[tid];
+      r.len = s.len;
+      if (len > 0 && (!STATS || st.rmin)) {
+        HaloCenter c;
+        c.cos_t = sm.cen_cos[lo]; c.phi = sm.cen_phi[lo]; c.sin_t = sm.cen_sin[lo]; c.D_a = sm.cen_Da[lo];
+        RingGeom g = ring_geom(hpx, iz, s, c);
+        if (STATS) {
+          double a, b;
+          span_hav_range(g, s.len, a, b);
+          atomicMin(&sm.hmin[lo], (unsigned long long)__double_as_longlong(a));
+          atomicMax(&sm.hmax[lo], (unsigned long long)__double_as_longlong(b));
+        } else {
+          r.startpix = s.startpix; r.nr = s.nr; r.ip_lo = s.ip_lo; r.hl = lo;
+          r.A = g.A; r.B = g.B; r.phi_step = g.phi_step; r.d0 = g.d0;
+          if (VEC) { sm.itemv[tid].phi0 = g.phi0; sm.itemv[tid].z = g.z; sm.itemv[tid].sth = g.sth; }
+        }
+      }
+      if (STATS && len > 0) atomicAdd(&sm.cnt[lo], (unsigned long long)len);
+    }
+    if (STATS) continue;  // counts and ranges only: no pixel walk (no barrier needed either)
+
+    // block exclusive scan of len
+    int32_t v = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) sm.warp_sum[warp] = v;
+    __syncthreads();
+    int32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < kPaintThreads / 32; ++w)
+      if (w < warp) woff += sm.warp_sum[w];
+    {
+      const int32_t start = woff + v - len, end = start + len;
+      sm.pix_off[tid] = start;
+      if (tid == kPaintThreads - 1) sm.pix_off[kPaintThreads] = end;
+      // every multiple of 32 inside [start, end) starts a warp-sized pixel group in this ring item
+      for (int32_t m = (start + 31) & ~31; m < end && (m >> 5) < kHintMax; m += 32) sm.hint[m >> 5] = tid;
+      const int32_t mend = min(end, (int32_t)kPixMapMax);
+      for (int32_t m = start; m < mend; ++m) sm.pixmap[m] = (uint8_t)tid;
+      if (do_stage) {
+#pragma unroll
+        for (int q = 0; q < kStageRegs; ++q) {
+          int e = tid + q * kPaintThreads;
+          if (e < stage_n) sm.stage[e] = stage_reg[q];
+        }
+      }
+    }
+    __syncthreads();
+    const int32_t total = sm.pix_off[kPaintThreads];
+    painted += (tid == 0) ? (unsigned long long)total : 0ull;
+
+    // phase 2: two pixels per thread per iteration (k and k + 256): independent dependency chains
+    // (table loads, series) overlap, then both REDs are issued
+    auto eval = [&](int32_t k, int64_t& pix) -> double {
+      int lo;
+      if (k < kPixMapMax) {
+        lo = sm.pixmap[k];
+        if (!AP_BOUNDS_OK(k >= sm.pix_off[lo] && k < sm.pix_off[lo + 1])) lo = 0;
+      } else if ((k >> 5) < kHintMax) {
+        lo = sm.hint[k >> 5];
+        while (sm.pix_off[lo + 1] <= k) ++lo;
+      } else {  // chunk with more than 32 Ki pixels (sky-sized discs): plain binary search
+        lo = 0;
+        int hi = kPaintThreads;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (sm.pix_off[mid] <= k) lo = mid; else hi = mid;
+        }
+      }
+      const RingItem& r = sm.item[lo];
+      const int32_t j = k - sm.pix_off[lo];
+      const int hl = r.hl;
+      double val;
+      if (VEC) {
+        RingGeom g;
+        g.phi_step = r.phi_step; g.phi0 = sm.itemv[lo].phi0; g.z = sm.itemv[lo].z; g.sth = sm.itemv[lo].sth;
+        HaloCenter c;
+        c.D_a = sm.cen_Da[hl]; c.cx = sm.cen_vec[hl][0]; c.cy = sm.cen_vec[hl][1]; c.cz = sm.cen_vec[hl][2];
+        double rx, ry, rz;
+        pixel_chord(g, j, c, rx, ry, rz);
+        val = profile_eval_vec<P>(sm.ctx[hl], rx, ry, rz);
+      } else {
+        double hav = r.A + r.B * sin2_half(r.d0 + (double)j * r.phi_step);
+        double R = sm.cen_Da[hl] * sep_from_hav(hav);
+        if (P == P_TABLE) {
+          const int64_t h = h0 + hl;
+          const int ns = tab.n_samples;
+          const double* x = tab.nodes + h * ns;
+          int i;
+          if (tab.uniform) {  // linspace nodes: the spline is C2, so +-1 ulp at a knot picks an equal piece
+            i = (int)((R - sm.ctx[hl][1]) * sm.ctx[hl][2]);
+            i = i < 0 ? 0 : (i > ns - 2 ? ns - 2 : i);
+          } else {
+            i = spline_interval(ns, x, R);
+          }
+          double t;
+          double2 c01, c23;
+          const int sh = hl - stage_lo;
+          if (do_stage && tab.uniform && sh < kStageHalos &&
+              AP_BOUNDS_OK(sh >= 0 && (sh * (ns - 1) + i) * 4 + 3 < stage_n && i >= 0 && i <= ns - 2)) {
+            t = R - (sm.ctx[hl][1] + (double)i * sm.ctx[hl][3]);  // node i of np.linspace to 1 ulp
+            const double2* c2 = reinterpret_cast<const double2*>(sm.stage + (sh * (ns - 1) + i) * 4);
+            c01 = c2[0];
+            c23 = c2[1];
+          } else {
+            t = R - __ldg(x + i);
+            const double2* c2 = reinterpret_cast<const double2*>(tab.coef + (h * (int64_t)(ns - 1) + i) * 4);
+            c01 = __ldg(c2);
+            c23 = __ldg(c2 + 1);
+          }
+          val = (c01.x + t * (c01.y + t * (c23.x + t * c23.y))) * sm.ctx[hl][0];
+        } else {
+          val = profile_eval_R<P>(sm.ctx[hl], R);
+        }
+      }
+      int32_t ip = r.ip_lo + j;
+      pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
+      return val;
+    };
+    for (int32_t k = tid; k < total; k += 2 * kPaintThreads) {
+      int64_t p0, p1 = 0;
+      const bool two = (k + kPaintThreads < total);
+      double v0 = eval(k, p0);
+      double v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
+      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) atomicAdd(&map[p0 - hpx.clip_pix0], (MapT)v0);
+      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) atomicAdd(&map[p1 - hpx.clip_pix0], (MapT)v1);
+    }
+    __syncthreads();
+  }
+  if (STATS) {
+    __syncthreads();
+    if (tid < G) {
+      int64_t h = h0 + tid;
+      unsigned long long c = sm.cnt[tid];
+      st.n_pix[h] = (int64_t)c;
+      if (st.n_rings) {
+        int32_t n = sm.hdr[tid].ir_last - sm.hdr[tid].ir_first + 1;
+        st.n_rings[h] = n > 0 ? n : 0;
+      }
+      if (st.rmin) {
+        double a = __longlong_as_double((long long)sm.hmin[tid]), b = __longlong_as_double((long long)sm.hmax[tid]);
+        st.rmin[h] = c ? sm.cen_Da[tid] * sep_from_hav(a) : INFINITY;
+        st.rmax[h] = c ? sm.cen_Da[tid] * sep_from_hav(b) : -INFINITY;
+      }
+      if (st.items && c > 0ull && c < (unsigned long long)st.item_ns) {
+        const unsigned long long at = atomicAdd(st.item_count, c);
+        for (unsigned long long k = 0; k < c; ++k)
+          if ((int64_t)(at + k) < st.item_cap) st.items[at + k] = h * 32 + (int64_t)k;
+      }
+    }
+    return;
+  }
+  if (n_painted && tid == 0 && painted) atomicAdd(n_painted, painted);
+}
+
+static int pick_halos_per_block(int64_t n, int max_halos) {
+  // enough blocks to fill 148 SMs several times over; many halos per block amortise phase 0
+  int64_t g = n / (148 * 8);
+  if (g < 1) g = 1;
+  if (g > max_halos) g = max_halos;
+  return (int)g;
+}
+
+template <int P>
+static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& pp, const TableArgs& tab, void* d_map,
+                        unsigned long long* d_n_painted, void* stream, const StatsArgs* stats = nullptr,
+                        bool f32 = false) {
+  if ((P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) && rm_ensure_tables(stream))
+    return fail("could not initialise the quadrature tables");
+  int g = pick_halos_per_block(halos->n, max_halos_per_block<P>());
+  int64_t blocks = (halos->n + g - 1) / g;
+  if (blocks > 0x7fffffffLL) return fail("too many blocks");
+  StatsArgs st;
+  memset(&st, 0, sizeof(st));
+  if (stats) st = *stats;
+  const Hpx hpx = disc_hpx(nside);
+  const unsigned nb = (unsigned)blocks;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (f32 && P != P_STATS) {
+    if (hpx.incl_fct)
+      paint_kernel<P, float, true><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+    else
+      paint_kernel<P, float, false><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+  } else {
+    if (hpx.incl_fct)
+      paint_kernel<P, double, true><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+    else
+      paint_kernel<P, double, false><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+  }
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// the per-pixel quadrature templates (P_B16_TAU2D, P_B16_RHOGAS2D, P_NFW_RHO2D_LOS) are instantiated in k_paint_los.cu
+int launch_paint_los(int profile, int64_t nside, const ap_halos* halos, const ParamPtrs& pp, const TableArgs& tab,
+                     void* d_map, unsigned long long* d_n_painted, void* stream, bool f32);

@@ -6,7 +6,7 @@ Mirrors `astropaint/paint_bucket.py` of syasini/AstroPaint for the hot path only
     Canvas(catalog, nside, R_times, inclusive) paint_bucket.py:773-955, 1175-1323, 1601-1966
     Painter(template).spray(canvas, **kwargs)  paint_bucket.py:2263-2676
 
-Everything per (halo, pixel) runs in hand-written sm_100a CUDA (csrc/kernels.cu) behind the C ABI
+Everything per (halo, pixel) runs in hand-written sm_100a CUDA (csrc/k_*.cu) behind the C ABI
 of include/astropaint_b200.h.  There is no CPU implementation of the path in this package.
 """
 import inspect
@@ -233,7 +233,7 @@ class Catalog:
         d["v_lon"] = d["v_ph"]
 
     def _build_dataframe_device(self, calculate_redshifts, default_redshift):
-        """the same 17 columns from csrc/kernels.cu::catalog_build_kernel, one pinned read-back"""
+        """the same 17 columns from csrc/k_core.cu::catalog_build_kernel, one pinned read-back"""
         d = self.data
         cols = {k: d[k].values.astype(np.float64, copy=False) for k in ("x", "y", "z", "v_x", "v_y", "v_z", "M_200c")}
         if calculate_redshifts:   # z_at_value per halo in the reference (:321-323); table inversion here, on the host

@@ -3,6 +3,5 @@
 #   bash tools/debug_bounds.sh
 set -e
 cd "$(dirname "$0")/.."
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DAP_DEBUG_BOUNDS -shared -Xcompiler -fPIC \
-  astropaint_b200/csrc/kernels.cu -o /tmp/libastropaint_b200_bounds.so
+python -c "import __graft_entry__ as g; g.build_library('/tmp/libastropaint_b200_bounds.so', defines=['-DAP_DEBUG_BOUNDS'], obj_dir='/tmp/ap_bounds_obj', force=True)"
 AP_LIB_PATH=/tmp/libastropaint_b200_bounds.so AP_REPORT_BOUNDS=1 python -m pytest tests -m gpu -q -x --timeout 900
