@@ -43,7 +43,7 @@ SIGNATURES = {
     "ap_paint_profile": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), C.POINTER(c_ptr), C.POINTER(c_i32),
                                    c_i32, c_ptr, c_ptr, c_ptr]),
     "ap_table_nodes": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
-    "ap_los_nodes": (C.c_int, [C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_los_nodes": (C.c_int, [C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_b16_tau_eval": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spline_build": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_spline_build_uniform": (C.c_int, [c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

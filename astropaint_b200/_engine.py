@@ -393,8 +393,9 @@ def los_nodes(kind, halos, args, nodes, n_nodes):
     """QUADPACK projection of the 3-D profile `kind` at every (halo, node); args = its per-halo arguments."""
     values = torch.empty_like(nodes)
     a = list(args) + [None] * (3 - len(args))
+    scratch = torch.empty((halos.n, 4), dtype=torch.float64, device=nodes.device)   # per-halo profile constants
     check(_capi.lib().ap_los_nodes(LOS_KINDS[kind], halos.n, ptr(a[0]), ptr(a[1]), ptr(a[2]), nodes.shape[1], ptr(nodes),
-                                   ptr(n_nodes), ptr(values), stream_ptr()))
+                                   ptr(n_nodes), ptr(values), ptr(scratch), stream_ptr()))
     return values
 
 

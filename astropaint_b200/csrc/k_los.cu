@@ -55,10 +55,23 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
 #ifndef AP_QAGI_MINBLOCKS
 #define AP_QAGI_MINBLOCKS 6
 #endif
+// per-halo constants of the 3-D profile (los_setup: eight pow() for the Battaglia fit and the critical density):
+// once per halo, one halo per lane, instead of once per (halo, node) thread of the node kernel
+template <int KIND>
+__global__ void __launch_bounds__(128) los_setup_kernel(int64_t n, const double* p0, const double* p1, const double* p2,
+                                                        const int32_t* n_nodes, double4* ctx_out) {
+  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n || n_nodes[h] == 0) return;
+  double ctx[kCtx];
+  los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+  ctx_out[h] = make_double4(ctx[0], ctx[1], ctx[2], ctx[3]);
+}
+
 template <int KIND, int FAST>
 __global__ void __launch_bounds__(AP_QAGI_THREADS, AP_QAGI_MINBLOCKS) los_nodes_kernel(int64_t n, const double* p0, const double* p1,
-                                                                           const double* p2, int32_t ns, const double* nodes,
-                                                                           const int32_t* n_nodes, double* values) {
+                                                                           const double* p2, const double4* halo_ctx, int32_t ns,
+                                                                           const double* nodes, const int32_t* n_nodes,
+                                                                           double* values) {
   fm_smem_init();
   // one thread per (halo, node).  A persistent grid-stride form (each resident thread reusing ONE local-memory
   // frame, which removes the ~138 GB of dead local-memory write-back per 1e7 halos) measured 191 ms against
@@ -71,15 +84,22 @@ __global__ void __launch_bounds__(AP_QAGI_THREADS, AP_QAGI_MINBLOCKS) los_nodes_
     return;
   }
   double ctx[kCtx];
-  los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+  if (halo_ctx) {
+    const double2* c = reinterpret_cast<const double2*>(halo_ctx + h);
+    const double2 c01 = __ldg(c), c23 = __ldg(c + 1);
+    ctx[0] = c01.x; ctx[1] = c01.y; ctx[2] = c23.x; ctx[3] = c23.y;
+  } else {
+    los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
+  }
   values[t] = los_eval<KIND, FAST>(ctx, nodes[t]);
 }
 
 extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const double* d_p1, const double* d_p2,
                             int32_t n_samples, const double* d_nodes, const int32_t* d_n_nodes, double* d_values,
-                            void* stream) {
+                            double* d_halo_scratch, void* stream) {
   if (n < 0) return fail("n < 0");
   if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
+  if (d_halo_scratch && (reinterpret_cast<uintptr_t>(d_halo_scratch) & 31)) return fail("los_nodes: d_halo_scratch must be 32-byte aligned");
   if (n == 0) return 0;
   if (!d_p0 || !d_p1 || (kind != LOS_NFW_RHO && !d_p2) || !d_nodes || !d_n_nodes || !d_values)
     return fail("los_nodes: NULL pointer");
@@ -88,11 +108,15 @@ extern "C" int ap_los_nodes(int kind, int64_t n, const double* d_p0, const doubl
   int64_t total = n * n_samples;
   unsigned blocks = (unsigned)((total + threads - 1) / threads);
   cudaStream_t st = (cudaStream_t)stream;
-#define AP_LOS_NODES(K)                                                                                                  \
-  if (quad_fast_enabled())                                                                                                     \
-    los_nodes_kernel<K, 1><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values);    \
-  else                                                                                                                   \
-    los_nodes_kernel<K, 0><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, n_samples, d_nodes, d_n_nodes, d_values)
+  const double4* hc = reinterpret_cast<const double4*>(d_halo_scratch);
+#define AP_LOS_NODES(K)                                                                                                     \
+  if (hc)                                                                                                                   \
+    los_setup_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, d_p0, d_p1, d_p2, d_n_nodes,                        \
+                                                                     reinterpret_cast<double4*>(d_halo_scratch));           \
+  if (quad_fast_enabled())                                                                                                  \
+    los_nodes_kernel<K, 1><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, hc, n_samples, d_nodes, d_n_nodes, d_values);   \
+  else                                                                                                                      \
+    los_nodes_kernel<K, 0><<<blocks, threads, 0, st>>>(n, d_p0, d_p1, d_p2, hc, n_samples, d_nodes, d_n_nodes, d_values)
   switch (kind) {
     case LOS_B16_TAU: AP_LOS_NODES(LOS_B16_TAU); break;
     case LOS_B16_NE: AP_LOS_NODES(LOS_B16_NE); break;

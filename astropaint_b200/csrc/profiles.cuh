@@ -124,6 +124,9 @@ struct B16Integrand {
   // The constant factor K2 = 2 rho0 rho_c(z) f_b / factor * sigma_T multiplies the INTEGRAL, not the
   // integrand (los_eval): with epsabs = 0 every QUADPACK test is homogeneous in the integrand's scale.
   AP_HD double operator()(double r) const {
+    // (Round 2: replacing the exp -> log pair of log(1 + y^alpha) by ONE table-driven degree-7 polynomial of
+    // softplus(alpha L) -- 12 fp64 instructions instead of 20 -- ran 66% SLOWER: its 64 B of coefficients per
+    // evaluation and lane saturate the shared-memory pipe (the pair reads 24 B); profiles/README.md.)
     double L = fast_log(AP_MUL(r, inv_R200xc));        // log((r / R_200c) / xc)
     double ya = fast_exp(AP_MUL(alpha, L));
     double fit = fast_exp(fm_fma(expo, fast_log(AP_ADD(1.0, ya)), AP_MUL(-0.2, L)));

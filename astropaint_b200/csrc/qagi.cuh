@@ -120,8 +120,15 @@ AP_NOINLINE AP_HD_NOINLINE void qk15i(const F& f_ref, double boun, double a, dou
   resabs = AP_MUL(resabs, hlgth);
   abserr = fabs(AP_MUL(AP_SUB(resk, resg), hlgth));
   if (resasc != 0.0 && abserr != 0.0) {
+#if defined(__CUDA_ARCH__) && !defined(AP_QK_IEEE_TAIL)
+    // call-free (200 abserr / resasc)^1.5: reciprocal and reciprocal square root by MUFU seed + Newton steps
+    // (<= 1 ulp from the IEEE division / sqrt; an overflowing or NaN intermediate ends in min(1, .) = 1 as before)
+    double q = AP_MUL(AP_MUL(200.0, abserr), fm_rcp(resasc));
+    double p = (q > 1.0e-290) ? AP_MUL(q, AP_MUL(q, fm_rsqrt(q))) : 0.0;
+#else
     double q = AP_MUL(200.0, abserr) / resasc;
     double p = AP_MUL(q, sqrt(q));  // q**1.5
+#endif
     abserr = AP_MUL(resasc, fmin(1.0, p));
   }
   if (resabs > kUflow / (50.0 * kEpmach)) abserr = fmax(AP_MUL(kEpmach * 50.0, resabs), abserr);
@@ -670,8 +677,15 @@ AP_RM_RULE_ATTR void qk15i_rm(const F& f_ref, double boun, int idx, double& resu
   resabs = AP_MUL(resabs, hlgth);
   abserr = fabs(AP_MUL(AP_SUB(resk, resg), hlgth));
   if (resasc != 0.0 && abserr != 0.0) {
+#if defined(__CUDA_ARCH__) && !defined(AP_QK_IEEE_TAIL)
+    // call-free (200 abserr / resasc)^1.5: reciprocal and reciprocal square root by MUFU seed + Newton steps
+    // (<= 1 ulp from the IEEE division / sqrt; an overflowing or NaN intermediate ends in min(1, .) = 1 as before)
+    double q = AP_MUL(AP_MUL(200.0, abserr), fm_rcp(resasc));
+    double p = (q > 1.0e-290) ? AP_MUL(q, AP_MUL(q, fm_rsqrt(q))) : 0.0;
+#else
     double q = AP_MUL(200.0, abserr) / resasc;
     double p = AP_MUL(q, sqrt(q));  // q**1.5
+#endif
     abserr = AP_MUL(resasc, fmin(1.0, p));
   }
   if (resabs > kUflow / (50.0 * kEpmach)) abserr = fmax(AP_MUL(kEpmach * 50.0, resabs), abserr);

@@ -148,9 +148,12 @@ int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d_rmin, cons
  * (lib/utils.py:445-448).  d_p0, d_p1, d_p2 are the 3-D profile's per-halo arguments in reference
  * order (R_200c, M_200c, redshift | rho_s, r_s, NULL).  Serves Battaglia16.tau_2D_interp / kSZ_T (n=15,
  * :242-271), Battaglia16.ne_2D (interpolate(n=20) of LOS_integrate(ne_3D), :201-218) and
- * NFW.rho_2D_interp (n=20, logspace; NFW.py:96-108).                                           */
+ * NFW.rho_2D_interp (n=20, logspace; NFW.py:96-108).  d_halo_scratch (optional, 4 * n doubles, 32-byte
+ * aligned): when given, the per-halo constants of the profile are formed once per halo by a small setup
+ * kernel instead of once per (halo, node) thread.                                               */
 int ap_los_nodes(int kind, int64_t n, const double* d_p0, const double* d_p1, const double* d_p2, int32_t n_samples,
-                 const double* d_nodes, const int32_t* d_n_nodes, double* d_values, void* stream);
+                 const double* d_nodes, const int32_t* d_n_nodes, double* d_values, double* d_halo_scratch,
+                 void* stream);
 
 /* Diagnostic: Battaglia16.tau_2D at arbitrary (R, halo) pairs with QUADPACK's abserr and neval
  * (scipy.integrate.quad full_output; lib/utils.py:448).  d_abserr / d_neval may be NULL.       */

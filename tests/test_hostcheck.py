@@ -422,3 +422,4 @@ def test_ang2pix_pix2ang_bit_exact(hc, nside):
     back = np.empty(allp.size, dtype=np.int64)
     hc.hc_ang2pix(nside, allp.size, _p(th), _p(ph), _p(back))
     assert np.array_equal(back, allp)
+
