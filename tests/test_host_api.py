@@ -18,7 +18,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/astropaint_b200.h but not exported"
     assert declared == set(_capi.SIGNATURES), "ctypes SIGNATURES out of sync with the header"
-    assert _capi.lib().ap_version() == 100
+    assert _capi.lib().ap_version() == 200
 
 
 def test_no_cpu_fallback_product_path_fails_loudly():
