@@ -38,6 +38,8 @@ SIGNATURES = {
                                      c_ptr, c_ptr, c_ptr]),
     "ap_paint_los_items_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                          c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_disc_near_ties": (C.c_int, [c_i64, C.POINTER(ApHalos), c_dbl, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "ap_query_disc_host": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_i64]),
     "ap_disc_pixels": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_scatter_add": (C.c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_paint_profile": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), C.POINTER(c_ptr), C.POINTER(c_i32),
@@ -64,6 +66,7 @@ SIGNATURES = {
     "ap_ud_grade": (C.c_int, [c_i64, c_ptr, c_i64, C.c_int, c_dbl, C.c_int, c_ptr, c_ptr]),
     "ap_ang2pix": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ap_pix2ang": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_spray_table_host": (C.c_int, [C.c_int, c_i64, c_i64] + [c_ptr] * 11 + [c_i32, c_i32, c_ptr, C.POINTER(C.c_uint64)]),
     "ap_host_register": (C.c_int, [c_ptr, C.c_uint64]),
     "ap_host_unregister": (C.c_int, [c_ptr]),
     "ap_copy_d2h_async": (C.c_int, [c_ptr, c_ptr, C.c_uint64, c_ptr]),

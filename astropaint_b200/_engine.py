@@ -334,6 +334,44 @@ def disc_count(halos, nside, inclusive=False, want_range=False, want_rings=False
     return n_pix, n_rings, rmin, rmax
 
 
+def disc_tie_audit(halos, nside, tol=1.0e-9):
+    """Near-tie recheck of the disc query.  The device lists the halos that have a span boundary (or a
+    ring-range decision) within `tol` pixels of an integer -- the only place where CUDA's libm and the CPU's can
+    disagree on a pixel set; the host recomputes exactly those discs with its own libm (ap_query_disc_host) and the
+    pixel count and pixel-id sum of both are compared.  Returns {"n_halos", "n_flagged", "n_flips", "flagged",
+    "flips", "min_margin"}: `flips` are positions (within `halos`) whose device pixel set differs from the host's."""
+    L = _capi.lib()
+    dev = halos.device
+    n = halos.n
+    n_flag = torch.zeros(1, dtype=torch.int64, device=dev)
+    flagged = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    margin = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    s = halos.struct()
+    check(L.ap_disc_near_ties(nside, C.byref(s), float(tol), ptr(n_flag), ptr(flagged), n, ptr(margin), stream_ptr()))
+    k = int(n_flag.item())
+    idx = torch.sort(flagged[:k]).values
+    out = {"n_halos": n, "n_flagged": k, "n_flips": 0, "flagged": idx.cpu().numpy(), "flips": np.empty(0, dtype=np.int64),
+           "min_margin": float(margin[:n].min().item()) if n else float("inf")}
+    if k == 0:
+        return out
+    sub = halos.view(0, n)
+    sub.cols = {c: v.index_select(0, idx) for c, v in halos.cols.items()}
+    sub.n = sub._n_all = k
+    n_pix, _, _, _ = disc_count(sub, nside)
+    off, pix, _, _ = disc_pixels(sub, nside, n_pix)
+    seg = torch.repeat_interleave(torch.arange(k, device=dev), n_pix)
+    d_sum = torch.zeros(k, dtype=torch.int64, device=dev).index_add_(0, seg, pix)
+    host = {c: np.ascontiguousarray(sub.cols[c].cpu().numpy()) for c in ("x", "y", "z", "__radius__")}
+    h_count = np.empty(k, dtype=np.int64)
+    h_sum = np.empty(k, dtype=np.int64)
+    check(L.ap_query_disc_host(nside, k, ptr(host["x"]), ptr(host["y"]), ptr(host["z"]), ptr(host["__radius__"]),
+                               L.ap_disc_mode(-1), ptr(h_count), ptr(h_sum), None, 0))
+    bad = (n_pix.cpu().numpy() != h_count) | (d_sum.cpu().numpy() != h_sum)
+    out["n_flips"] = int(bad.sum())
+    out["flips"] = out["flagged"][bad]
+    return out
+
+
 def disc_pixels(halos, nside, n_pix, lo=0, hi=None, want_R=False, want_vec=False):
     """Flat pixel list of halos [lo, hi): returns (offsets[int64, hi-lo+1], pix, R or None, R_vec or None)."""
     L = _capi.lib()

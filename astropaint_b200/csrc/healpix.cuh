@@ -264,6 +264,35 @@ AP_HD RingSpan ring_span_t(const Hpx& h, const DiscHeader& d, int64_t iz) {
   return s;
 }
 
+// Near-tie audit of the exclusive query: how close the two floor() arguments of ring iz come to an integer
+// (in pixels).  A span boundary can differ between two libm implementations (CUDA's atan2 / cos vs glibc's, <= 2 ulp
+// apart) only when this margin is of the order of 1e-11; ap_disc_near_ties lists the halos below a tolerance so that
+// the host can recompute exactly those with its own libm.  +inf for rings the disc does not cross.
+// distance of ring_above()'s truncated argument from the next integer boundary (the ring range irmin / irmax)
+AP_HD double ring_above_margin(const Hpx& h, double z) {
+  const double az = fabs(z);
+  const double a = (az <= kTwoThird) ? AP_MUL((double)h.nside, AP_SUB(2.0, AP_MUL(1.5, z)))
+                                     : AP_MUL((double)h.nside, sqrt(AP_MUL(3.0, AP_SUB(1.0, az))));
+  return fmin(fabs(a - rint(a)), fabs(az - kTwoThird) * (double)h.nside);
+}
+
+AP_HD double ring_tie_margin(const Hpx& h, const DiscHeader& d, int64_t iz) {
+  if (iz < d.irmin || iz > d.irmax) return INFINITY;
+  int64_t startpix, nr;
+  bool shifted;
+  ring_info(h, iz, startpix, nr, shifted);
+  const double z = ring2z(h, iz);
+  const double x = AP_MUL(AP_SUB(d.cosr, AP_MUL(z, d.z0)), d.xa);
+  const double ysq = AP_SUB(AP_SUB(1.0, AP_MUL(z, z)), AP_MUL(x, x));
+  if (ysq <= 0) return fabs(ysq) * (double)nr;   // the ring grazes the disc: report how close to "no intersection"
+  const double dphi = atan2(sqrt(ysq), x);
+  if (!(dphi > 0)) return 0.0;
+  const double shift = shifted ? 0.5 : 0.0;
+  const double f = AP_MUL((double)nr, kInvTwoPi);
+  const double a = AP_SUB(AP_MUL(f, AP_SUB(d.phi, dphi)), shift), b = AP_SUB(AP_MUL(f, AP_ADD(d.phi, dphi)), shift);
+  return fmin(fabs(a - rint(a)), fabs(b - rint(b)));
+}
+
 AP_HD RingSpan ring_span(const Hpx& h, const DiscHeader& d, int64_t iz) {
   return h.incl_fct ? ring_span_t<true>(h, d, iz) : ring_span_t<false>(h, d, iz);
 }

@@ -246,6 +246,70 @@ extern "C" int ap_disc_pixels(int64_t nside, const ap_halos* halos, const int64_
 }
 
 // ------------------------------------------------------------------------------------------
+// Near-tie audit of the disc query: the device lists the halos with a span boundary within `tol`
+// pixels of an integer (or a ring-range decision within tol of flipping); the host recomputes their pixel sets with
+// its own libm (ap_query_disc_host) and the two are compared (astropaint_b200/_engine.py::disc_tie_audit).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) disc_near_ties_kernel(Hpx hpx, HalosDev H, double tol, unsigned long long* n_flagged,
+                                                             int64_t* flagged, int64_t cap, double* min_margin) {
+  int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H.n) return;
+  DiscHeader d = disc_header_t<false>(hpx, H.x[h], H.y[h], H.z[h], H.radius[h]);
+  double m = INFINITY;
+  {  // the ring range itself: ring_above(cos(theta -+ radius))
+    const double theta = atan2(sqrt(AP_ADD(AP_MUL(H.x[h], H.x[h]), AP_MUL(H.y[h], H.y[h]))), H.z[h]);
+    const double r = H.radius[h];
+    if (r < kPi) m = fmin(ring_above_margin(hpx, cos(AP_SUB(theta, r))), ring_above_margin(hpx, cos(AP_ADD(theta, r))));
+  }
+  for (int64_t iz = d.irmin; iz <= d.irmax; ++iz) m = fmin(m, ring_tie_margin(hpx, d, iz));
+  if (min_margin) min_margin[h] = m;
+  if (m < tol) {
+    unsigned long long at = atomicAdd(n_flagged, 1ull);
+    if ((int64_t)at < cap) flagged[at] = h;
+  }
+}
+
+extern "C" int ap_disc_near_ties(int64_t nside, const ap_halos* halos, double tol, unsigned long long* d_n_flagged,
+                                 int64_t* d_flagged, int64_t cap, double* d_min_margin, void* stream) {
+  if (check_nside(nside)) return 1;
+  if (check_halos(halos, false)) return 1;
+  if (!d_n_flagged || (cap > 0 && !d_flagged) || cap < 0) return fail("disc_near_ties: NULL pointer");
+  if (halos->n == 0) return 0;
+  disc_near_ties_kernel<<<(unsigned)((halos->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      make_hpx(nside), to_dev(halos), tol, d_n_flagged, d_flagged, cap, d_min_margin);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// hp.query_disc on the HOST (this library's ring arithmetic compiled for the CPU, glibc libm): per disc the pixel
+// count, the sum of the pixel ids and, optionally, the sorted pixel list of ONE disc.  All pointers are host pointers.
+extern "C" int ap_query_disc_host(int64_t nside, int64_t n, const double* h_x, const double* h_y, const double* h_z,
+                                  const double* h_radius, int inclusive_fact, int64_t* h_count, int64_t* h_pixsum,
+                                  int64_t* h_pix_first, int64_t pix_cap) {
+  if (check_nside(nside)) return 1;
+  if (n < 0 || inclusive_fact < 0) return fail("query_disc_host: bad arguments");
+  if (n > 0 && (!h_x || !h_y || !h_z || !h_radius)) return fail("query_disc_host: NULL pointer");
+  Hpx hp = make_hpx(nside);
+  hpx_set_inclusive(hp, inclusive_fact);
+  for (int64_t i = 0; i < n; ++i) {
+    DiscHeader d = disc_header(hp, h_x[i], h_y[i], h_z[i], h_radius[i]);
+    int64_t c = 0, sum = 0;
+    for (int64_t iz = d.ir_first; iz <= d.ir_last; ++iz) {
+      RingSpan sp = ring_span(hp, d, iz);
+      for (int32_t j = 0; j < sp.len; ++j) {
+        const int64_t p = span_pixel_sorted(sp, j);
+        if (i == 0 && h_pix_first && c + j < pix_cap) h_pix_first[c + j] = p;
+        sum += p;
+      }
+      c += sp.len > 0 ? sp.len : 0;
+    }
+    if (h_count) h_count[i] = c;
+    if (h_pixsum) h_pixsum[i] = sum;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // Pixel <-> angle maps of the RING scheme for the centre generators (hp.ang2pix / hp.pix2ang:
 // paint_bucket.py:996, 1085, 1183, 1199, 1238).  Streaming kernels: 16 B in + 8 B out per element.
 // ------------------------------------------------------------------------------------------

@@ -368,3 +368,105 @@ extern "C" int ap_paint_los_items_f32(int kind, int64_t nside, const ap_halos* h
   return paint_los_items_impl(kind, nside, halos, d_p0, d_p1, d_p2, d_scale, d_n_items, item_cap, d_items, d_map, true,
                               d_n_painted, stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry for the tabulated templates (@interpolate(@LOS_integrate(profile_3D))): the whole K1 -> nodes ->
+// QUADPACK -> spline -> K3 -> bypass pipeline of Painter.spray for Battaglia16.tau_2D_interp / kSZ_T / ne_2D and
+// NFW.rho_2D_interp, host pointers in and out (the table counterpart of ap_spray_host)
+// ------------------------------------------------------------------------------------------
+extern "C" int ap_spray_table_host(int kind, int64_t nside, int64_t n, const double* h_x, const double* h_y,
+                                   const double* h_z, const double* h_radius, const double* h_theta, const double* h_phi,
+                                   const double* h_D_a, const double* h_p0, const double* h_p1, const double* h_p2,
+                                   const double* h_scale, int32_t n_samples, int32_t method, double* h_map,
+                                   uint64_t* h_n_painted) {
+  if (check_nside(nside)) return 1;
+  if (n < 0) return fail("n < 0");
+  if (kind < 0 || kind > LOS_NFW_RHO) return fail("unknown LOS integrand kind");
+  if (n_samples < 4 || n_samples > kMaxNodes) return fail("n_samples must be in [4, 32]");
+  if (method != 0 && method != 1) return fail("method must be 0 (linspace) or 1 (logspace)");
+  if (!h_map) return fail("h_map == NULL");
+  const int64_t npix = 12 * nside * nside;
+  const double* cols[11] = {h_x, h_y, h_z, h_radius, h_theta, h_phi, h_D_a, h_p0, h_p1, h_p2, h_scale};
+  const int n_required = (kind == LOS_NFW_RHO) ? 9 : 10;
+  for (int i = 0; i < n_required && n > 0; ++i)
+    if (!cols[i]) return fail("spray_table_host: NULL halo column");
+  const int64_t nn = n > 0 ? n : 1, ns = n_samples;
+  // one device allocation carved into 32-byte aligned pieces
+  struct Piece { void** ptr; size_t bytes; };
+  double *d_cols[11] = {0}, *d_map = nullptr, *d_rmin = nullptr, *d_rmax = nullptr, *d_nodes = nullptr, *d_values = nullptr,
+         *d_coef = nullptr, *d_ctx = nullptr;
+  int64_t *d_n_pix = nullptr, *d_items = nullptr;
+  int32_t* d_n_nodes = nullptr;
+  unsigned long long* d_cnt = nullptr;  // [0] painted pairs, [1] bypass items
+  const int64_t item_cap = nn * (ns - 1);
+  Piece pieces[] = {{(void**)&d_map, sizeof(double) * (size_t)npix}, {(void**)&d_rmin, 8 * (size_t)nn},
+                    {(void**)&d_rmax, 8 * (size_t)nn}, {(void**)&d_nodes, 8 * (size_t)(nn * ns)},
+                    {(void**)&d_values, 8 * (size_t)(nn * ns)}, {(void**)&d_coef, 8 * (size_t)(nn * (ns - 1) * 4)},
+                    {(void**)&d_ctx, 32 * (size_t)nn}, {(void**)&d_n_pix, 8 * (size_t)nn},
+                    {(void**)&d_items, 8 * (size_t)item_cap}, {(void**)&d_n_nodes, 4 * (size_t)nn},
+                    {(void**)&d_cnt, 16}};
+  size_t total = 0;
+  for (auto& p : pieces) total += (p.bytes + 255) & ~(size_t)255;
+  for (int i = 0; i < 11; ++i) total += (8 * (size_t)nn + 255) & ~(size_t)255;
+  char* base = nullptr;
+  cudaStream_t st = nullptr;
+  auto cleanup = [&]() {
+    if (base) cudaFree(base);
+    if (st) cudaStreamDestroy(st);
+  };
+#define AP_TRY(call)                                                     \
+  do {                                                                   \
+    cudaError_t e_ = (call);                                             \
+    if (e_ != cudaSuccess) {                                             \
+      cleanup();                                                         \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    }                                                                    \
+  } while (0)
+#define AP_RC(call)        \
+  do {                     \
+    if ((call) != 0) {     \
+      cleanup();           \
+      return 1;            \
+    }                      \
+  } while (0)
+  AP_TRY(cudaStreamCreate(&st));
+  AP_TRY(cudaMalloc(&base, total));
+  size_t off = 0;
+  for (auto& p : pieces) {
+    *p.ptr = base + off;
+    off += (p.bytes + 255) & ~(size_t)255;
+  }
+  for (int i = 0; i < 11; ++i) {
+    d_cols[i] = reinterpret_cast<double*>(base + off);
+    off += (8 * (size_t)nn + 255) & ~(size_t)255;
+    if (cols[i] && n > 0) AP_TRY(cudaMemcpyAsync(d_cols[i], cols[i], 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+  }
+  AP_TRY(cudaMemcpyAsync(d_map, h_map, sizeof(double) * (size_t)npix, cudaMemcpyHostToDevice, st));
+  AP_TRY(cudaMemsetAsync(d_cnt, 0, 16, st));
+  if (n > 0) {
+    ap_halos H;
+    H.n = n;
+    H.d_x = d_cols[0]; H.d_y = d_cols[1]; H.d_z = d_cols[2]; H.d_radius = d_cols[3];
+    H.d_theta = d_cols[4]; H.d_phi = d_cols[5]; H.d_D_a = d_cols[6];
+    const double* p2 = h_p2 ? d_cols[9] : nullptr;
+    const double* sc = h_scale ? d_cols[10] : nullptr;
+    AP_RC(ap_disc_count_items(nside, &H, d_n_pix, d_rmin, d_rmax, n_samples, d_items, item_cap, d_cnt + 1, st));
+    AP_RC(ap_table_nodes(n, d_n_pix, d_rmin, d_rmax, n_samples, method, d_nodes, d_n_nodes, st));
+    AP_RC(ap_los_nodes(kind, n, d_cols[7], d_cols[8], p2, n_samples, d_nodes, d_n_nodes, d_values, d_ctx, st));
+    if (method == 0)
+      AP_RC(ap_spline_build_uniform(n, n_samples, d_nodes, d_values, d_n_nodes, d_coef, st));
+    else
+      AP_RC(ap_spline_build(n, n_samples, d_nodes, d_values, d_n_nodes, d_coef, st));
+    AP_RC(ap_paint_table(nside, &H, n_samples, method == 0, d_nodes, d_coef, d_n_nodes, sc, d_map, d_cnt, st));
+    AP_RC(ap_paint_los_items(kind, nside, &H, d_cols[7], d_cols[8], p2, sc, d_cnt + 1, item_cap, d_items, d_map, d_cnt, st));
+  }
+  AP_TRY(cudaMemcpyAsync(h_map, d_map, sizeof(double) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+  unsigned long long cnt = 0;
+  AP_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  AP_TRY(cudaStreamSynchronize(st));
+  if (h_n_painted) *h_n_painted = cnt;
+  cleanup();
+  return 0;
+#undef AP_TRY
+#undef AP_RC
+}

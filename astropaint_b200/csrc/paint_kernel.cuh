@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
   const int32_t T = sm.ring_off[G];
   unsigned long long painted = 0;
 
-  for (int32_t base = 0; base < T; base += kPaintThreads) {
+  // gridDim.y blocks share the halos of blockIdx.x: block y takes every gridDim.y-th chunk of 256 ring items, so a
+  // catalog of few, sky-sized discs (BASELINE config 1) is not serialised on the block that owns the largest disc
+  for (int32_t base = (int32_t)blockIdx.y * kPaintThreads; base < T; base += kPaintThreads * (int32_t)gridDim.y) {
     // P_TABLE: the spline coefficients of the halos this chunk touches are one contiguous run in HBM;
     // start streaming the first kStageHalos of them now (coalesced), park them in shared memory after
     // phase 1 so that phase 2 never waits on a dependent global load
@@ -384,7 +386,8 @@ static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& p
   memset(&st, 0, sizeof(st));
   if (stats) st = *stats;
   const Hpx hpx = disc_hpx(nside);
-  const unsigned nb = (unsigned)blocks;
+  // few blocks (small catalog): split each block's ring items over up to 8 blocks (K1 keeps its per-block sums)
+  const dim3 nb((unsigned)blocks, (P != P_STATS && blocks <= 4096) ? 8u : 1u);
   cudaStream_t cs = (cudaStream_t)stream;
   if (f32 && P != P_STATS) {
     if (hpx.incl_fct)

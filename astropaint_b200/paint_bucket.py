@@ -662,6 +662,13 @@ class Canvas:
             for _, pix, _, _ in self._gen(halo_list):
                 yield pix
 
+        def gen_pixel_ang(self, halo_list="All"):
+            """(theta, phi) of the pixels of each halo's disc: hp.pix2ang(nside, pixel_index)
+            (paint_bucket.py:1231-1238)"""
+            for pix in self.gen_pixel_index(halo_list):
+                theta, phi = eng.pix2ang(self.nside, pix) if len(pix) else (np.empty(0), np.empty(0))
+                yield (theta, phi)
+
         def gen_cent2pix_rad(self, halo_list="All"):
             for halo, _, R, _ in self._gen(halo_list, want_R=True):
                 yield R / self.center_D_a[halo]

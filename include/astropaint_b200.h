@@ -117,6 +117,19 @@ int ap_disc_count_items(int64_t nside, const ap_halos* halos, int64_t* d_n_pix, 
                         int32_t n_samples, int64_t* d_items, int64_t item_cap, unsigned long long* d_item_count,
                         void* stream);
 
+/* Near-tie audit of the disc query (hp.query_disc, paint_bucket.py:1222).  The span boundaries are floor() of
+ * expressions holding atan2 / cos, where CUDA's libm and the CPU's may differ in the last bit: a boundary can flip
+ * only if its floor argument lies within ~1e-11 of an integer.  ap_disc_near_ties appends every halo that has a
+ * boundary within `tol` pixels of an integer to d_flagged (their number in *d_n_flagged, which the caller zeroes;
+ * d_min_margin[n], optional, receives each halo's smallest margin); ap_query_disc_host recomputes discs on the HOST
+ * with the CPU's libm (count and sum of pixel ids per disc; the pixel list of the first disc, optional) so the
+ * caller can compare.  inclusive_fact as in ap_disc_mode.                                                    */
+int ap_disc_near_ties(int64_t nside, const ap_halos* halos, double tol, unsigned long long* d_n_flagged,
+                      int64_t* d_flagged, int64_t cap, double* d_min_margin, void* stream);
+int ap_query_disc_host(int64_t nside, int64_t n, const double* h_x, const double* h_y, const double* h_z,
+                       const double* h_radius, int inclusive_fact, int64_t* h_count, int64_t* h_pixsum,
+                       int64_t* h_pix_first, int64_t pix_cap);
+
 /* Flat (halo, pixel) work list: pixel ids of halo h in ascending order at
  * d_pix[d_pix_off[h] .. d_pix_off[h+1]) — identical to np.concatenate of gen_pixel_index().
  * Optional outputs (NULL to skip): d_R[total] = gen_cent2pix_mpc (:1266-1273),
@@ -222,6 +235,16 @@ int ap_spray_host(int profile, int64_t nside, int64_t n, const double* h_x, cons
                   const double* h_z, const double* h_radius, const double* h_theta, const double* h_phi,
                   const double* h_D_a, const double* const* h_params, const int32_t* h_strides,
                   int32_t n_params, double* h_map, uint64_t* h_n_painted);
+
+/* The same for the tabulated templates -- @interpolate(@LOS_integrate(profile_3D)): Battaglia16.tau_2D_interp / kSZ_T
+ * (kind AP_LOS_B16_TAU, n_samples 15, method 0), Battaglia16.ne_2D (AP_LOS_B16_NE, 20, 0), NFW.rho_2D_interp
+ * (AP_LOS_NFW_RHO, 20, method 1 = logspace) -- i.e. Painter.spray of BASELINE configs 2 and 3 with HOST buffers in and
+ * out: K1, nodes, QUADPACK, spline, K3 and the `len(R) < n_samples` bypass.  h_p0..h_p2: the 3-D profile's per-halo
+ * arguments (h_p2 NULL for NFW); h_scale (optional): per-halo multiplier (kSZ: -v_r / c * T_cmb * (1 + z)).      */
+int ap_spray_table_host(int kind, int64_t nside, int64_t n, const double* h_x, const double* h_y, const double* h_z,
+                        const double* h_radius, const double* h_theta, const double* h_phi, const double* h_D_a,
+                        const double* h_p0, const double* h_p1, const double* h_p2, const double* h_scale,
+                        int32_t n_samples, int32_t method, double* h_map, uint64_t* h_n_painted);
 
 /* Host side of the map (Canvas.pixels is a host ndarray in the reference, paint_bucket.py:798, 858-869): the
  * ranks of one node write their bands into ONE host array.  ap_host_register page-locks a caller-owned host

@@ -338,3 +338,54 @@ def test_oracle_reproduces_healpy_docstring_examples():
     assert abs(np.sqrt(4 * np.pi / H.nside2npix(128)) * 10800 / np.pi - K.NSIDE2RESOL_128_ARCMIN) < 1e-13
     assert abs(4 * np.pi / H.nside2npix(128) - K.NSIDE2PIXAREA_128) < 1e-19
     assert H.ud_grade(np.arange(48.), 1).tolist() == K.UD_GRADE_48_TO_1
+
+
+def _disc_agreement_job(job):
+    """one chunk of the two-statement comparison (run in a worker process)"""
+    from oracle.query_disc_ineq import DiscByInequality, compare
+    nside, seed, n, special = job
+    rng = np.random.default_rng(seed)
+    hp = H.HealpixRing(nside)
+    ineq = DiscByInequality(nside)
+    mu = rng.uniform(-1, 1, n)
+    ph = rng.uniform(0, 2 * np.pi, n)
+    # radii: log-uniform 0.3 .. 70 arcmin like the bench catalog
+    rad = np.deg2rad(10 ** rng.uniform(np.log10(0.3), np.log10(70), n) / 60.0)
+    if special:      # poles, the polar-cap / equatorial-belt boundary, phi = 0 wrap; sky-sized and sub-pixel discs
+        mu[:40] = np.repeat([1.0, -1.0, 1 - 1e-9, -1 + 1e-9, 2.0 / 3.0, -2.0 / 3.0, 0.0, 1e-12], 5)
+        ph[:8] = [0.0, np.pi / 2, np.pi, 1.5 * np.pi, 1e-15, 2 * np.pi - 1e-15, np.pi / 4, 0.75 * np.pi]
+        rad[40:60] = rng.uniform(0.2, 3.2, 20) if nside == 512 else rng.uniform(20, 200, 20) / nside
+        rad[60:80] = rng.uniform(0, 1.5 / nside, 20)
+    scale = rng.uniform(10, 5000, n)            # the reference passes un-normalised Mpc vectors
+    st = np.sqrt(np.clip(1 - mu * mu, 0, None))
+    log = []
+    for i in range(n):
+        vec = (scale[i] * st[i] * np.cos(ph[i]), scale[i] * st[i] * np.sin(ph[i]), scale[i] * mu[i])
+        only_a, only_b, margins = compare(hp, ineq, vec, float(rad[i]))
+        for tag, arr in (("floor-form only", only_a), ("inequality only", only_b)):
+            for p in arr:
+                log.append((nside, seed, i, tag, int(p), margins.get(int(p))))
+    return n, log
+
+
+def test_two_independent_statements_of_query_disc_agree():
+    """the floor-form restatement of healpix's query_disc (oracle/healpix_np.py)
+    against the inequality form cos(angdist(pixel centre, c)) > cos r with integer ring / pixel enumeration
+    (oracle/query_disc_ineq.py) on 1e5 random discs at nside 512 .. 8192 (Websky-shaped radii plus polar, sky-sized and
+    sub-pixel discs).  Any disagreement must be a pixel whose centre lies on the disc's edge to rounding error, and
+    every one is logged with its distance from the edge."""
+    import multiprocessing as mp
+    jobs = [(nside, 1000 * nside + k, 3125, k == 0) for nside in (512, 2048, 4096, 8192) for k in range(8)]
+    with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        results = pool.map(_disc_agreement_job, jobs)
+    n_discs = sum(r[0] for r in results)
+    log = [row for r in results for row in r[1]]
+    assert n_discs == 100000
+    if log:
+        print(f"\n{len(log)} disagreeing pixels over {n_discs} discs:")
+        for row in log[:50]:
+            print("  nside %d seed %d disc %d %s pixel %d  cos(dist) - cos(r) = %s" % row)
+    # a disagreement is only legitimate ON the edge: |cos(dist) - cos(r)| at rounding level
+    for nside, seed, i, tag, p, margin in log:
+        assert margin is not None and abs(margin) < 1e-13, (nside, seed, i, tag, p, margin)
+    assert len(log) <= 5
