@@ -132,6 +132,37 @@ def test_C3_pixel_sets_on_the_gate_subsample_of_the_1e7_catalog(websky_1e7):
     print(f"C3: {n_checked} discs, {n_pixels} pixels, {n_polar} polar discs, largest {n_pix.max()}, smallest {n_pix.min()}")
 
 
+def test_polar_discs_at_nside_8192():
+    """The Websky-shaped catalogs above hold no pole-containing disc (a 1.5' disc on a uniform sphere), so the
+    polar branches of the query (whole rings above irmin / below irmax, the caps' 4 i pixels per ring) are gated
+    here at the bench resolution: 300 halos moved to within their own disc radius of either pole."""
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    from astropaint_b200.profiles import NFW
+    from oracle import reference_loop as ref, profiles_np as oprof
+    df = synthetic.websky_like(300, seed=77, m_min=2e13)
+    cat0 = ap.Catalog(df.copy())
+    rng = np.random.default_rng(77)
+    radius = 5 * np.deg2rad(cat0.data["R_ang_200c"].values / 60.0)
+    theta = rng.uniform(0, 1.5, 300) * radius                       # two thirds of them contain the pole
+    theta[:4] = [0.0, 1e-12, radius[2], 0.5 * radius[3]]
+    theta[150:] = np.pi - theta[150:]
+    phi = rng.uniform(0, 2 * np.pi, 300)
+    D = np.sqrt(df.x ** 2 + df.y ** 2 + df.z ** 2).values
+    df["x"], df["y"], df["z"] = D * np.sin(theta) * np.cos(phi), D * np.sin(theta) * np.sin(phi), D * np.cos(theta)
+    cat = ap.Catalog(df)
+    nside = 8192
+    n_checked, n_pixels = _check_pixel_sets(cat, nside, 5, np.arange(300))
+    canvas = ap.Canvas(cat, nside, R_times=5)
+    p = ap.Painter(NFW.kSZ_T)
+    p.spray(canvas)
+    want = np.zeros(12 * nside * nside)
+    pairs = ref.spray(want, cat.data, nside, oprof.nfw_kSZ_T, R_times=5)
+    assert int(p.last_spray["d_count"].item()) == pairs == n_pixels
+    assert want[:4].any() and want[-4:].any()                        # the polar pixels themselves are painted
+    map_close(canvas.pixels, want, 1e-6)
+
+
 MAP_CASES = [("C2", 4096, "Battaglia16.tau_2D_interp", "b16_tau_2D_interp"),
              ("C3", 8192, "Battaglia16.kSZ_T", "b16_kSZ_T"),
              ("C4", 8192, "NFW.BG", "nfw_BG")]
