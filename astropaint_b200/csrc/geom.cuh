@@ -91,14 +91,19 @@ AP_HD double sin_quarter(double x) {
   return x + x * (x2 * p);
 }
 
+// sin^2(d / 2) for |d / 2| < 1/8: 5-term series (the branch of sin2_half every disc that is not polar or sky-sized
+// takes; the painter's straight-line pixel loop calls it directly when a whole chunk of ring items is known to qualify)
+AP_HD double sin2_half_small(double d) {
+  const double x = 0.5 * d;
+  const double x2 = x * x;  // next term x^10 / 39916800 < 2.4e-17 relative
+  const double s = x * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0 + x2 * (-1.0 / 5040.0 + x2 * (1.0 / 362880.0)))));
+  return s * s;
+}
+
 // sin^2(d / 2); small arguments (every disc that is not polar or sky-sized) take a 5-term series
 AP_HD double sin2_half(double d) {
   double x = 0.5 * d, s;
-  if (fabs(x) < 0.125) {
-    double x2 = x * x;  // next term x^10 / 39916800 < 2.4e-17 relative
-    s = x * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0 + x2 * (-1.0 / 5040.0 + x2 * (1.0 / 362880.0)))));
-    return s * s;
-  }
+  if (fabs(x) < 0.125) return sin2_half_small(d);
   // sin^2 has period pi: fold x into [-pi/2, pi/2], then sin^2(x) = 1 - sin^2(pi/2 - |x|) above pi/4
   x = x - kPi * rint(x * (1.0 / kPi));
   const double ax = fabs(x);
@@ -131,14 +136,19 @@ AP_HD double two_asin_sqrt(double u) {
   return kPi - 4.0 * asin_half(w * fm_rsqrt(w));
 }
 
+// separation [rad] for hav < 1e-4 (theta < 0.02 rad), branch-free: the series branch of sep_from_hav with its
+// zero guard as a select
+AP_HD double sep_from_hav_small(double hav) {
+  const bool pos = hav > 1.0e-290;       // hav is 0 or >= ~1e-35 by construction; keeps fm_rsqrt on normal numbers
+  const double sq = hav * fm_rsqrt(pos ? hav : 1.0);
+  // asin(s)/s = 1 + h/6 + 3h^2/40 + 15h^3/336 + 105h^4/3456 + ..., h = s^2 (next term < 3e-22)
+  const double v = 2.0 * sq * (1.0 + hav * (1.0 / 6.0 + hav * (3.0 / 40.0 + hav * (15.0 / 336.0 + hav * (105.0 / 3456.0)))));
+  return pos ? v : 0.0;
+}
+
 // separation [rad] from its haversine: theta = 2 asin(sqrt(hav)); series below hav = 1e-4
 AP_HD double sep_from_hav(double hav) {
-  if (hav < 1.0e-4) {
-    if (!(hav > 1.0e-290)) return 0.0;   // hav is 0 or >= ~1e-35 by construction; keeps fm_rsqrt on normal numbers
-    double sq = hav * fm_rsqrt(hav);
-    // asin(s)/s = 1 + h/6 + 3h^2/40 + 15h^3/336 + 105h^4/3456 + ..., h = s^2 (next term < 3e-22)
-    return 2.0 * sq * (1.0 + hav * (1.0 / 6.0 + hav * (3.0 / 40.0 + hav * (15.0 / 336.0 + hav * (105.0 / 3456.0)))));
-  }
+  if (hav < 1.0e-4) return sep_from_hav_small(hav);
   if (hav <= 0.5) return two_asin_sqrt(hav);
   double co = 1.0 - hav;
   if (!(co > 1.0e-290)) return kPi;

@@ -91,8 +91,16 @@ struct PaintShared {
 // the span lengths gives the flat pixel numbering; phase 2 walks the pixels with consecutive lanes
 // on consecutive pixels of a ring (sector-coalesced fp64 RED traffic), evaluates separation,
 // template and accumulates.  No work list ever touches HBM.
+// Four resident blocks per SM (64 registers) for every template whose pixel loop is a few dozen fp64 operations:
+// measured on the bench catalog, P_TABLE runs 7.3 ms per 1e7 halos at 64 registers, 8.2 ms at 80 and 10.1 ms at the
+// 103 ptxas takes when left alone (the loop is issue-bound and needs the warps).  The per-pixel quadrature templates
+// get two blocks (128 registers): they are bound by the QUADPACK rule, not by this kernel's bookkeeping.
+template <int P>
+constexpr int paint_min_blocks() {
+  return (P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) ? 2 : 4;
+}
 template <int P, class MapT, bool INCL>
-__global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
+__global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
                                                                StatsArgs st, int halos_per_block,
                                                                MapT* __restrict__ map,
                                                                unsigned long long* n_painted) {
@@ -151,15 +159,29 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    int32_t run = 0;
-    for (int i = 0; i < G; ++i) {
-      sm.ring_off[i] = run;
-      int32_t n = sm.hdr[i].ir_last - sm.hdr[i].ir_first + 1;
-      run += n > 0 ? n : 0;
+  // exclusive scan of the halos' ring counts (G <= 112: four warps): warp scans, then the warp totals
+  int32_t ring_incl = 0;
+  if (tid < 128) {
+    int32_t n = 0;
+    if (tid < G) {
+      n = sm.hdr[tid].ir_last - sm.hdr[tid].ir_first + 1;
+      n = n > 0 ? n : 0;
     }
-    sm.ring_off[G] = run;
+    ring_incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, ring_incl, o);
+      if (lane >= o) ring_incl += t;
+    }
+    if (lane == 31) sm.warp_sum[warp] = ring_incl;
   }
+  __syncthreads();
+  if (tid < G) {
+    int32_t add = 0;
+    for (int w = 0; w < warp; ++w) add += sm.warp_sum[w];
+    sm.ring_off[tid + 1] = ring_incl + add;
+  }
+  if (tid == 0) sm.ring_off[0] = 0;
   __syncthreads();
   const int32_t T = sm.ring_off[G];
   unsigned long long painted = 0;
@@ -194,6 +216,10 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
     // phase 1: one ring item per thread
     int32_t it = base + tid;
     int32_t len = 0;
+    // "small" ring item: every pixel has |d / 2| < 1/8 and a haversine below 1e-4 (theta < 0.02 rad) and, for the
+    // tabulated template, its halo's spline sits in the staged shared-memory copy.  When ALL items of the chunk
+    // are small, phase 2 runs a straight-line pixel loop (no series / table-path branches).
+    bool small_ok = !VEC && !STATS;
     if (it < T) {
       int lo = 0, hi = G;  // largest hl with ring_off[hl] <= it
       while (hi - lo > 1) {
@@ -222,6 +248,9 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
           r.startpix = s.startpix; r.nr = s.nr; r.ip_lo = s.ip_lo; r.hl = lo;
           r.A = g.A; r.B = g.B; r.phi_step = g.phi_step; r.d0 = g.d0;
           if (VEC) { sm.itemv[tid].phi0 = g.phi0; sm.itemv[tid].z = g.z; sm.itemv[tid].sth = g.sth; }
+          const double dmax = fmax(fabs(g.d0), fabs(g.d0 + (double)(s.len - 1) * g.phi_step));
+          small_ok = small_ok && dmax < 0.25 && (g.A + g.B * (0.25 * dmax * dmax)) < 1.0e-4;   // sin^2(x) <= x^2
+          if (P == P_TABLE) small_ok = small_ok && do_stage && tab.uniform && (lo - stage_lo) < kStageHalos;
         }
       }
       if (STATS && len > 0) atomicAdd(&sm.cnt[lo], (unsigned long long)len);
@@ -257,9 +286,10 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
         }
       }
     }
-    __syncthreads();
+    const bool all_small = __syncthreads_and(small_ok ? 1 : 0) != 0;
     const int32_t total = sm.pix_off[kPaintThreads];
     painted += (tid == 0) ? (unsigned long long)total : 0ull;
+    const bool fastp = !VEC && all_small && total <= kPixMapMax;
 
     // phase 2: two pixels per thread per iteration (k and k + 256): independent dependency chains
     // (table loads, series) overlap, then both REDs are issued
@@ -329,11 +359,41 @@ __global__ void __launch_bounds__(kPaintThreads) paint_kernel(Hpx hpx, HalosDev 
       pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
       return val;
     };
+    // the same arithmetic with every data-dependent branch resolved for the whole chunk (small discs: the common case)
+    auto eval_small = [&](int32_t k, int64_t& pix) -> double {
+      const int lo = sm.pixmap[k];
+      const RingItem& r = sm.item[lo];
+      const int32_t j = k - sm.pix_off[lo];
+      const int hl = r.hl;
+      const double hav = r.A + r.B * sin2_half_small(r.d0 + (double)j * r.phi_step);
+      const double R = sm.cen_Da[hl] * sep_from_hav_small(hav);
+      double val;
+      if (P == P_TABLE) {
+        const int ns = tab.n_samples;
+        int i = (int)((R - sm.ctx[hl][1]) * sm.ctx[hl][2]);
+        i = i < 0 ? 0 : (i > ns - 2 ? ns - 2 : i);
+        const double t = R - (sm.ctx[hl][1] + (double)i * sm.ctx[hl][3]);
+        const double2* c2 = reinterpret_cast<const double2*>(sm.stage + ((hl - stage_lo) * (ns - 1) + i) * 4);
+        const double2 c01 = c2[0], c23 = c2[1];
+        val = (c01.x + t * (c01.y + t * (c23.x + t * c23.y))) * sm.ctx[hl][0];
+      } else {
+        val = profile_eval_R<P>(sm.ctx[hl], R);
+      }
+      const int32_t ip = r.ip_lo + j;
+      pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
+      return val;
+    };
     for (int32_t k = tid; k < total; k += 2 * kPaintThreads) {
       int64_t p0, p1 = 0;
       const bool two = (k + kPaintThreads < total);
-      double v0 = eval(k, p0);
-      double v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
+      double v0, v1;
+      if (fastp) {
+        v0 = eval_small(k, p0);
+        v1 = two ? eval_small(k + kPaintThreads, p1) : 0.0;
+      } else {
+        v0 = eval(k, p0);
+        v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
+      }
       if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) atomicAdd(&map[p0 - hpx.clip_pix0], (MapT)v0);
       if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) atomicAdd(&map[p1 - hpx.clip_pix0], (MapT)v1);
     }

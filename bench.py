@@ -457,6 +457,11 @@ def run_configs(dev, which, steps, warmup):
         return e0.elapsed_time(e1) / steps
 
     def spray_config(cat, nside, tmpl, bytes_per_halo, label):
+        """`ms` / `value`: CUDA events around Canvas.clean() + Painter.spray (zero-fill of the map, pinned H2D of the
+        catalog columns, every kernel).  `kernel_ms` / `roofline_frac`: the painting kernel(s) alone on resident
+        inputs (closed-form templates: ap_paint_profile; tabulated: the K1..bypass pipeline), against the HBM roofline
+        with SURVEY 8(d)'s algorithmic bytes."""
+        from astropaint_b200 import _engine as eng
         cat.pin_memory()
         canvas = ap.Canvas(cat, nside, R_times=R_TIMES)
         p = ap.Painter(tmpl)
@@ -467,11 +472,30 @@ def run_configs(dev, which, steps, warmup):
         ms = timed(one)
         pairs = int(p.last_spray["d_count"].item())
         alg = 16.0 * pairs + bytes_per_halo * cat.size
-        return canvas, {"workload": label, "halo_pixels": pairs, "ms": ms, "value": pairs / (ms / 1e3), "unit": UNIT,
-                        "path": p.last_spray["path"], "algorithmic_bytes": alg,
-                        "roofline_frac": alg / (ms / 1e3) / 1e9 / hbm_peak,
-                        "timed": "CUDA events around Canvas.clean() + Painter.spray (zero-fill of the map, pinned H2D of "
-                                 "the catalog columns and every kernel of the spray)"}
+        out = {"workload": label, "halo_pixels": pairs, "ms": ms, "value": pairs / (ms / 1e3), "unit": UNIT,
+               "path": p.last_spray["path"], "algorithmic_bytes": alg}
+        # the kernels alone
+        halos = eng.DeviceHalos(cat.data, R_TIMES, dev)
+        d_map = canvas._device_band()
+        info = getattr(tmpl, "_ap_device", None)
+        if info is not None:
+            cols = [halos.col(a) for a in info["args"]] + [torch.full((1,), float(v), dtype=torch.float64, device=dev)
+                                                           for v in info["kwonly"].values()]
+            kms = timed(lambda: eng.paint_profile(halos, nside, info["id"], cols, d_map))
+            out["kernel"] = f"paint_kernel<{tmpl.__name__}>"
+        else:
+            ti = tmpl._ap_device_table
+            targs = [halos.col(a) for a in ti["args"]]
+            tm = eng.Timers()
+            kms = timed(lambda: eng.table_chunk(halos, nside, ti["kind"], targs, None, ti["n_samples"], ti["sampling_method"],
+                                                d_map, None, tm))
+            ph = tm.phase_ms(scale=1.0 / (steps + warmup))
+            out["phase_ms"] = ph
+            out["kernel"] = "K1 + nodes + QUADPACK + spline + K3 + bypass (fp64-bound: see phase_ms)"
+        out["kernel_ms"] = kms
+        out["roofline_frac"] = alg / (kms / 1e3) / 1e9 / hbm_peak
+        del halos
+        return canvas, out
 
     cat6 = None
     if "C1" in which:
@@ -496,11 +520,17 @@ def run_configs(dev, which, steps, warmup):
             canvas.stack_cutouts(halo_list, lon_range=[-0.2, 0.2], lat_range=[-0.2, 0.2], xpix=200)
         ms = timed(stack)
         samples = 100_000 * 200 * 200
+        from astropaint_b200 import _engine as eng
+        d_map = canvas.pixels_device
+        d_lon = eng.to_device(cat6.data["lon"].values[halo_list], dev)
+        d_lat = eng.to_device(cat6.data["lat"].values[halo_list], dev)
+        kms = timed(lambda: eng.stack_cutouts(d_map, NSIDE, d_lon, d_lat, [-0.2, 0.2], [-0.2, 0.2], 200, 200))
         out["C5"] = {"workload": "stack_cutouts of 1e5 halos, 0.4 x 0.4 deg, 200 x 200, from the C4 map (nside 8192)",
                      "samples": samples, "ms": ms, "value": 1e5 / (ms / 1e3), "unit": "cutouts/s",
-                     "algorithmic_bytes": 8.0 * samples, "roofline_frac": 8.0 * samples / (ms / 1e3) / 1e9 / hbm_peak,
-                     "timed": "CUDA events around Canvas.stack_cutouts (H2D of lon/lat, fused project + gather + "
-                              "accumulate kernel, D2H of the 200 x 200 stack)"}
+                     "algorithmic_bytes": 8.0 * samples, "kernel": "cutout_kernel<STACK>", "kernel_ms": kms,
+                     "roofline_frac": 8.0 * samples / (kms / 1e3) / 1e9 / hbm_peak,
+                     "timed": "ms: CUDA events around Canvas.stack_cutouts (H2D of lon/lat, fused project + gather + "
+                              "accumulate kernel, D2H of the 200 x 200 stack); kernel_ms: the kernel alone"}
     return out
 
 
