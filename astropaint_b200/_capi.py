@@ -38,6 +38,9 @@ SIGNATURES = {
                                      c_ptr, c_ptr, c_ptr]),
     "ap_paint_los_items_f32": (C.c_int, [C.c_int, c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                          c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ap_emit_begin": (C.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i32]),
+    "ap_emit_end": (C.c_int, []),
+    "ap_segment_accumulate": (C.c_int, [c_i64, c_ptr, c_ptr, c_i32, c_i64, c_ptr, C.c_int, c_ptr]),
     "ap_disc_near_ties": (C.c_int, [c_i64, C.POINTER(ApHalos), c_dbl, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "ap_query_disc_host": (C.c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_i64]),
     "ap_disc_pixels": (C.c_int, [c_i64, C.POINTER(ApHalos), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -213,6 +213,44 @@ class band_clip:
         return False
 
 
+class emit_pairs:
+    """`with emit_pairs(n_max, labels, npix, device) as e:` -- deterministic accumulation.  Every painting launch of
+    this thread inside the block appends (pixel << shift | halo label, value) pairs instead of adding atomically
+    (ap_emit_begin); `e.accumulate(d_map, pix0)` afterwards sorts the keys and adds every pixel's values in label
+    order with plain stores (ap_segment_accumulate): the summation order of the reference's serial loop, bit-reproducible
+    from run to run."""
+
+    def __init__(self, n_max, labels, npix, device):
+        self.n_max = int(n_max)
+        pix_bits = max(1, int(npix - 1).bit_length())
+        self.shift = min(40, 63 - pix_bits)
+        self.labels = labels
+        self.keys = torch.empty(max(self.n_max, 1), dtype=torch.int64, device=device)
+        self.vals = torch.empty(max(self.n_max, 1), dtype=torch.float64, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def __enter__(self):
+        check(_capi.lib().ap_emit_begin(ptr(self.keys), ptr(self.vals), ptr(self.count), self.n_max, ptr(self.labels),
+                                        self.shift))
+        return self
+
+    def __exit__(self, *exc):
+        check(_capi.lib().ap_emit_end())
+        return False
+
+    def accumulate(self, d_map, pix0=0):
+        n = int(self.count.item())
+        if n > self.n_max:
+            raise RuntimeError(f"deterministic accumulation: {n} pairs painted but room for {self.n_max}")
+        if n == 0:
+            return 0
+        keys, perm = torch.sort(self.keys[:n])      # keys are unique (a halo paints a pixel once): any sort is deterministic
+        vals = self.vals[:n].index_select(0, perm)
+        check(_capi.lib().ap_segment_accumulate(n, ptr(keys), ptr(vals), self.shift, int(pix0), ptr(d_map),
+                                                int(d_map.dtype == torch.float32), stream_ptr()))
+        return n
+
+
 class Timers:
     """CUDA-event ticks on the launching stream; phase_ms() sums the time between consecutive ticks by name."""
 

@@ -36,6 +36,30 @@ static __device__ unsigned long long g_bounds_errors = 0ull;
 #else
 #define AP_BOUNDS_OK(cond) true
 #endif
+// One painted value: an fp64 (or fp32) RED into the rank's band of the map, or -- in deterministic mode -- an
+// append to the (key, value) list with one warp-aggregated slot allocation per converged group of lanes.
+#if defined(__CUDACC__)
+template <class MapT>
+__device__ __forceinline__ void accumulate(const Hpx& hpx, MapT* map, int64_t pix, double val, int64_t halo) {
+  if (hpx.emit_keys) {
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(hpx.emit_count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
+    if ((long long)slot < hpx.emit_cap) {
+      const unsigned long long label = (unsigned long long)(hpx.emit_labels ? hpx.emit_labels[halo] : halo);
+      hpx.emit_keys[slot] = ((unsigned long long)pix << hpx.emit_shift) | label;
+      hpx.emit_vals[slot] = val;
+    }
+  } else {
+    atomicAdd(&map[pix - hpx.clip_pix0], (MapT)val);
+  }
+}
+#endif
+
 #define AP_TU_BOUNDS_GETTER(name)                                                          \
   long long name() {                                                                       \
     unsigned long long v = 0;                                                              \

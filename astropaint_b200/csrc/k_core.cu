@@ -14,6 +14,11 @@
 //   patch_ops.cuh                 K6  apply_func library: spline prefilter + rotate, taper, weight, stack
 #include "internal.cuh"
 
+static unsigned stream_grid_n(int64_t n) {  // grid-stride launch: at most 148 SMs x 8 resident blocks of 256
+  int64_t b = (n + 255) / 256;
+  return (unsigned)(b < 148 * 8 ? (b < 1 ? 1 : b) : 148 * 8);
+}
+
 // ------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------
@@ -55,9 +60,41 @@ extern "C" int ap_band_clip(int64_t ring_lo, int64_t ring_hi) {
   g_clip_hi = ring_hi;
   return 0;
 }
+// Deterministic accumulation of the calling thread's next painting launches (ap_emit_begin .. ap_emit_end)
+struct EmitState {
+  unsigned long long* keys = nullptr;
+  double* vals = nullptr;
+  unsigned long long* count = nullptr;
+  long long cap = 0;
+  const long long* labels = nullptr;
+  int shift = 0;
+};
+static thread_local EmitState g_emit;
+extern "C" int ap_emit_begin(uint64_t* d_keys, double* d_vals, unsigned long long* d_count, int64_t cap,
+                             const int64_t* d_labels, int32_t shift) {
+  if (!d_keys || !d_vals || !d_count || cap < 0) return fail("emit_begin: NULL buffer");
+  if (shift < 1 || shift > 40) return fail("emit_begin: shift (bits kept for the halo label) must be in [1, 40]");
+  g_emit.keys = reinterpret_cast<unsigned long long*>(d_keys);
+  g_emit.vals = d_vals;
+  g_emit.count = d_count;
+  g_emit.cap = cap;
+  g_emit.labels = reinterpret_cast<const long long*>(d_labels);
+  g_emit.shift = shift;
+  return 0;
+}
+extern "C" int ap_emit_end(void) {
+  g_emit = EmitState();
+  return 0;
+}
 Hpx disc_hpx(int64_t nside) {
   Hpx h = make_hpx(nside);
   hpx_set_inclusive(h, g_incl_fact);
+  h.emit_keys = g_emit.keys;
+  h.emit_vals = g_emit.vals;
+  h.emit_count = g_emit.count;
+  h.emit_cap = g_emit.cap;
+  h.emit_labels = g_emit.labels;
+  h.emit_shift = g_emit.shift;
   if (g_clip_hi > 0) {
     const int64_t top = 4 * nside;
     h.clip_lo = (int32_t)(g_clip_lo < top ? g_clip_lo : top);
@@ -241,6 +278,39 @@ extern "C" int ap_disc_pixels(int64_t nside, const ap_halos* halos, const int64_
   int64_t blocks = (halos->n * 32 + threads - 1) / threads;
   disc_pixels_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(disc_hpx(nside), to_dev(halos), d_pix_off,
                                                                              d_pix, d_R, d_R_vec);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Deterministic accumulation, second half: the (pixel << shift | halo) keys arrive SORTED; the thread that finds the
+// first entry of a pixel adds that pixel's values to the map one after the other, in halo order -- the order the
+// reference's serial loop adds them in (np.add.at over halos 0, 1, 2, ...; paint_bucket.py:2380-2389).  Plain
+// loads and stores: every pixel has exactly one writer.
+// ------------------------------------------------------------------------------------------
+template <class MapT>
+__global__ void __launch_bounds__(256) segment_accumulate_kernel(int64_t n, const unsigned long long* __restrict__ keys,
+                                                                 const double* __restrict__ vals, int shift, int64_t pix0,
+                                                                 MapT* __restrict__ map) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long pix = keys[i] >> shift;
+    if (i > 0 && (keys[i - 1] >> shift) == pix) continue;   // not the first entry of its pixel
+    MapT acc = map[(int64_t)pix - pix0];
+    for (int64_t j = i; j < n && (keys[j] >> shift) == pix; ++j) acc += (MapT)vals[j];
+    map[(int64_t)pix - pix0] = acc;
+  }
+}
+
+extern "C" int ap_segment_accumulate(int64_t n, const uint64_t* d_keys_sorted, const double* d_vals_sorted, int32_t shift,
+                                     int64_t pix0, void* d_map, int f32, void* stream) {
+  if (n < 0 || shift < 1 || shift > 40) return fail("segment_accumulate: bad arguments");
+  if (n == 0) return 0;
+  if (!d_keys_sorted || !d_vals_sorted || !d_map) return fail("segment_accumulate: NULL pointer");
+  const unsigned long long* k = reinterpret_cast<const unsigned long long*>(d_keys_sorted);
+  if (f32)
+    segment_accumulate_kernel<float><<<stream_grid_n(n), 256, 0, (cudaStream_t)stream>>>(n, k, d_vals_sorted, shift, pix0, (float*)d_map);
+  else
+    segment_accumulate_kernel<double><<<stream_grid_n(n), 256, 0, (cudaStream_t)stream>>>(n, k, d_vals_sorted, shift, pix0, (double*)d_map);
   AP_LAUNCH_CHECK();
   return 0;
 }

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev 
         double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
         const int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
         if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && pix >= hpx.clip_pix0 && pix < hpx.npix)) {
-          atomicAdd(&map[pix - hpx.clip_pix0], (MapT)val);
+          accumulate(hpx, map, pix, val, h);
           ++painted;
         }
         break;

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
 
     // phase 2: two pixels per thread per iteration (k and k + 256): independent dependency chains
     // (table loads, series) overlap, then both REDs are issued
-    auto eval = [&](int32_t k, int64_t& pix) -> double {
+    auto eval = [&](int32_t k, int64_t& pix, int& hl_out) -> double {
       int lo;
       if (k < kPixMapMax) {
         lo = sm.pixmap[k];
@@ -357,10 +357,11 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
       }
       int32_t ip = r.ip_lo + j;
       pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
+      hl_out = hl;
       return val;
     };
     // the same arithmetic with every data-dependent branch resolved for the whole chunk (small discs: the common case)
-    auto eval_small = [&](int32_t k, int64_t& pix) -> double {
+    auto eval_small = [&](int32_t k, int64_t& pix, int& hl_out) -> double {
       const int lo = sm.pixmap[k];
       const RingItem& r = sm.item[lo];
       const int32_t j = k - sm.pix_off[lo];
@@ -381,21 +382,23 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
       }
       const int32_t ip = r.ip_lo + j;
       pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
+      hl_out = hl;
       return val;
     };
     for (int32_t k = tid; k < total; k += 2 * kPaintThreads) {
       int64_t p0, p1 = 0;
+      int g0 = 0, g1 = 0;
       const bool two = (k + kPaintThreads < total);
       double v0, v1;
       if (fastp) {
-        v0 = eval_small(k, p0);
-        v1 = two ? eval_small(k + kPaintThreads, p1) : 0.0;
+        v0 = eval_small(k, p0, g0);
+        v1 = two ? eval_small(k + kPaintThreads, p1, g1) : 0.0;
       } else {
-        v0 = eval(k, p0);
-        v1 = two ? eval(k + kPaintThreads, p1) : 0.0;
+        v0 = eval(k, p0, g0);
+        v1 = two ? eval(k + kPaintThreads, p1, g1) : 0.0;
       }
-      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) atomicAdd(&map[p0 - hpx.clip_pix0], (MapT)v0);
-      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) atomicAdd(&map[p1 - hpx.clip_pix0], (MapT)v1);
+      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) accumulate(hpx, map, p0, v0, h0 + g0);
+      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) accumulate(hpx, map, p1, v1, h0 + g1);
     }
     __syncthreads();
   }

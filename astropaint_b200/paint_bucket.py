@@ -304,12 +304,18 @@ class Catalog:
 class Canvas:
     """Full-sky HEALPix (RING) canvas; the fp64 pixel array lives in HBM while painting."""
 
-    def __init__(self, catalog, nside, mode="healpy", R_times=1, inclusive=False, *, accumulate="fp64"):
+    def __init__(self, catalog, nside, mode="healpy", R_times=1, inclusive=False, *, accumulate="fp64",
+                 deterministic=False):
         """`accumulate="fp32"` (extra, keyword-only) keeps the map in float32: templates are still
-        evaluated in fp64, each value is rounded once before it is accumulated (parity bar 1e-4)."""
+        evaluated in fp64, each value is rounded once before it is accumulated (parity bar 1e-4).
+        `deterministic=True` (extra, keyword-only): sprays of templates with a device twin accumulate by
+        sort-then-segmented-reduce instead of atomics -- every pixel receives its values in catalog order, as in the
+        reference's serial loop, so the map is bit-reproducible from run to run (slower: the (pixel, value) pairs are
+        materialised and sorted)."""
         assert mode == "healpy", "currently only full sky is supported"
         assert accumulate in ("fp64", "fp32")
         self.accumulate = accumulate
+        self.deterministic = bool(deterministic)
         self._nside = int(nside)
         self._npix = 12 * self._nside * self._nside
         self._lmax = 3 * self._nside - 1
@@ -516,6 +522,36 @@ class Canvas:
             self._state = "device"
         self.discs = self.Disc(self.catalog, self.nside, self.R_times, self.inclusive)
         self._mark_painted()
+
+    # ---- map files (reference: paint_bucket.py:1478-1558; hp.write_map / hp.read_map restated in lib/fits_map.py)
+    def _map_filename(self, filename, prefix, suffix):
+        if prefix and str(prefix)[-1] != "_":
+            prefix = "".join([prefix, "_"])
+        if suffix and str(suffix)[0] != "_":
+            suffix = "".join(["_", suffix])
+        if filename is None:
+            filename = f"{str(prefix or '')}{self.template_name}_NSIDE={self.nside}{str(suffix or '')}.fits"
+        return filename
+
+    def save_map_to_file(self, filename=None, prefix=None, suffix=None, overwrite=True):
+        """save the map as a HEALPix FITS file (healpy.write_map's layout: one float32 column, RING).  With several
+        ranks the call is collective (`pixels` assembles the bands) and rank 0 writes."""
+        from .lib import fits_map
+        from . import parallel
+        filename = self._map_filename(filename, prefix, suffix)
+        pixels = self.pixels
+        if parallel.world()[0] == 0:
+            fits_map.write_map(filename, pixels, overwrite=overwrite)
+        parallel.barrier()
+
+    def load_map_from_file(self, filename=None, prefix=None, suffix=None, inplace=True):
+        """load a HEALPix FITS map (healpy.read_map) into canvas.pixels, or return it"""
+        from .lib import fits_map
+        m = fits_map.read_map(self._map_filename(filename, prefix, suffix))
+        if inplace:
+            self.pixels = m
+        else:
+            return m
 
     def discs_coverage(self):
         """The 0/1 map Canvas.show_discs draws (paint_bucket.py:1433-1458: junk_pixels[disc] = 1 for every halo's
@@ -999,7 +1035,7 @@ class Painter:
         dev = d_band.device
         # the decision to stream must be the same on every rank: it depends on the catalog size only
         host = None
-        if cat.size // band.world_size >= self.PREFETCH_MIN_HALOS:
+        if cat.size // band.world_size >= self.PREFETCH_MIN_HALOS and not canvas.deterministic:
             host = canvas._reusable_host()
         plan = _bands.Plan(band, reach, n_chunks=None if host is not None else 1)
         lo, hi = plan.halo_lo, plan.halo_hi
@@ -1086,7 +1122,17 @@ class Painter:
                 eng.copy_d2h(host.band_view(rel_lo, rel_hi), d_band[rel_lo:rel_hi], stream=copy_stream)
                 mark("copy", f"pixels {rel_lo}:{rel_hi}", copy_stream)
             path += "+stream"
-        eng.run_chunks(plan, paint_chunk, chunk_done)
+        if canvas.deterministic:
+            # sort-then-segmented-reduce: pairs for at most every pixel of every disc of the slice (K1 counts)
+            with eng.band_clip(band):
+                n_max = int(eng.disc_count(halos, nside)[0].sum().item()) if halos.n else 0
+            labels = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).to(dev)
+            with eng.emit_pairs(n_max, labels, canvas.npix, dev) as pairs:
+                eng.run_chunks(plan, paint_chunk, None)
+            pairs.accumulate(d_band, band.pix_lo)
+            path += "+deterministic"
+        else:
+            eng.run_chunks(plan, paint_chunk, chunk_done)
         if host is not None:
             canvas._prefetch = (copy_stream, band.npix)
         canvas._dfull = None
@@ -1101,6 +1147,9 @@ class Painter:
         partial map; the partial maps are summed over NVLink and every rank keeps its own band of the sum."""
         import torch
         from . import parallel
+        if canvas.deterministic:
+            raise NotImplementedError("Canvas(deterministic=True) is available for templates with a device twin; "
+                                      f"'{self.template_name}' runs on the host-template path (atomic scatter)")
         band = canvas._band()
         d_band = canvas._device_band()
         if band.whole:

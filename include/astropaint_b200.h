@@ -117,6 +117,20 @@ int ap_disc_count_items(int64_t nside, const ap_halos* halos, int64_t* d_n_pix, 
                         int32_t n_samples, int64_t* d_items, int64_t item_cap, unsigned long long* d_item_count,
                         void* stream);
 
+/* Deterministic accumulation (the sort-then-segmented-reduce form of np.add.at, paint_bucket.py:2387-2389).  Between
+ * ap_emit_begin and ap_emit_end every painting entry point called by this thread (ap_paint_profile, ap_paint_table,
+ * ap_paint_los_items, _f32 forms) appends each painted value to d_keys / d_vals instead of adding it atomically:
+ * key = pixel << shift | label, label = d_labels[halo] (or the halo's position when d_labels is NULL; must be below
+ * 2^shift).  *d_count (zeroed by the caller) receives the number of pairs; pairs beyond cap are dropped.  The caller
+ * sorts the keys (values along) and calls ap_segment_accumulate, which adds every pixel's values to d_map in label
+ * order -- the reference's serial summation order -- with plain stores; d_map addresses pixel pix0 (the band's first
+ * pixel under ap_band_clip, else 0).  Results are bit-reproducible from run to run.                          */
+int ap_emit_begin(uint64_t* d_keys, double* d_vals, unsigned long long* d_count, int64_t cap, const int64_t* d_labels,
+                  int32_t shift);
+int ap_emit_end(void);
+int ap_segment_accumulate(int64_t n, const uint64_t* d_keys_sorted, const double* d_vals_sorted, int32_t shift,
+                          int64_t pix0, void* d_map, int f32, void* stream);
+
 /* Near-tie audit of the disc query (hp.query_disc, paint_bucket.py:1222).  The span boundaries are floor() of
  * expressions holding atan2 / cos, where CUDA's libm and the CPU's may differ in the last bit: a boundary can flip
  * only if its floor argument lies within ~1e-11 of an integer.  ap_disc_near_ties appends every halo that has a

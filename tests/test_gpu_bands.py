@@ -170,3 +170,34 @@ def test_two_rank_spray_equals_single_rank():
     sys.stderr.write(out.stderr[-4000:])
     assert out.returncode == 0
     assert out.stdout.count("OK") >= 2 * 5
+
+
+def test_deterministic_accumulation_is_bit_reproducible(band_cats):
+    """Canvas(deterministic=True): sort-then-segmented-reduce instead of atomics (SURVEY 7.2 K3 alternative).  Two runs
+    give bit-identical maps (the atomic path only agrees to rounding), the map equals the atomic one to 1e-12, the
+    emulated ranks' bands tile it bit for bit, and a host-evaluated template refuses the mode."""
+    import astropaint_b200 as ap
+    from astropaint_b200 import _bands
+    from astropaint_b200.profiles import NFW, Battaglia16
+    for cat_name, nside, tmpl in [("box", 128, NFW.kSZ_T), ("websky", 2048, Battaglia16.kSZ_T), ("websky", 512, Battaglia16.tau_2D_interp)]:
+        cat = band_cats[cat_name]
+        maps = []
+        for _ in range(2):
+            canvas = ap.Canvas(cat, nside, R_times=5, deterministic=True)
+            p = ap.Painter(tmpl)
+            p.spray(canvas)
+            assert p.last_spray["path"].endswith("+deterministic")
+            maps.append(canvas.pixels.copy())
+        assert np.array_equal(maps[0], maps[1])
+        atomic, n_atomic = _whole_map(cat, nside, 5, tmpl)
+        assert int(p.last_spray["d_count"].item()) == n_atomic
+        map_close(maps[0], atomic, 1e-10)
+        parts = []
+        for r in range(3):
+            canvas = ap.Canvas(cat, nside, R_times=5, deterministic=True)
+            canvas._band_override = _bands.Band(nside, r, 3)
+            ap.Painter(tmpl).spray(canvas)
+            parts.append(canvas._dmap.cpu().numpy())
+        assert np.array_equal(np.concatenate(parts), maps[0])      # same pixels, same values, same order of addition
+    with pytest.raises(NotImplementedError):
+        ap.Painter(lambda R, R_200c: np.exp(-R / R_200c)).spray(ap.Canvas(band_cats["websky_big"], 256, deterministic=True))

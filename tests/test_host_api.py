@@ -219,3 +219,30 @@ def test_band_plan_ownership_and_streaming_are_safe():
         for r in (1, nside - 1, nside, 2 * nside, 3 * nside, 3 * nside + 1, 4 * nside - 1):
             assert _bands.ring_start(nside, r) == hp.ring_info(r)[0]
             assert abs(_bands.ring_z(nside, r) - hp.ring2z(r)) < 1e-15
+
+
+def test_fits_map_round_trip_and_layout(tmp_path):
+    """Canvas.save_map_to_file / load_map_from_file (paint_bucket.py:1478-1558): healpy.write_map's default layout
+    (float32 column TEMPERATURE, 1024 pixels per row, RING keywords) read back by healpy.read_map's restatement."""
+    from astropaint_b200.lib import fits_map
+    rng = np.random.default_rng(0)
+    for nside in (4, 16, 64):
+        m = rng.normal(size=12 * nside * nside)
+        fn = str(tmp_path / f"map_{nside}.fits")
+        fits_map.write_map(fn, m, overwrite=True)
+        raw = open(fn, "rb").read()
+        assert len(raw) % 2880 == 0 and raw[:30].decode().startswith("SIMPLE  =                    T")
+        hdr = raw[2880:2880 * 2].decode()
+        per_row = 1024 if 12 * nside * nside > 1024 else 1
+        for card in ("XTENSION= 'BINTABLE'", "PIXTYPE = 'HEALPIX '", "ORDERING= 'RING    '", f"TFORM1  = '{per_row}E",
+                     "TTYPE1  = 'TEMPERATURE'", "INDXSCHM= 'IMPLICIT'"):
+            assert card in hdr, card
+        assert f"{nside:>20}" in hdr[hdr.index("NSIDE   ="):hdr.index("NSIDE   =") + 80]
+        back = fits_map.read_map(fn)
+        assert back.dtype == np.float64 and np.array_equal(back, m.astype(np.float32).astype(np.float64))
+        with pytest.raises(OSError):
+            fits_map.write_map(fn, m, overwrite=False)
+        fits_map.write_map(fn, m, overwrite=True, dtype=np.float64)
+        assert np.array_equal(fits_map.read_map(fn), m)
+    with pytest.raises(ValueError):
+        fits_map.write_map(str(tmp_path / "bad.fits"), np.zeros(13))
