@@ -842,11 +842,18 @@ class Canvas:
         if ypix is None:
             ypix = xpix
         if apply_func is None:
+            from . import parallel
             idx, lonra, latra, xpix, ypix = self._cutout_setup(halo_list, lon_range, lat_range, xpix, ypix)
-            d_map = self.pixels_device
+            d_map = self.pixels_device           # several ranks: the bands gathered over NVLink
+            rank, ws = parallel.world()
+            if ws > 1:                           # each rank stacks its share of the halos, the small stacks are summed
+                idx = np.array_split(idx, ws)[rank]
             d_lon = eng.to_device(self.catalog.data["lon"].values[idx], d_map.device)
             d_lat = eng.to_device(self.catalog.data["lat"].values[idx], d_map.device)
-            stack = eng.stack_cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix).cpu().numpy()
+            d_stack = eng.stack_cutouts(d_map, self.nside, d_lon, d_lat, lonra, latra, xpix, ypix)
+            if ws > 1:
+                parallel.reduce_partial_map(d_stack, "all")
+            stack = d_stack.cpu().numpy()
         else:
             stack = self._stack_cutouts_device(halo_list, lon_range, lat_range, xpix, ypix, apply_func, func_kwargs)
             if stack is None:       # some callable has no device twin: the reference's loop over cutouts

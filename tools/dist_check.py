@@ -63,5 +63,19 @@ for name, tmpl, c, nside, inclusive in CASES:
     print(f"rank {rank}/{ws} {name}: path {p.last_spray['path']}, device {err_dev:.2e} host {err_host:.2e} "
           f"streamed {err_again:.2e}, pairs {int(n_painted.item())} vs {n_want}: {'OK' if ok else 'MISMATCH'}", flush=True)
     assert ok
+# stack_cutouts: each rank stacks its share of the halo list from the gathered map; the stacks are summed over NVLink
+canvas = ap.Canvas(cat, 2048, R_times=5)
+ap.Painter(NFW.kSZ_T).spray(canvas)
+got = canvas.stack_cutouts(halo_list=np.arange(500), lon_range=[-0.5, 0.5], xpix=64, inplace=False)
+c2 = ap.Canvas(cat, 2048, R_times=5)
+c2._band_override = _bands.Band(2048, 0, 1)
+ap.Painter(NFW.kSZ_T).spray(c2)
+d_lon = torch.from_numpy(cat.data["lon"].values[:500].copy()).cuda()
+d_lat = torch.from_numpy(cat.data["lat"].values[:500].copy()).cuda()
+from astropaint_b200 import _engine as eng  # noqa: E402
+want = eng.stack_cutouts(c2._dmap, 2048, d_lon, d_lat, [-0.5, 0.5], [-0.5, 0.5], 64, 64).cpu().numpy()
+err = float(np.abs(got - want).max() / np.abs(want).max())
+print(f"rank {rank}/{ws} stack_cutouts sharded over ranks: {err:.2e}: {'OK' if err < 1e-12 else 'MISMATCH'}", flush=True)
+assert err < 1e-12
 dist.barrier()
 dist.destroy_process_group()
