@@ -26,15 +26,6 @@ struct Hpx {
   // band of the map one rank owns.  Default: every ring, clip_pix0 = 0.
   int32_t clip_lo, clip_hi;
   int64_t clip_pix0;
-  // Deterministic accumulation (ap_emit_begin): instead of an atomic add, every painted (pixel, value) pair is
-  // appended to a list as key = pixel << emit_shift | halo label; the caller sorts the keys and sums each pixel's
-  // values in halo order (ap_segment_accumulate).  NULL = atomics.
-  unsigned long long* emit_keys;
-  double* emit_vals;
-  unsigned long long* emit_count;
-  long long emit_cap;
-  const long long* emit_labels;
-  int32_t emit_shift;
 };
 
 AP_HD Hpx make_hpx(int64_t nside) {
@@ -51,12 +42,6 @@ AP_HD Hpx make_hpx(int64_t nside) {
   h.clip_lo = 1;
   h.clip_hi = (int32_t)(4 * nside);
   h.clip_pix0 = 0;
-  h.emit_keys = nullptr;
-  h.emit_vals = nullptr;
-  h.emit_count = nullptr;
-  h.emit_cap = 0;
-  h.emit_labels = nullptr;
-  h.emit_shift = 0;
   return h;
 }
 

@@ -17,6 +17,19 @@
 
 using namespace ap;
 
+// Deterministic accumulation (ap_emit_begin): instead of an atomic add, every painted (pixel, value) pair is
+// appended to a list as key = pixel << shift | halo label; the caller sorts the keys and sums each pixel's values in
+// halo order (ap_segment_accumulate).  keys == NULL = atomics.
+struct EmitArgs {
+  unsigned long long* keys;
+  double* vals;
+  unsigned long long* count;
+  long long cap;
+  const long long* labels;
+  int32_t shift;
+};
+EmitArgs emit_args();                    // the calling thread's ap_emit_begin state
+
 int fail(const std::string& m);          // records the message for ap_last_error(), returns 1
 Hpx disc_hpx(int64_t nside);             // make_hpx + the calling thread's inclusive / band-clip modes
 int quad_fast_enabled();                 // ap_quad_fast_path setting
@@ -39,20 +52,21 @@ static __device__ unsigned long long g_bounds_errors = 0ull;
 // One painted value: an fp64 (or fp32) RED into the rank's band of the map, or -- in deterministic mode -- an
 // append to the (key, value) list with one warp-aggregated slot allocation per converged group of lanes.
 #if defined(__CUDACC__)
-template <class MapT>
-__device__ __forceinline__ void accumulate(const Hpx& hpx, MapT* map, int64_t pix, double val, int64_t halo) {
-  if (hpx.emit_keys) {
+template <bool EMIT, class MapT>
+__device__ __forceinline__ void accumulate(const Hpx& hpx, const EmitArgs& em, MapT* map, int64_t pix, double val,
+                                           int64_t halo) {
+  if (EMIT) {
     const unsigned mask = __activemask();
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(mask) - 1;
     unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(hpx.emit_count, (unsigned long long)__popc(mask));
+    if (lane == leader) base = atomicAdd(em.count, (unsigned long long)__popc(mask));
     base = __shfl_sync(mask, base, leader);
     const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
-    if ((long long)slot < hpx.emit_cap) {
-      const unsigned long long label = (unsigned long long)(hpx.emit_labels ? hpx.emit_labels[halo] : halo);
-      hpx.emit_keys[slot] = ((unsigned long long)pix << hpx.emit_shift) | label;
-      hpx.emit_vals[slot] = val;
+    if ((long long)slot < em.cap) {
+      const unsigned long long label = (unsigned long long)(em.labels ? em.labels[halo] : halo);
+      em.keys[slot] = ((unsigned long long)pix << em.shift) | label;
+      em.vals[slot] = val;
     }
   } else {
     atomicAdd(&map[pix - hpx.clip_pix0], (MapT)val);

@@ -61,15 +61,8 @@ extern "C" int ap_band_clip(int64_t ring_lo, int64_t ring_hi) {
   return 0;
 }
 // Deterministic accumulation of the calling thread's next painting launches (ap_emit_begin .. ap_emit_end)
-struct EmitState {
-  unsigned long long* keys = nullptr;
-  double* vals = nullptr;
-  unsigned long long* count = nullptr;
-  long long cap = 0;
-  const long long* labels = nullptr;
-  int shift = 0;
-};
-static thread_local EmitState g_emit;
+static thread_local EmitArgs g_emit = {nullptr, nullptr, nullptr, 0, nullptr, 0};
+EmitArgs emit_args() { return g_emit; }
 extern "C" int ap_emit_begin(uint64_t* d_keys, double* d_vals, unsigned long long* d_count, int64_t cap,
                              const int64_t* d_labels, int32_t shift) {
   if (!d_keys || !d_vals || !d_count || cap < 0) return fail("emit_begin: NULL buffer");
@@ -83,18 +76,12 @@ extern "C" int ap_emit_begin(uint64_t* d_keys, double* d_vals, unsigned long lon
   return 0;
 }
 extern "C" int ap_emit_end(void) {
-  g_emit = EmitState();
+  g_emit = EmitArgs{nullptr, nullptr, nullptr, 0, nullptr, 0};
   return 0;
 }
 Hpx disc_hpx(int64_t nside) {
   Hpx h = make_hpx(nside);
   hpx_set_inclusive(h, g_incl_fact);
-  h.emit_keys = g_emit.keys;
-  h.emit_vals = g_emit.vals;
-  h.emit_count = g_emit.count;
-  h.emit_cap = g_emit.cap;
-  h.emit_labels = g_emit.labels;
-  h.emit_shift = g_emit.shift;
   if (g_clip_hi > 0) {
     const int64_t top = 4 * nside;
     h.clip_lo = (int32_t)(g_clip_lo < top ? g_clip_lo : top);

@@ -275,12 +275,12 @@ extern "C" int ap_spline_build_uniform(int64_t n, int32_t n_samples, const doubl
 // (ap_disc_count_items: halo * 32 + pixel ordinal, appended on the device, their number in *n_items), so the
 // host never reads a count back; the grid is sized for the SMs and strides over the list, one quadrature per
 // lane.  Pixels outside the calling rank's ring band (ap_band_clip) belong to another rank and are skipped.
-template <int KIND, class MapT>
+template <int KIND, class MapT, bool EMIT>
 __global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev H, const double* p0, const double* p1,
                                                               const double* p2, const double* scale,
                                                               const unsigned long long* n_items, int64_t item_cap,
                                                               const int64_t* items, MapT* map,
-                                                              unsigned long long* n_painted) {
+                                                              unsigned long long* n_painted, EmitArgs em) {
   fm_smem_init();
   const int64_t total = min((int64_t)*n_items, item_cap);
   unsigned painted = 0;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev 
         double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
         const int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
         if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && pix >= hpx.clip_pix0 && pix < hpx.npix)) {
-          accumulate(hpx, map, pix, val, h);
+          accumulate<EMIT>(hpx, em, map, pix, val, h);
           ++painted;
         }
         break;
@@ -321,10 +321,13 @@ template <int KIND>
 static void launch_los_items(bool f32, unsigned blocks, cudaStream_t st, Hpx hpx, HalosDev H, const double* p0,
                              const double* p1, const double* p2, const double* scale, const unsigned long long* n_items,
                              int64_t item_cap, const int64_t* items, void* map, unsigned long long* n_painted) {
-  if (f32)
-    paint_los_items_kernel<KIND, float><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (float*)map, n_painted);
+  const EmitArgs em = emit_args();
+  if (em.keys)
+    paint_los_items_kernel<KIND, double, true><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (double*)map, n_painted, em);
+  else if (f32)
+    paint_los_items_kernel<KIND, float, false><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (float*)map, n_painted, em);
   else
-    paint_los_items_kernel<KIND, double><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (double*)map, n_painted);
+    paint_los_items_kernel<KIND, double, false><<<blocks, 128, 0, st>>>(hpx, H, p0, p1, p2, scale, n_items, item_cap, items, (double*)map, n_painted, em);
 }
 
 static int paint_los_items_impl(int kind, int64_t nside, const ap_halos* halos, const double* p0, const double* p1,

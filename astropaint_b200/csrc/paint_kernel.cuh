@@ -99,11 +99,14 @@ template <int P>
 constexpr int paint_min_blocks() {
   return (P == P_B16_TAU2D || P == P_B16_RHOGAS2D || P == P_NFW_RHO2D_LOS) ? 2 : 4;
 }
-template <int P, class MapT, bool INCL>
+// EMIT: deterministic mode -- painted values are appended to the (key, value) list of ap_emit_begin instead of being
+// added atomically; a separate instantiation, so that the atomic kernel carries neither the branch nor its registers
+// (as a run-time flag it cost K3 0.7 ms per 1e7 halos and a 32-byte spill)
+template <int P, class MapT, bool INCL, bool EMIT>
 __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_kernel(Hpx hpx, HalosDev H, ParamPtrs pp, TableArgs tab,
                                                                StatsArgs st, int halos_per_block,
                                                                MapT* __restrict__ map,
-                                                               unsigned long long* n_painted) {
+                                                               unsigned long long* n_painted, EmitArgs em) {
   constexpr bool VEC = (P == P_NFW_BG);
   constexpr bool STATS = (P == P_STATS);
   __shared__ PaintShared<P> sm;
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
       }
       int32_t ip = r.ip_lo + j;
       pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
-      hl_out = hl;
+      if (EMIT) hl_out = hl;
       return val;
     };
     // the same arithmetic with every data-dependent branch resolved for the whole chunk (small discs: the common case)
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
       }
       const int32_t ip = r.ip_lo + j;
       pix = r.startpix + (ip < 0 ? ip + r.nr : ip);
-      hl_out = hl;
+      if (EMIT) hl_out = hl;
       return val;
     };
     for (int32_t k = tid; k < total; k += 2 * kPaintThreads) {
@@ -397,8 +400,8 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
         v0 = eval(k, p0, g0);
         v1 = two ? eval(k + kPaintThreads, p1, g1) : 0.0;
       }
-      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) accumulate(hpx, map, p0, v0, h0 + g0);
-      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) accumulate(hpx, map, p1, v1, h0 + g1);
+      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) accumulate<EMIT>(hpx, em, map, p0, v0, h0 + g0);
+      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) accumulate<EMIT>(hpx, em, map, p1, v1, h0 + g1);
     }
     __syncthreads();
   }
@@ -452,16 +455,23 @@ static int launch_paint(int64_t nside, const ap_halos* halos, const ParamPtrs& p
   // few blocks (small catalog): split each block's ring items over up to 8 blocks (K1 keeps its per-block sums)
   const dim3 nb((unsigned)blocks, (P != P_STATS && blocks <= 4096) ? 8u : 1u);
   cudaStream_t cs = (cudaStream_t)stream;
-  if (f32 && P != P_STATS) {
+  const HalosDev hd = to_dev(halos);
+  const EmitArgs em = emit_args();
+  if (em.keys && P != P_STATS) {   // deterministic mode: the map is not touched by this launch
     if (hpx.incl_fct)
-      paint_kernel<P, float, true><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+      paint_kernel<P, double, true, true><<<nb, kPaintThreads, 0, cs>>>(hpx, hd, pp, tab, st, g, (double*)d_map, d_n_painted, em);
     else
-      paint_kernel<P, float, false><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (float*)d_map, d_n_painted);
+      paint_kernel<P, double, false, true><<<nb, kPaintThreads, 0, cs>>>(hpx, hd, pp, tab, st, g, (double*)d_map, d_n_painted, em);
+  } else if (f32 && P != P_STATS) {
+    if (hpx.incl_fct)
+      paint_kernel<P, float, true, false><<<nb, kPaintThreads, 0, cs>>>(hpx, hd, pp, tab, st, g, (float*)d_map, d_n_painted, em);
+    else
+      paint_kernel<P, float, false, false><<<nb, kPaintThreads, 0, cs>>>(hpx, hd, pp, tab, st, g, (float*)d_map, d_n_painted, em);
   } else {
     if (hpx.incl_fct)
-      paint_kernel<P, double, true><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+      paint_kernel<P, double, true, false><<<nb, kPaintThreads, 0, cs>>>(hpx, hd, pp, tab, st, g, (double*)d_map, d_n_painted, em);
     else
-      paint_kernel<P, double, false><<<nb, kPaintThreads, 0, cs>>>(hpx, to_dev(halos), pp, tab, st, g, (double*)d_map, d_n_painted);
+      paint_kernel<P, double, false, false><<<nb, kPaintThreads, 0, cs>>>(hpx, hd, pp, tab, st, g, (double*)d_map, d_n_painted, em);
   }
   AP_LAUNCH_CHECK();
   return 0;
