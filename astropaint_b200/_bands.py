@@ -93,7 +93,7 @@ class Band:
 #: work (= halo count) ratio of consecutive chunks.  A chunk's device->host copy overlaps the next chunk's
 #: compute, so what stays exposed at the end of a spray is the LAST chunk's copy: geometrically shrinking
 #: chunks end on a small one, and a ratio >= t_copy / t_compute keeps every earlier copy hidden
-#: (measured in round 1, tools/e2e_chunks.py: 10 x 0.75 beats 8 equal chunks by 11 ms at 1e7 halos).
+#: (measured in round 1 on the 1e7-halo bench catalog: 10 chunks x 0.75 beat 8 equal chunks by 11 ms end to end).
 CHUNK_RATIO = 0.75
 MAX_CHUNKS = 10
 MIN_CHUNK_HALOS = 50_000
