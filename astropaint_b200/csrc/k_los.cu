@@ -46,14 +46,16 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
   return 0;
 }
 
-// 6 blocks of 128 threads per SM (80 registers): measured 176.1 / 173.5 / 180.9 / 182.9 ms
-// per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers); the kernel is fp64-pipe bound
-// (66% of the DFMA issue rate, profiles/), not occupancy bound
+// 8 blocks of 128 threads per SM (64 registers, 32 warps).  Round 1 (per-thread los_setup inside the kernel) measured
+// 176.1 / 173.5 / 180.9 / 182.9 ms per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers); with the
+// per-halo constants in their own kernel the 64-register build no longer pays for the spills: 138.7 ms at 6 blocks,
+// 135.8 at 8, 137.3 at 9 (56 registers), 136.6 at 10 (48), 135.6 as 4 blocks of 256 (gpurun_out/r2_variants*.log).
+// More warps buy little: the kernel is bound by fp64 throughput, not by latency (profiles/README.md).
 #ifndef AP_QAGI_THREADS
 #define AP_QAGI_THREADS 128
 #endif
 #ifndef AP_QAGI_MINBLOCKS
-#define AP_QAGI_MINBLOCKS 6
+#define AP_QAGI_MINBLOCKS 8
 #endif
 // per-halo constants of the 3-D profile (los_setup: eight pow() for the Battaglia fit and the critical density):
 // once per halo, one halo per lane, instead of once per (halo, node) thread of the node kernel

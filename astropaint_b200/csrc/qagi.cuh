@@ -7,7 +7,7 @@
 // Battaglia16 integrand reaches ~2.5e-3, so reproducing the reference map to 1e-6 means
 // reproducing QUADPACK's adaptive decisions, not the integral: this file follows the
 // published netlib algorithm (Piessens et al. 1983, public domain) statement by statement.
-// csrc/hostcheck.cpp compiles it with g++ and tests/test_qagi_host.py checks it against
+// csrc/hostcheck.cpp compiles it with g++ and tests/test_hostcheck.py checks it against
 // scipy.integrate.quad (value, abserr, neval) on the CPU.
 #pragma once
 #include "common.cuh"
