@@ -278,7 +278,7 @@ extern "C" int ap_spline_build_uniform(int64_t n, int32_t n_samples, const doubl
 // host never reads a count back; the grid is sized for the SMs and strides over the list, one quadrature per
 // lane.  Pixels outside the calling rank's ring band (ap_band_clip) belong to another rank and are skipped.
 template <int KIND, class MapT, bool EMIT>
-__global__ void __launch_bounds__(128) paint_los_items_kernel(Hpx hpx, HalosDev H, const double* p0, const double* p1,
+__global__ void __launch_bounds__(128, 6) paint_los_items_kernel(Hpx hpx, HalosDev H, const double* p0, const double* p1,
                                                               const double* p2, const double* scale,
                                                               const unsigned long long* n_items, int64_t item_cap,
                                                               const int64_t* items, MapT* map,
