@@ -46,16 +46,18 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
   return 0;
 }
 
-// 8 blocks of 128 threads per SM (64 registers, 32 warps).  Round 1 (per-thread los_setup inside the kernel) measured
-// 176.1 / 173.5 / 180.9 / 182.9 ms per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers); with the
-// per-halo constants in their own kernel the 64-register build no longer pays for the spills: 138.7 ms at 6 blocks,
-// 135.8 at 8, 137.3 at 9 (56 registers), 136.6 at 10 (48), 135.6 as 4 blocks of 256 (gpurun_out/r2_variants*.log).
-// More warps buy little: the kernel is bound by fp64 throughput, not by latency (profiles/README.md).
+// 6 blocks of 128 threads per SM (80 registers, 24 warps).  Round 1 (per-thread los_setup inside the kernel) measured
+// 176.1 / 173.5 / 180.9 / 182.9 ms per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers).  Round 2, with
+// the per-halo constants in their own kernel: timed ALONE for 30 ms bursts the 64-register build wins (135.8 ms at 8
+// blocks against 138.7 at 6, 137.3 at 9, 136.6 at 10, 135.6 as 4 blocks of 256; gpurun_out/r2_variants*.log), but in the
+// sustained step its 32 warps per SM draw enough power for the 1 kW cap to pull the SM clock from 1965 to ~1870 MHz
+// (nvidia-smi: sw_power_cap active) and it LOSES: 141.3 ms against 138.5 ms, same box, back to back, twice
+// (gpurun_out/r2_mb_ab.log).  The kernel is bound by fp64 throughput per watt, not by latency: more warps buy nothing.
 #ifndef AP_QAGI_THREADS
 #define AP_QAGI_THREADS 128
 #endif
 #ifndef AP_QAGI_MINBLOCKS
-#define AP_QAGI_MINBLOCKS 8
+#define AP_QAGI_MINBLOCKS 6
 #endif
 // per-halo constants of the 3-D profile (los_setup: eight pow() for the Battaglia fit and the critical density):
 // once per halo, one halo per lane, instead of once per (halo, node) thread of the node kernel
