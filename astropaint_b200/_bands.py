@@ -59,24 +59,33 @@ def ring_above(nside, z):
     return ir if z > 0 else 4 * nside - ir - 1
 
 
-def owner_rings(nside, world_size):
-    """First ring of every rank's band plus the end marker 4 nside: equal shares of the sphere's area
-    (z = 1 - 2 g / G), aligned to ring boundaries.  Depends on (nside, world_size) only, so every rank and
-    every spray agrees on it."""
+def owner_rings(nside, world_size, weights=None):
+    """First ring of every rank's band plus the end marker 4 nside, aligned to ring boundaries: shares of the
+    sphere's area proportional to `weights` (z = 1 - 2 F_g, F the cumulative share), equal shares when None.
+    Depends on (nside, world_size, weights) only, so every rank and every spray agrees on it."""
+    if weights is None:
+        cum = [(g + 1.0) / world_size for g in range(world_size)]
+    else:
+        w = np.asarray(weights, dtype=np.float64)
+        assert len(w) == world_size and np.all(w > 0), "one positive weight per rank"
+        cum = list(np.cumsum(w / w.sum()))
     rings = [1]
     for g in range(1, world_size):
-        r = ring_above(nside, 1.0 - 2.0 * g / world_size) + 1
+        r = ring_above(nside, 1.0 - 2.0 * cum[g - 1]) + 1
         rings.append(min(max(r, rings[-1]), 4 * nside))
     rings.append(4 * nside)
     return rings
 
 
 class Band:
-    """The part of the map one rank owns: rings [ring_lo, ring_hi) = pixels [pix_lo, pix_hi)."""
+    """The part of the map one rank owns: rings [ring_lo, ring_hi) = pixels [pix_lo, pix_hi).  `weights` (one per
+    rank, the same on every rank) sizes the bands, e.g. by each GPU's measured device->host bandwidth so that the
+    read-back of the map finishes on all ranks together (parallel.readback_weights)."""
 
-    def __init__(self, nside, rank, world_size):
+    def __init__(self, nside, rank, world_size, weights=None):
         self.nside, self.rank, self.world_size = int(nside), int(rank), int(world_size)
-        self.rings = owner_rings(self.nside, self.world_size)
+        self.weights = None if weights is None else tuple(float(x) for x in weights)
+        self.rings = owner_rings(self.nside, self.world_size, self.weights)
         self.pix_bounds = [ring_start(self.nside, r) for r in self.rings]
         self.ring_lo, self.ring_hi = self.rings[rank], self.rings[rank + 1]
         self.pix_lo, self.pix_hi = self.pix_bounds[rank], self.pix_bounds[rank + 1]

@@ -305,17 +305,23 @@ class Canvas:
     """Full-sky HEALPix (RING) canvas; the fp64 pixel array lives in HBM while painting."""
 
     def __init__(self, catalog, nside, mode="healpy", R_times=1, inclusive=False, *, accumulate="fp64",
-                 deterministic=False):
+                 deterministic=False, band_balance="area"):
         """`accumulate="fp32"` (extra, keyword-only) keeps the map in float32: templates are still
         evaluated in fp64, each value is rounded once before it is accumulated (parity bar 1e-4).
         `deterministic=True` (extra, keyword-only): sprays of templates with a device twin accumulate by
         sort-then-segmented-reduce instead of atomics -- every pixel receives its values in catalog order, as in the
         reference's serial loop, so the map is bit-reproducible from run to run (slower: the (pixel, value) pairs are
-        materialised and sorted)."""
+        materialised and sorted).
+        `band_balance` (extra, keyword-only; several ranks only): "area" gives every rank an equal share of the sphere
+        (balances the painting), "readback" sizes the bands by each GPU's measured device->host bandwidth
+        (parallel.readback_weights) so that `canvas.pixels` lands on all ranks together -- for workflows that read the
+        map back after every spray on hosts whose PCIe paths are not equal."""
         assert mode == "healpy", "currently only full sky is supported"
         assert accumulate in ("fp64", "fp32")
+        assert band_balance in ("area", "readback")
         self.accumulate = accumulate
         self.deterministic = bool(deterministic)
+        self.band_balance = band_balance
         self._nside = int(nside)
         self._npix = 12 * self._nside * self._nside
         self._lmax = 3 * self._nside - 1
@@ -373,7 +379,8 @@ class Canvas:
             if b is not None and self._state == "device":
                 raise RuntimeError("the process group changed while the canvas held a device map; read canvas.pixels "
                                    "(or clean()) before initialising / destroying torch.distributed")
-            self._band_cache = b = _bands.Band(self.nside, rank, ws)
+            weights = parallel.readback_weights() if (ws > 1 and self.band_balance == "readback") else None
+            self._band_cache = b = _bands.Band(self.nside, rank, ws, weights)
         return b
 
     @property

@@ -62,6 +62,43 @@ def barrier():
         dist.barrier()
 
 
+_READBACK_WEIGHTS = {}
+
+
+def readback_weights(megabytes=256, reps=3):
+    """Device->host bandwidth of every rank's GPU while ALL ranks copy at once [GB/s], the same list on every rank
+    (collective, measured once per process group and cached).  On a multi-GPU host the PCIe paths are not equal --
+    on the 8xB200 box of the bench the four GPUs of one half reach 11.7 GB/s each and the other four 18.5 GB/s
+    when all eight copy -- so bands sized by these numbers (Canvas(band_balance="readback")) finish their read-back
+    together, where equal-area bands wait for the slowest link."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = world()
+    if ws == 1:
+        return [1.0]
+    if ws in _READBACK_WEIGHTS:
+        return _READBACK_WEIGHTS[ws]
+    from . import _engine as eng
+    n = megabytes * (1 << 20) // 8
+    d = torch.zeros(n, dtype=torch.float64, device="cuda")
+    h = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    seen = []
+    for _ in range(reps + 1):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.copy_d2h(h, d)
+        e1.record()
+        e1.synchronize()
+        seen.append(8.0 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    t = torch.zeros(ws, dtype=torch.float64, device="cuda")
+    t[rank] = float(np.median(seen[1:]))       # the first copy warms the path up
+    dist.all_reduce(t)
+    _READBACK_WEIGHTS[ws] = [float(x) for x in t.cpu()]
+    return _READBACK_WEIGHTS[ws]
+
+
 def gather_bands(d_band, band, dtype):
     """Full map on every rank's device from the owners' bands: one broadcast per band over NVLink."""
     import torch

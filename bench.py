@@ -384,7 +384,8 @@ def run_b200(args):
     if not args.no_e2e:
         del halos, cols, args_t, d_band
         torch.cuda.empty_cache()
-        canvas = ap.Canvas(cat, NSIDE, R_times=R_TIMES)
+        # every step reads the map back: size the bands by each GPU's device->host bandwidth (equal areas at N = 1)
+        canvas = ap.Canvas(cat, NSIDE, R_times=R_TIMES, band_balance="readback")
         painter = ap.Painter(Battaglia16.kSZ_T)
         h2d_cols = ["x", "y", "z", "theta", "phi", "D_a", "R_ang_200c", "R_200c", "M_200c", "redshift", "v_r"]
 
@@ -411,6 +412,8 @@ def run_b200(args):
         line["e2e"] = {"value": pairs / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_h2d * len(h2d_cols)),
                        "d2h_bytes_per_step": 8 * npix, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                        "path": painter.last_spray["path"], "chunks": painter.last_spray["chunks"], "map_sum": e2e_sum,
+                       "band_balance": "readback" if world > 1 else "area",
+                       "readback_GBps_per_rank": [round(x, 1) for x in canvas._band().weights] if world > 1 else None,
                        "api": "Catalog.pin_memory(); Canvas.clean(); Painter(Battaglia16.kSZ_T).spray(canvas); canvas.pixels "
                               "(all ranks; each copies its band into the node's shared host map)"}
         del canvas, painter

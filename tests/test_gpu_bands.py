@@ -169,7 +169,7 @@ def test_two_rank_spray_equals_single_rank():
     sys.stdout.write(out.stdout[-4000:])
     sys.stderr.write(out.stderr[-4000:])
     assert out.returncode == 0
-    assert out.stdout.count("OK") >= 2 * 6
+    assert out.stdout.count("OK") >= 2 * 7
 
 
 def test_deterministic_accumulation_is_bit_reproducible(band_cats):

@@ -183,7 +183,12 @@ def test_band_plan_ownership_and_streaming_are_safe():
     rng = np.random.default_rng(0)
     for nside, ws, n_chunks in [(16, 1, 5), (16, 3, 2), (64, 8, 3), (64, 2, 6), (128, 5, 4)]:
         hp = H.HealpixRing(nside)
-        bands = [_bands.Band(nside, r, ws) for r in range(ws)]
+        # equal-area bands, or bands sized by per-rank weights (Canvas(band_balance="readback"))
+        weights = None if nside != 64 else list(rng.uniform(0.5, 2.0, ws))
+        bands = [_bands.Band(nside, r, ws, weights) for r in range(ws)]
+        if weights is not None:
+            share = np.array([b.npix for b in bands]) / hp.npix
+            assert np.allclose(share, np.array(weights) / np.sum(weights), atol=2.0 / nside)
         assert bands[0].pix_lo == 0 and bands[-1].pix_hi == hp.npix
         assert all(bands[r].pix_hi == bands[r + 1].pix_lo for r in range(ws - 1))
         assert all(b.pix_lo == _bands.ring_start(nside, b.ring_lo) for b in bands)

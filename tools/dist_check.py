@@ -33,11 +33,14 @@ cat = ap.Catalog(synthetic.websky_like(20000, seed=3))
 small = ap.Catalog(synthetic.websky_like(300, seed=4, m_min=2e14))
 ap.Painter.PREFETCH_MIN_HALOS = 2000
 _bands.MIN_CHUNK_HALOS = 1000
-CASES = [("NFW.kSZ_T", NFW.kSZ_T, cat, 2048, False), ("Battaglia16.kSZ_T", Battaglia16.kSZ_T, cat, 2048, False),
+CASES = [("NFW.kSZ_T", NFW.kSZ_T, cat, 2048, False), ("NFW.kSZ_T readback-balanced bands", NFW.kSZ_T, cat, 2048, "readback"),
+         ("Battaglia16.kSZ_T", Battaglia16.kSZ_T, cat, 2048, False),
          ("NFW.BG", NFW.BG, cat, 2048, False), ("NFW.kSZ_T inclusive", NFW.kSZ_T, cat, 1024, True),
          ("python template (host path)", py_template, small, 512, False)]
 for name, tmpl, c, nside, inclusive in CASES:
-    canvas = ap.Canvas(c, nside, R_times=5, inclusive=inclusive)
+    balance = "readback" if inclusive == "readback" else "area"
+    inclusive = inclusive is True
+    canvas = ap.Canvas(c, nside, R_times=5, inclusive=inclusive, band_balance=balance)
     p = ap.Painter(tmpl)
     p.spray(canvas)                                      # collective: this rank paints its band
     n_painted = torch.zeros(1, dtype=torch.int64, device="cuda") + p.last_spray["d_count"]
