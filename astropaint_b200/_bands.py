@@ -104,8 +104,12 @@ class Band:
 #: chunks end on a small one, and a ratio >= t_copy / t_compute keeps every earlier copy hidden
 #: (measured in round 1 on the 1e7-halo bench catalog: 10 chunks x 0.75 beat 8 equal chunks by 11 ms end to end).
 CHUNK_RATIO = 0.75
-MAX_CHUNKS = 10
+MAX_CHUNKS = 12
 MIN_CHUNK_HALOS = 50_000
+#: no chunk larger than this share: when the read-back is SLOWER than the painting (several ranks: the host ingests
+#: ~110 GB/s from eight GPUs) the copy engine idles until the first large chunk is painted, so the large chunks of the
+#: geometric series are split into equal ones (8-GPU trace: a 25% chunk kept the copy engine idle for 7 of 70 ms)
+MAX_CHUNK_SHARE = 0.12
 #: share of the first chunk when there are three or more: the halo columns go host->device chunk by chunk on
 #: their own stream, so painting starts as soon as this small lead chunk has arrived and every later upload hides
 #: behind the previous chunk's kernels
@@ -141,8 +145,16 @@ class Plan:
             n_chunks = max(1, min(MAX_CHUNKS, m // MIN_CHUNK_HALOS))
         ratio = CHUNK_RATIO if ratio is None else ratio
         if n_chunks >= 3:
-            f = np.power(float(ratio), np.arange(n_chunks - 1))
-            f = np.concatenate([[LEAD_FRACTION], (1.0 - LEAD_FRACTION) * f / f.sum()])
+            # lead chunk, equal body chunks of at most MAX_CHUNK_SHARE, then a tail shrinking by `ratio`
+            n_tail = min(n_chunks - 2, 5)
+            tail = MAX_CHUNK_SHARE * np.power(float(ratio), np.arange(1, n_tail + 1))
+            n_body = n_chunks - 1 - n_tail
+            body_total = 1.0 - LEAD_FRACTION - tail.sum()
+            if body_total <= 0 or body_total / n_body > 2.5 * MAX_CHUNK_SHARE:     # too few chunks for that shape
+                f = np.power(float(ratio), np.arange(n_chunks - 1))
+                f = np.concatenate([[LEAD_FRACTION], (1.0 - LEAD_FRACTION) * f / f.sum()])
+            else:
+                f = np.concatenate([[LEAD_FRACTION], np.full(n_body, body_total / n_body), tail])
         else:
             f = np.power(float(ratio), np.arange(n_chunks))
         cuts = lo + np.round(np.cumsum(f / f.sum()) * m).astype(np.int64)

@@ -27,7 +27,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 cat = ap.Catalog(synthetic.websky_like(n_halos, seed=1))
 cat.pin_memory()
-canvas = ap.Canvas(cat, 8192, R_times=5)
+canvas = ap.Canvas(cat, 8192, R_times=5, band_balance=os.environ.get("AP_BAND_BALANCE", "readback"))
 painter = ap.Painter(Battaglia16.kSZ_T)
 
 
