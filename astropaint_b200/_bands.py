@@ -104,11 +104,12 @@ class Band:
 #: chunks end on a small one, and a ratio >= t_copy / t_compute keeps every earlier copy hidden
 #: (measured in round 1 on the 1e7-halo bench catalog: 10 chunks x 0.75 beat 8 equal chunks by 11 ms end to end).
 CHUNK_RATIO = 0.75
-MAX_CHUNKS = 12
+MAX_CHUNKS = 10            # 12 with capped shares (several ranks)
 MIN_CHUNK_HALOS = 50_000
-#: no chunk larger than this share: when the read-back is SLOWER than the painting (several ranks: the host ingests
-#: ~110 GB/s from eight GPUs) the copy engine idles until the first large chunk is painted, so the large chunks of the
-#: geometric series are split into equal ones (8-GPU trace: a 25% chunk kept the copy engine idle for 7 of 70 ms)
+#: Several ranks: the read-back is SLOWER than the painting (the host ingests ~110 GB/s from eight GPUs), so the copy
+#: engine should start early and never idle: no chunk larger than this share -- the large chunks of the geometric series
+#: are split into equal ones (8-GPU trace: a 25% chunk kept the copy engine idle for 7 of 70 ms).  With one rank the
+#: painting is the slower side and the plain geometric series is 2 ms better end to end (fewer, larger launches).
 MAX_CHUNK_SHARE = 0.12
 #: share of the first chunk when there are three or more: the halo columns go host->device chunk by chunk on
 #: their own stream, so painting starts as soon as this small lead chunk has arrived and every later upload hides
@@ -141,10 +142,14 @@ class Plan:
                 hi = lo
         self.halo_lo, self.halo_hi = lo, hi
         m = hi - lo
+        capped = not band.whole
         if n_chunks is None:
-            n_chunks = max(1, min(MAX_CHUNKS, m // MIN_CHUNK_HALOS))
+            n_chunks = max(1, min(MAX_CHUNKS + (2 if capped else 0), m // MIN_CHUNK_HALOS))
         ratio = CHUNK_RATIO if ratio is None else ratio
-        if n_chunks >= 3:
+        if n_chunks >= 3 and not capped:
+            f = np.power(float(ratio), np.arange(n_chunks - 1))
+            f = np.concatenate([[LEAD_FRACTION], (1.0 - LEAD_FRACTION) * f / f.sum()])
+        elif n_chunks >= 3:
             # lead chunk, equal body chunks of at most MAX_CHUNK_SHARE, then a tail shrinking by `ratio`
             n_tail = min(n_chunks - 2, 5)
             tail = MAX_CHUNK_SHARE * np.power(float(ratio), np.arange(1, n_tail + 1))
