@@ -71,12 +71,44 @@ class Catalog:
         self.build_dataframe(calculate_redshifts=self.calculate_redshifts,
                              default_redshift=self.default_redshift, device=self.device_build)
 
+    @staticmethod
+    def _fingerprint(values):
+        """cheap identity of a column's contents (microseconds, checked on every spray): where the array lives, its
+        length and a CRC of ~2000 evenly spaced elements.  Catches a replaced column and bulk in-place edits
+        (`df["v_r"] *= 2`); NOT an edit of a few elements -- reassign `catalog.data` (or call pin_memory() again)
+        after such edits."""
+        import zlib
+        v = np.asarray(values)
+        step = max(1, v.shape[0] // 2048) if v.ndim else 1
+        return (v.__array_interface__["data"][0], v.shape, zlib.crc32(np.ascontiguousarray(v[::step]).tobytes()))
+
+    def _geometry_fingerprint(self):
+        d = self._data
+        return tuple(self._fingerprint(d[k].values) for k in ("x", "y", "z", "R_ang_200c"))
+
+    def staged(self, names):
+        """The page-locked staging of pin_memory() if it is still current for the columns `names` (stale columns are
+        staged again), else None."""
+        if not getattr(self, "_pinned", None):
+            return None
+        for k in names:
+            if k in self._pinned and self._pinned_fp.get(k) != self._fingerprint(self._data[k].values):
+                import torch
+                order = self.theta_order()[0]
+                self._pinned[k] = torch.from_numpy(
+                    np.ascontiguousarray(self._data[k].values[order], dtype=np.float64)).pin_memory()
+                self._pinned_fp[k] = self._fingerprint(self._data[k].values)
+        return self._pinned
+
     def theta_order(self):
         """(order, theta_sorted, r_ang_max): the catalog rows by increasing colatitude of the disc centre
         (formed from x, y, z exactly like hp.query_disc's centre, paint_bucket.py:1223-1225), that colatitude,
         and the largest R_ang_200c [arcmin].  The painting path walks the halos in this order: the halos that
         can touch one ring band of the map are then ONE contiguous slice (astropaint_b200/_bands.py), and
         consecutive halos write neighbouring rings.  Computed once per catalog, invalidated with `data`."""
+        if getattr(self, "_order", None) is not None and self._order_fp != self._geometry_fingerprint():
+            self._order = None           # x, y, z or R_ang_200c were edited in place: the order, reach and staging are stale
+            self._pinned = None
         if getattr(self, "_order", None) is None:
             d = self._data
             x, y, z = (d[k].values.astype(np.float64, copy=False) for k in ("x", "y", "z"))
@@ -84,6 +116,7 @@ class Catalog:
             order = np.argsort(key, kind="stable")
             r_ang_max = float(np.nanmax(d["R_ang_200c"].values)) if len(d) else 0.0
             self._order = (order, key[order], r_ang_max)
+            self._order_fp = self._geometry_fingerprint()
             self._reach = {}
         return self._order
 
@@ -109,6 +142,7 @@ class Catalog:
         order = self.theta_order()[0]
         self._pinned = {k: torch.from_numpy(np.ascontiguousarray(self._data[k].values[order], dtype=np.float64)).pin_memory()
                         for k in self._data.columns if np.issubdtype(self._data[k].dtype, np.number)}
+        self._pinned_fp = {k: self._fingerprint(self._data[k].values) for k in self._pinned}
         return self
 
     # ------------------------ sample data ------------------------
@@ -1054,7 +1088,8 @@ class Painter:
         plan = _bands.Plan(band, reach, n_chunks=None if host is not None else 1)
         lo, hi = plan.halo_lo, plan.halo_hi
         rows = order[lo:hi]
-        pinned = getattr(cat, "_pinned", None)
+        needed = list(eng.GEOMETRY_COLUMNS) + ["R_ang_200c"] + [a for a in self._catalog_cols]
+        pinned = cat.staged(needed)
         # a page-locked catalog painted in several chunks is uploaded chunk by chunk on its own stream
         piecewise = bool(pinned) and len(plan.chunks) > 1
         halos = eng.DeviceHalos(cat.data, canvas.R_times, dev, rows=rows, pinned=pinned,

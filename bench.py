@@ -283,7 +283,7 @@ def run_b200(args):
     order = cat.theta_order()[0]
     plan = _bands.Plan(band, cat.disc_reach(R_TIMES), n_chunks=1)
     lo, hi = plan.halo_lo, plan.halo_hi
-    halos = eng.DeviceHalos(cat.data, R_TIMES, dev, rows=order[lo:hi], pinned=cat._pinned, pinned_range=(lo, hi))
+    halos = eng.DeviceHalos(cat.data, R_TIMES, dev, rows=order[lo:hi], pinned=cat.staged([]), pinned_range=(lo, hi))
     cols = {k: halos.col(k) for k in ("R_200c", "M_200c", "redshift", "v_r")}
     T_cmb, c_kms, ns = Battaglia16.T_cmb, Battaglia16.c, 15
     npix = 12 * NSIDE * NSIDE

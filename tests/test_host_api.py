@@ -251,3 +251,25 @@ def test_fits_map_round_trip_and_layout(tmp_path):
         assert np.array_equal(fits_map.read_map(fn), m)
     with pytest.raises(ValueError):
         fits_map.write_map(str(tmp_path / "bad.fits"), np.zeros(13))
+
+
+def test_catalog_order_and_staging_follow_in_place_edits():
+    """The colatitude order, the disc reach and the page-locked staging are caches of catalog columns: an in-place
+    edit of the geometry (or of a staged column) must invalidate them, not be painted from stale copies."""
+    import astropaint_b200 as ap
+    from astropaint_b200 import synthetic
+    cat = ap.Catalog(synthetic.websky_like(5000, seed=2))
+    order0 = cat.theta_order()[0].copy()
+    reach0 = cat.disc_reach(5)[0].copy()
+    assert cat.theta_order()[0] is cat.theta_order()[0]                     # cached
+    cat.data["z"] = -cat.data["z"].values                                   # replaced column: mirror the sky
+    order1 = cat.theta_order()[0]
+    assert not np.array_equal(order0, order1)
+    assert not np.array_equal(reach0, cat.disc_reach(5)[0])
+    z = cat.data["z"].values
+    if z.flags.writeable:
+        z *= 0.5                                                            # in-place bulk edit of the same array
+        cat.theta_order()
+        assert cat._order_fp == cat._geometry_fingerprint()
+    fp = ap.Catalog._fingerprint(np.arange(1000.0))
+    assert fp != ap.Catalog._fingerprint(np.arange(1000.0) * 2)
