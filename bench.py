@@ -197,6 +197,35 @@ def load_peaks():
         return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
+def fp64_instr_per_eval_from_sass():
+    """fp64 instructions per integrand evaluation, counted in the SASS of the library that is actually loaded: the
+    largest loop of los_nodes_kernel<LOS_B16_TAU, FAST> is one trip of the Gauss-Kronrod rule = FOUR evaluations
+    (profiles/r2_sass_quadpack_trip.txt).  Returns (count, source); falls back to the committed count when cuobjdump
+    is not on the box."""
+    import re
+    import shutil
+    from astropaint_b200 import _capi
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        out = subprocess.run([exe, "-sass", "-fun", "_Z16los_nodes_kernelILi0ELi1EEvlPKdS1_S1_PK7double4iS1_PKiPd",
+                              _capi.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+        ins = [(int(m.group(1), 16), m.group(2)) for m in re.finditer(r"/\*([0-9a-f]{4,5})\*/\s+(.*?);", out)]
+        loops = []
+        for a, t in ins:
+            if "BRA" in t:
+                mm = re.search(r"0x([0-9a-f]+)", t)
+                if mm and int(mm.group(1), 16) < a:
+                    loops.append((a - int(mm.group(1), 16), int(mm.group(1), 16), a))
+        _, lo, hi = max(loops)
+        ops = [re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for a, t in ins if lo <= a <= hi]
+        n = sum(op in ("DFMA", "DMUL", "DADD") for op in ops)
+        if 100 < n < 400:
+            return n / 4.0, f"cuobjdump -sass of the loaded library: {n} DFMA/DMUL/DADD in the rule's {len(ops)}-instruction trip of 4 evaluations"
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return float(FP64_INSTR_PER_EVAL), "committed count (profiles/r2_sass_quadpack_trip.txt); cuobjdump unavailable"
+
+
 def measure_fp64_peak(dev):
     """thread-level fp64 instructions per second this GPU sustains (ap_fp64_peak, CUDA events, best of 3)"""
     import ctypes as C
@@ -360,13 +389,14 @@ def run_b200(args):
     fp64_peak = measure_fp64_peak(dev)
     nev = mean_neval(dev, halos, cols, nodes, n_nodes)
     n_quad = ns * n_big
-    fp64_instr = n_quad * nev * FP64_INSTR_PER_EVAL
+    per_eval, per_eval_src = fp64_instr_per_eval_from_sass() if rank == 0 else (float(FP64_INSTR_PER_EVAL), "")
+    fp64_instr = n_quad * nev * per_eval
     fp64_rate = fp64_instr / (phase_ms["los_nodes"] / 1e3)
     roofline_dominant = {"kernel": "los_nodes_kernel<b16_tau> (QUADPACK dqagie per (halo, node))", "bound": "fp64-pipe",
                          "achieved": fp64_rate, "peak": fp64_peak, "unit": "fp64 thread-instructions/s",
                          "frac": fp64_rate / fp64_peak, "launch_ms": phase_ms["los_nodes"],
                          "share_of_step": phase_ms["los_nodes"] / ms_step, "quadratures_per_launch": n_quad,
-                         "mean_neval": nev, "fp64_instr_per_eval": FP64_INSTR_PER_EVAL,
+                         "mean_neval": nev, "fp64_instr_per_eval": per_eval, "fp64_instr_per_eval_source": per_eval_src,
                          "peak_source": "ap_fp64_peak DFMA probe timed in this run (8 chains x 8 blocks x 256 threads per SM)",
                          "peak_tflops_fp64": 2 * fp64_peak / 1e12}
     del nodes, n_nodes, n_pix, rmin_t, rmax_t
