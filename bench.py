@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--halos", type=int, default=10_000_000, help="halos of the WHOLE catalog (BASELINE config 3: 1e7)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE config 3: ONE catalog of --halos halos over all ranks); weak: the catalog "
+                         "grows with the ranks (--halos per rank; every rank still owns one band of the one map)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-halos", type=int, default=400, help="halos of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -56,10 +59,14 @@ def parse():
     return ap.parse_args()
 
 
+def total_halos(args, n_gpus):
+    return args.halos * (n_gpus if args.scaling == "weak" else 1)
+
+
 def config(args, n_gpus):
-    return {"workload": f"BASELINE config 3: Websky-shaped synthetic full-sky catalog, {args.halos} halos in total, "
+    return {"workload": f"BASELINE config 3: Websky-shaped synthetic full-sky catalog, {total_halos(args, n_gpus)} halos in total, "
                         f"Battaglia16.kSZ_T (tau_2D_interp x v_r), nside {NSIDE}, R_times {R_TIMES}",
-            "halos_total": args.halos, "nside": NSIDE, "R_times": R_TIMES, "template": "Battaglia16.kSZ_T",
+            "halos_total": total_halos(args, n_gpus), "nside": NSIDE, "R_times": R_TIMES, "template": "Battaglia16.kSZ_T",
             "parallelism": f"ring-band ownership x{n_gpus}: each rank paints the halos touching its band of the map, "
                            "no partial maps, no reduction; bands copied to one shared host map over each GPU's own PCIe link",
             "catalog_staging": "Catalog.pin_memory(): columns page-locked in colatitude order, once per catalog, "
@@ -131,7 +138,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     value = pairs / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"first {n} halos of the workload catalog per step ({pairs} halo-pixels), oracle "
@@ -305,7 +312,8 @@ def run_b200(args):
 
     # ---- inputs: ONE catalog (same seed on every rank), staged once; this rank's slice resident in HBM ----
     t_stage = time.perf_counter()
-    cat = ap.Catalog(synthetic.websky_like(args.halos, seed=1))
+    n_total = total_halos(args, world)
+    cat = ap.Catalog(synthetic.websky_like(n_total, seed=1))
     cat.pin_memory()
     stage_s = time.perf_counter() - t_stage
     band = _bands.Band(NSIDE, rank, world)
@@ -378,7 +386,7 @@ def run_b200(args):
     if os.path.exists(traffic_file):
         try:
             tr = json.load(open(traffic_file))
-            if world == 1 and tr.get("halos") == args.halos:
+            if world == 1 and tr.get("halos") == n_total:
                 roofline["traffic"] = tr.get("paint_table_bytes_per_launch")
         except (OSError, ValueError):
             pass
@@ -402,9 +410,9 @@ def run_b200(args):
     del nodes, n_nodes, n_pix, rmin_t, rmax_t
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args, world),
-            "halo_pixels_per_step": pairs_all, "halos_per_s": args.halos / (ms_step / 1e3),
+            "halo_pixels_per_step": pairs_all, "halos_per_s": n_total / (ms_step / 1e3),
             "halos_painted_all_ranks": halos_painted, "phase_ms": phase_ms, "dominant_phase": dominant,
             "gpu_launches": launches_per_step * len(plan.chunks) * args.steps, "torch_elementwise_launches": 5 * args.steps,
             "map_checksum": checksum, "catalog_stage_s": stage_s,
