@@ -25,7 +25,7 @@ struct Hpx {
   // the map pointer handed to the kernel addresses pixel clip_pix0 (the first pixel of ring clip_lo) -- the
   // band of the map one rank owns.  Default: every ring, clip_pix0 = 0.
   int32_t clip_lo, clip_hi;
-  int64_t clip_pix0;
+  int64_t clip_pix0, clip_pix1;   // first pixel of ring clip_lo, first pixel past ring clip_hi - 1
 };
 
 AP_HD Hpx make_hpx(int64_t nside) {
@@ -42,6 +42,7 @@ AP_HD Hpx make_hpx(int64_t nside) {
   h.clip_lo = 1;
   h.clip_hi = (int32_t)(4 * nside);
   h.clip_pix0 = 0;
+  h.clip_pix1 = h.npix;
   return h;
 }
 

@@ -90,6 +90,8 @@ Hpx disc_hpx(int64_t nside) {
     bool shifted;
     if (h.clip_lo < top) ring_info(h, h.clip_lo, h.clip_pix0, nr, shifted);
     else h.clip_pix0 = h.npix;
+    if (h.clip_hi < top) ring_info(h, h.clip_hi, h.clip_pix1, nr, shifted);
+    else h.clip_pix1 = h.npix;
   }
   return h;
 }AP_TU_BOUNDS_GETTER(ap_bounds_core)

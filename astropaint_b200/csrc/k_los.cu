@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(128, 6) paint_los_items_kernel(Hpx hpx, HalosD
         los_setup<KIND>(p0[h], p1[h], p2 ? p2[h] : 0.0, ctx);
         double val = los_eval<KIND>(ctx, R) * (scale ? scale[h] : 1.0);
         const int64_t pix = s.startpix + (ip < 0 ? ip + s.nr : ip);
-        if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && pix >= hpx.clip_pix0 && pix < hpx.npix)) {
+        if (AP_BOUNDS_OK(ip + s.nr >= 0 && ip < s.nr && pix >= hpx.clip_pix0 && pix < hpx.clip_pix1)) {
           accumulate<EMIT>(hpx, em, map, pix, val, h);
           ++painted;
         }

@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
         v0 = eval(k, p0, g0);
         v1 = two ? eval(k + kPaintThreads, p1, g1) : 0.0;
       }
-      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.npix)) accumulate<EMIT>(hpx, em, map, p0, v0, h0 + g0);
-      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.npix)) accumulate<EMIT>(hpx, em, map, p1, v1, h0 + g1);
+      if (AP_BOUNDS_OK(p0 >= hpx.clip_pix0 && p0 < hpx.clip_pix1)) accumulate<EMIT>(hpx, em, map, p0, v0, h0 + g0);
+      if (two && AP_BOUNDS_OK(p1 >= hpx.clip_pix0 && p1 < hpx.clip_pix1)) accumulate<EMIT>(hpx, em, map, p1, v1, h0 + g1);
     }
     __syncthreads();
   }
