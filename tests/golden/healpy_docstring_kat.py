@@ -5,7 +5,8 @@ healpy.pixelfunc (ang2pix, pix2ang, pix2vec, vec2pix, ring2nest, max_pixrad, nsi
 ud_grade) -- they could not be re-fetched here.  Their evidential weight comes from agreement: the oracle
 (written independently from the HEALPix paper's ring-scheme formulas) reproduces all 28 integers and 40 floats,
 which neither a mis-remembered example nor a wrong restatement would do by chance.  They pin the RING pixel numbering, the pixel-centre convention, the RING<->NEST map that ud_grade
-goes through and ud_grade's averaging; they do not pin query_disc (its docstring has no numeric example).
+goes through and ud_grade's averaging.  query_disc has no numeric docstring example; its two known answers at the end
+of this file come from healpy's own TEST SUITE instead (see there).
 Floats are quoted as printed (8 decimals unless the docstring shows repr precision).
 """
 import numpy as np
@@ -32,3 +33,17 @@ NSIDE2RESOL_128_ARCMIN = 27.483891294539248
 NSIDE2PIXAREA_128 = 6.391586616190171e-05
 MAX_PIXRAD_16 = 0.0660147614                                        # '%.10f' % hp.max_pixrad(16)
 UD_GRADE_48_TO_1 = [5.5, 7.25, 9., 10.75, 21.75, 21.75, 23.75, 25.75, 36.5, 38.25, 40., 41.75]  # hp.ud_grade(np.arange(48.), 1)
+
+
+# ---- hp.query_disc: the two known answers of healpy's own test-suite, healpy/test/test_query_disc.py, class
+# TestQueryDisc (setUp: NSIDE = 8, vec = [0.17101007, 0.03015369, 0.98480775], radius = np.radians(6)):
+#   test_not_inclusive:  query_disc(NSIDE, vec, radius, inclusive=False) == [4]
+#   test_inclusive:      query_disc(NSIDE, vec, radius, inclusive=True)  == [0, 3, 4, 5, 11, 12, 13, 23]
+# (both annotated there with the output of the HEALPix IDL routine `query_disc, 8, vec, 6, listpix, /DEG, NESTED=0
+# [, /inclusive]`).  Restated FROM MEMORY like everything in this file (round 2): the oracle, written before these
+# vectors were recalled, reproduces the single pixel and the eight-pixel list exactly -- the only anchor of the disc
+# query (exclusive AND inclusive, fact = 4) to something the real healpy asserts.
+QUERY_DISC_TEST = dict(nside=8, vec=[0.17101007, 0.03015369, 0.98480775], radius_deg=6.0,
+                       exclusive=[4], inclusive=[0, 3, 4, 5, 11, 12, 13, 23])
+# healpy.rotator.angdist docstring: hp.rotator.angdist([.2, 0], [.2, 1e-6]) -> array([1.98669331e-07])
+ANGDIST_EXAMPLE = dict(dir1=[0.2, 0.0], dir2=[0.2, 1e-6], value=1.98669331e-07)

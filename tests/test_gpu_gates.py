@@ -262,3 +262,20 @@ def test_table_host_entry_and_pixel_ang_generator():
     for (theta, phi), pix in zip(canvas.discs.gen_pixel_ang(halo_list=[0, 5, 17]), canvas.discs.gen_pixel_index(halo_list=[0, 5, 17])):
         t, f = hp.pix2ang(pix)
         assert np.allclose(theta, t, rtol=0, atol=1e-14) and np.allclose(phi, f, rtol=0, atol=1e-14)
+
+
+def test_device_query_disc_reproduces_healpys_own_test_vectors():
+    """the CUDA disc query (exclusive and inclusive) on the two pixel lists healpy/test/test_query_disc.py asserts"""
+    import pandas as pd
+    import astropaint_b200 as ap
+    from .golden import healpy_docstring_kat as K
+    q = K.QUERY_DISC_TEST
+    v = np.array(q["vec"]) * 100.0                       # 100 Mpc away in that direction
+    cat = ap.Catalog(pd.DataFrame({"x": [v[0]], "y": [v[1]], "z": [v[2]], "v_x": [0.0], "v_y": [0.0], "v_z": [0.0],
+                                   "M_200c": [1e14]}))
+    # R_times such that R_times * arcmin2rad(R_ang_200c) is the test's radius of 6 degrees
+    R_times = q["radius_deg"] * 60.0 / float(cat.data["R_ang_200c"].values[0])
+    for inclusive, want in ((False, q["exclusive"]), (True, q["inclusive"])):
+        canvas = ap.Canvas(cat, q["nside"], R_times=R_times, inclusive=inclusive)
+        got = next(canvas.discs.gen_pixel_index())
+        assert got.tolist() == want, (inclusive, got)

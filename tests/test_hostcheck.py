@@ -423,3 +423,15 @@ def test_ang2pix_pix2ang_bit_exact(hc, nside):
     hc.hc_ang2pix(nside, allp.size, _p(th), _p(ph), _p(back))
     assert np.array_equal(back, allp)
 
+
+
+def test_device_header_reproduces_healpys_query_disc_test_vectors(hc):
+    """healpix.cuh (host build of the device code) on the two pixel lists healpy's own test-suite asserts"""
+    from .golden import healpy_docstring_kat as K
+    q = K.QUERY_DISC_TEST
+    r = float(np.radians(q["radius_deg"]))
+    out = np.zeros(64, dtype=np.int64)
+    n = hc.hc_query_disc(q["nside"], *q["vec"], r, out.ctypes.data, 64)
+    assert out[:n].tolist() == q["exclusive"]
+    n = hc.hc_query_disc_inclusive(q["nside"], *q["vec"], r, 4, out.ctypes.data, 64)
+    assert out[:n].tolist() == q["inclusive"]

@@ -389,3 +389,22 @@ def test_two_independent_statements_of_query_disc_agree():
     for nside, seed, i, tag, p, margin in log:
         assert margin is not None and abs(margin) < 1e-13, (nside, seed, i, tag, p, margin)
     assert len(log) <= 5
+
+
+def test_query_disc_reproduces_healpys_own_test_vectors():
+    """healpy/test/test_query_disc.py asserts two pixel lists (tests/golden/healpy_docstring_kat.py::QUERY_DISC_TEST):
+    both statements of the exclusive query and the inclusive query (fact 4, healpy's default) reproduce them; angdist
+    reproduces its docstring example."""
+    from .golden import healpy_docstring_kat as K
+    from oracle.query_disc_ineq import DiscByInequality
+    q = K.QUERY_DISC_TEST
+    hp = H.HealpixRing(q["nside"])
+    r = np.radians(q["radius_deg"])
+    assert hp.query_disc(q["vec"], r).tolist() == q["exclusive"]
+    assert DiscByInequality(q["nside"]).query(q["vec"], r).tolist() == q["exclusive"]
+    assert hp.query_disc(q["vec"], r, inclusive=True).tolist() == q["inclusive"]
+    a = K.ANGDIST_EXAMPLE
+    v1 = np.array([np.sin(a["dir1"][0]) * np.cos(a["dir1"][1]), np.sin(a["dir1"][0]) * np.sin(a["dir1"][1]), np.cos(a["dir1"][0])])
+    v2 = np.array([np.sin(a["dir2"][0]) * np.cos(a["dir2"][1]), np.sin(a["dir2"][0]) * np.sin(a["dir2"][1]), np.cos(a["dir2"][0])])
+    d = np.arctan2(np.linalg.norm(np.cross(v1, v2)), np.dot(v1, v2))
+    assert abs(d - a["value"]) < 5e-16
