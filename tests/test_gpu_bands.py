@@ -201,3 +201,25 @@ def test_deterministic_accumulation_is_bit_reproducible(band_cats):
         assert np.array_equal(np.concatenate(parts), maps[0])      # same pixels, same values, same order of addition
     with pytest.raises(NotImplementedError):
         ap.Painter(lambda R, R_200c: np.exp(-R / R_200c)).spray(ap.Canvas(band_cats["websky_big"], 256, deterministic=True))
+
+
+def test_map_file_round_trip_through_the_canvas(tmp_path, band_cats):
+    """Canvas.save_map_to_file / load_map_from_file (paint_bucket.py:1478-1558): the painted map written in healpy's
+    FITS layout (float32, as hp.write_map's default) and read back into a second canvas, which keeps painting on it."""
+    import astropaint_b200 as ap
+    from astropaint_b200.profiles import NFW
+    cat = band_cats["websky"]
+    canvas = ap.Canvas(cat, 256, R_times=5)
+    ap.Painter(NFW.kSZ_T).spray(canvas)
+    painted = canvas.pixels.copy()
+    fn = str(tmp_path / "ksz.fits")
+    canvas.save_map_to_file(filename=fn)
+    default_name = canvas._map_filename(None, "run1", "v2")
+    assert default_name == "run1_kSZ_T_NSIDE=256_v2.fits"
+    other = ap.Canvas(cat, 256, R_times=5)
+    other.load_map_from_file(filename=fn)
+    assert np.array_equal(other.pixels, painted.astype(np.float32).astype(np.float64))
+    assert other._alm_is_outdated and other._state == "host"
+    ap.Painter(NFW.kSZ_T).spray(other)                      # additive on the loaded map
+    map_close(other.pixels, painted.astype(np.float32).astype(np.float64) + painted, 1e-7)
+    assert np.array_equal(canvas.load_map_from_file(filename=fn, inplace=False), painted.astype(np.float32).astype(np.float64))
