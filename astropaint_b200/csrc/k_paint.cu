@@ -106,6 +106,7 @@ static int paint_table_impl(int64_t nside, const ap_halos* halos, int32_t n_samp
   TableArgs tab;
   tab.nodes = d_nodes; tab.coef = d_coef; tab.n_nodes = d_n_nodes; tab.scale = d_scale; tab.n_samples = n_samples;
   tab.uniform = uniform_nodes ? 1 : 0;
+  tab.stage = (n_samples <= kStageMaxNodes && (reinterpret_cast<uintptr_t>(d_coef) & 15) == 0) ? 1 : 0;
   return launch_paint<P_TABLE>(nside, halos, pp, tab, d_map, d_n_painted, stream, nullptr, f32);
 }
 extern "C" int ap_paint_table(int64_t nside, const ap_halos* halos, int32_t n_samples, int32_t uniform_nodes,

@@ -20,6 +20,35 @@ constexpr int kStageMaxNodes = 15;
 constexpr int P_TABLE = 100;   // tabulated template (spline of per-halo nodes)
 constexpr int P_STATS = 101;   // no painting: per-halo pixel count and R range (K1)
 
+// 1-D bulk copy (TMA, cp.async.bulk) global -> shared completing on an mbarrier: the spline coefficients of the halos
+// a chunk touches are ONE contiguous run in HBM, so one elected thread moves them while the block computes ring spans
+// (round 1 staged them through registers: a binary search, 7 LDG and 7 STS per thread and chunk, 13% of K3's stall
+// samples in the ncu source page)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous chunk's generic-proxy reads of the buffer
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
 struct ParamPtrs {
   const double* p[kMaxParams];
   int32_t stride[kMaxParams];
@@ -33,6 +62,7 @@ struct TableArgs {
   const double* scale;
   int32_t n_samples;
   int32_t uniform;  // nodes are linspace: interval index by multiplication
+  int32_t stage;    // coefficients may be staged with bulk copies (n_samples <= 15, 16-byte aligned d_coef)
 };
 
 struct StatsArgs {
@@ -79,7 +109,9 @@ struct PaintShared {
   int32_t warp_sum[kPaintThreads / 32];
   int32_t hint[kHintMax];  // hint[g] = ring item holding pixel 32 g of the current chunk
   uint8_t pixmap[P == P_STATS ? 1 : kPixMapMax];  // ring item of each of the first 4 Ki pixels
-  double stage[P == P_TABLE ? kStageHalos * (kStageMaxNodes - 1) * 4 : 1];
+  __align__(16) double stage[P == P_TABLE ? kStageHalos * (kStageMaxNodes - 1) * 4 : 2];
+  unsigned long long stage_bar;       // mbarrier of the bulk copy into `stage`
+  int32_t stage_lo, stage_ok;         // first staged halo of the chunk; every halo of the chunk is staged
   // P_STATS accumulators
   unsigned long long cnt[P == P_STATS ? MAXH : 1];
   unsigned long long hmin[P == P_STATS ? MAXH : 1], hmax[P == P_STATS ? MAXH : 1];
@@ -161,6 +193,7 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
       profile_setup<P>(p, sm.ctx[tid]);
     }
   }
+  if (P == P_TABLE && tid == 0) mbar_init(&sm.stage_bar, 1);
   __syncthreads();
   // exclusive scan of the halos' ring counts (G <= 112: four warps): warp scans, then the warp totals
   int32_t ring_incl = 0;
@@ -188,32 +221,30 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
   __syncthreads();
   const int32_t T = sm.ring_off[G];
   unsigned long long painted = 0;
+  uint32_t stage_phase = 0;
 
   // gridDim.y blocks share the halos of blockIdx.x: block y takes every gridDim.y-th chunk of 256 ring items, so a
   // catalog of few, sky-sized discs (BASELINE config 1) is not serialised on the block that owns the largest disc
   for (int32_t base = (int32_t)blockIdx.y * kPaintThreads; base < T; base += kPaintThreads * (int32_t)gridDim.y) {
-    // P_TABLE: the spline coefficients of the halos this chunk touches are one contiguous run in HBM;
-    // start streaming the first kStageHalos of them now (coalesced), park them in shared memory after
-    // phase 1 so that phase 2 never waits on a dependent global load
-    constexpr int kStageRegs = (P == P_TABLE) ? (kStageHalos * (kStageMaxNodes - 1) * 4 + kPaintThreads - 1) / kPaintThreads : 1;
-    double stage_reg[kStageRegs];
-    int stage_lo = 0, stage_n = 0;
-    const bool do_stage = (P == P_TABLE) && tab.n_samples <= kStageMaxNodes;
-    if (do_stage) {
-      int lo = 0, hi = G;
+    // P_TABLE: the spline coefficients of the halos this chunk touches are one contiguous run in HBM: one thread
+    // starts a bulk copy of the first kStageHalos of them into shared memory now; it lands while phase 1 runs
+    const bool do_stage = (P == P_TABLE) && tab.stage != 0;
+    if (do_stage && tid == 0) {
+      int lo = 0, hi = G;   // halo of the chunk's first ring item
       while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (sm.ring_off[mid] <= base) lo = mid; else hi = mid;
       }
-      stage_lo = lo;
-      const int nc = (tab.n_samples - 1) * 4;
-      stage_n = min(kStageHalos, G - lo) * nc;
-      const double* src = tab.coef + (h0 + lo) * (int64_t)nc;
-#pragma unroll
-      for (int q = 0; q < kStageRegs; ++q) {
-        int e = tid + q * kPaintThreads;
-        stage_reg[q] = (e < stage_n) ? __ldg(src + e) : 0.0;
+      const int32_t last_it = min(base + kPaintThreads, T) - 1;
+      int lo2 = lo, hi2 = G;  // halo of its last ring item
+      while (hi2 - lo2 > 1) {
+        int mid = (lo2 + hi2) >> 1;
+        if (sm.ring_off[mid] <= last_it) lo2 = mid; else hi2 = mid;
       }
+      sm.stage_lo = lo;
+      sm.stage_ok = (lo2 - lo) < kStageHalos;
+      const int nc = (tab.n_samples - 1) * 4;
+      bulk_copy_g2s(sm.stage, tab.coef + (h0 + lo) * (int64_t)nc, (uint32_t)(min(kStageHalos, G - lo) * nc * 8), &sm.stage_bar);
     }
 
     // phase 1: one ring item per thread
@@ -253,7 +284,7 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
           if (VEC) { sm.itemv[tid].phi0 = g.phi0; sm.itemv[tid].z = g.z; sm.itemv[tid].sth = g.sth; }
           const double dmax = fmax(fabs(g.d0), fabs(g.d0 + (double)(s.len - 1) * g.phi_step));
           small_ok = small_ok && dmax < 0.25 && (g.A + g.B * (0.25 * dmax * dmax)) < 1.0e-4;   // sin^2(x) <= x^2
-          if (P == P_TABLE) small_ok = small_ok && do_stage && tab.uniform && (lo - stage_lo) < kStageHalos;
+          if (P == P_TABLE) small_ok = small_ok && do_stage && tab.uniform;
         }
       }
       if (STATS && len > 0) atomicAdd(&sm.cnt[lo], (unsigned long long)len);
@@ -281,15 +312,16 @@ __global__ void __launch_bounds__(kPaintThreads, paint_min_blocks<P>()) paint_ke
       for (int32_t m = (start + 31) & ~31; m < end && (m >> 5) < kHintMax; m += 32) sm.hint[m >> 5] = tid;
       const int32_t mend = min(end, (int32_t)kPixMapMax);
       for (int32_t m = start; m < mend; ++m) sm.pixmap[m] = (uint8_t)tid;
-      if (do_stage) {
-#pragma unroll
-        for (int q = 0; q < kStageRegs; ++q) {
-          int e = tid + q * kPaintThreads;
-          if (e < stage_n) sm.stage[e] = stage_reg[q];
-        }
-      }
     }
+    // (the barrier inside the scan above made thread 0's stage_lo / stage_ok visible)
+    const int stage_lo = do_stage ? sm.stage_lo : 0;
+    const int stage_n = do_stage ? min(kStageHalos, G - stage_lo) * (tab.n_samples - 1) * 4 : 0;
+    if (P == P_TABLE) small_ok = small_ok && (!do_stage || sm.stage_ok != 0);
     const bool all_small = __syncthreads_and(small_ok ? 1 : 0) != 0;
+    if (do_stage) {   // the coefficients have landed (phase flips every chunk)
+      mbar_wait(&sm.stage_bar, stage_phase);
+      stage_phase ^= 1u;
+    }
     const int32_t total = sm.pix_off[kPaintThreads];
     painted += (tid == 0) ? (unsigned long long)total : 0ull;
     const bool fastp = !VEC && all_small && total <= kPixMapMax;
