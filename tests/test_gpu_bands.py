@@ -50,6 +50,7 @@ CASES = [
     ("b16_tau_bypass", "websky", 512, 5, "Battaglia16.tau_2D_interp", 5),     # most discs < 15 pixels: bypass list
     ("gaussian_sky_discs", "box", 128, 5, "spherical.gaussian_2D", 8),        # polar caps, sky-sized discs
     ("nfw_rho_logspace", "websky_big", 1024, 5, "NFW.rho_2D_interp", 2),
+    ("nside_not_a_power_of_two", "box", 96, 2, "NFW.kSZ_T", 5),
 ]
 
 
