@@ -49,10 +49,10 @@ extern "C" int ap_table_nodes(int64_t n, const int64_t* d_n_pix, const double* d
 // 6 blocks of 128 threads per SM (80 registers, 24 warps).  Round 1 (per-thread los_setup inside the kernel) measured
 // 176.1 / 173.5 / 180.9 / 182.9 ms per 1e7 halos at 7 / 6 / 5 / 4 blocks (72 / 80 / 96 / 128 registers).  Round 2, with
 // the per-halo constants in their own kernel: timed ALONE for 30 ms bursts the 64-register build wins (135.8 ms at 8
-// blocks against 138.7 at 6, 137.3 at 9, 136.6 at 10, 135.6 as 4 blocks of 256; gpurun_out/r2_variants*.log), but in the
+// blocks against 138.7 at 6, 137.3 at 9, 136.6 at 10, 135.6 as 4 blocks of 256; profiles/r2_runs/r2_variants*.log), but in the
 // sustained step its 32 warps per SM draw enough power for the 1 kW cap to pull the SM clock from 1965 to ~1870 MHz
 // (nvidia-smi: sw_power_cap active) and it LOSES: 141.3 ms against 138.5 ms, same box, back to back, twice
-// (gpurun_out/r2_mb_ab.log).  (A pure-DFMA probe holds 1965 MHz for seconds, so it is the kernel's memory-side activity --
+// (profiles/r2_runs/r2_mb_ab.log).  (A pure-DFMA probe holds 1965 MHz for seconds, so it is the kernel's memory-side activity --
 // table look-ups, local-memory frames, register-file traffic of 32 warps -- that costs the power, not the fp64 pipe.)
 #ifndef AP_QAGI_THREADS
 #define AP_QAGI_THREADS 128
