@@ -273,3 +273,17 @@ def test_catalog_order_and_staging_follow_in_place_edits():
         assert cat._order_fp == cat._geometry_fingerprint()
     fp = ap.Catalog._fingerprint(np.arange(1000.0))
     assert fp != ap.Catalog._fingerprint(np.arange(1000.0) * 2)
+
+
+def test_redshift_table_inversion_equals_root_finding():
+    """Catalog(calculate_redshifts=True): the table inversion of D_c(z) used for catalogs agrees with the per-halo root
+    finder (the reference's z_at_value, lib/transform.py:116-119) far inside any tolerance of the path."""
+    from astropaint_b200.lib.cosmology import cosmo
+    rng = np.random.default_rng(1)
+    D = np.concatenate([rng.uniform(1.0, 9000.0, 40), [0.5, 150.0, 7734.0]])
+    table = cosmo.z_at_comoving_distance(D)                       # > 32 values: table path
+    exact = np.array([cosmo.z_at_comoving_distance(float(d)) for d in D[:12]])
+    assert np.abs(table[:12] - exact).max() < 1e-9
+    assert np.all(np.diff(cosmo.z_at_comoving_distance(np.linspace(1, 9000, 100))) > 0)
+    back = np.array([cosmo.comoving_distance(float(zz)) for zz in table[:8]])
+    assert np.abs(back - D[:8]).max() < 1e-6 * D[:8].max()
